@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- point clouds/s of the fused diffusion-head + flow-match Euler sampling path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4] [--impl reference]
+
+One "step" = one full sampling pass (S = 25 Euler steps of the depth-6 head) over one batch of
+B clouds x N point tokens of synthetic input.  Default workload = BASELINE.json configs[1]
+(NOVA-0.3B head d6w768, 2048 points, bf16; B = 32 clouds per GPU => 65 536 rows per head call).
+N > 1: one process per GPU (torchrun), the batch of clouds is sharded data-parallel (weak scaling:
+B clouds per GPU), no collective inside the denoise loop, ONE all-gather of the generated points
+inside the timed region.
+
+Printed JSON (one line, rank 0):
+  value / ms_per_step : device-resident inputs, CUDA events on the launching stream, max over ranks
+  e2e                 : same metric through the public API with pinned HOST buffers; H2D of the
+                        noise + condition and D2H of the points inside the timed region
+  roofline            : bound = tensor; achieved = algorithmic FLOP per step (BASELINE.md section 3:
+                        F_min*B*N*S + 4*D^2*B*N, hoisted work not credited) / step time; peak =
+                        MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)
+  gemm                : the dominant kernel (tcgen05 GEMM, AdaLN shape M x 20D x D) timed alone
+  cpu_baseline        : the CPU oracle (port of the reference's torch code) on a bounded sample
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, points, clouds per GPU, dtype)
+    "cfg2": dict(width=768, points=2048, batch=32, desc="NOVA-0.3B d48w768 head mlp_d6w768, 2048 points, bf16"),
+    "cfg3": dict(width=1024, points=1024, batch=64, desc="NOVA-0.6B d48w1024 head mlp_d6w1024, 1024 points, bf16"),
+    "cfg3-2048": dict(width=1024, points=2048, batch=32, desc="NOVA-0.6B head mlp_d6w1024, 2048 points, bf16"),
+    "cfg4": dict(width=1536, points=2048, batch=32, desc="NOVA-1.4B d48w1536 head mlp_d6w1536, 2048 points, bf16"),
+}
+S_STEPS = 25
+DEPTH = 6
+T = 3
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=float(p["bf16_tflops"]), sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    hbm=float(p["hbm_gbs"]), source="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def algorithmic_flops(D, rows, steps=S_STEPS):
+    """per token-step 2*(32 D^2 + 2 T D), plus 4 D^2 once per token (hoisted cond)."""
+    return rows * (steps * 2.0 * (32 * D * D + 2 * T * D) + 4.0 * D * D)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def cpu_baseline_run(width, points, sample_clouds, threads, repeats=1):
+    """Time the CPU oracle (port of the reference's DiffusionMLP + scheduler loop, fp32) on a bounded sample."""
+    from oracle import head as OH
+    from oracle import loop as OL
+
+    torch.set_num_threads(threads)
+    sd = OH.init_state_dict(DEPTH, width, width, 1, 3, seed=1337)
+    g = torch.Generator().manual_seed(2024)
+    noise = torch.randn(sample_clouds, 3, points, 1, generator=g)
+    z = torch.randn(sample_clouds, points, width, generator=g)
+    with torch.no_grad():
+        OL.denoise(sd, z[:1, :64], noise[:1, :, :64], num_steps=2)  # warm the thread pool
+        best = float("inf")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            OL.denoise(sd, z, noise, num_steps=S_STEPS)
+            best = min(best, time.perf_counter() - t0)
+    return sample_clouds / best, best
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's own algorithm on the host cores (oracle port: the reference is
+    Python/torch and cannot travel to the GPU box; oracle/ restates it call for call)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_clouds = 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, secs = cpu_baseline_run(wl["width"], wl["points"], sample_clouds, threads)
+        if i >= args.warmup:
+            vals.append((v, secs))
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(s for _, s in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "point_clouds_per_sec", "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "points": wl["points"], "width": wl["width"],
+                   "diffusion_steps": S_STEPS, "clouds_per_step": sample_clouds},
+        "head_tokens_per_s": value * wl["points"],
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_clouds} cloud x {wl['points']} tokens x {S_STEPS} steps per step, fp32, "
+                                   f"oracle/loop.py denoise (reference algorithm, condition projection not hoisted)"},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default: workload's)")
+    ap.add_argument("--impl", default="nova", choices=["nova", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+
+    import nova_pointcloud_b200 as nb
+    from nova_pointcloud_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    D, N, B = wl["width"], wl["points"], wl["batch"]
+    total = B * world
+    head = nb.synth.make_head(D, DEPTH, dtype=torch.bfloat16, device=dev)
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(S_STEPS)
+    # per-rank shard of the synthetic batch (seed offset by rank), pinned host copies for the e2e leg
+    noise_h, z_h = nb.synth.make_inputs(B, N, D, seed=2024 + rank, dtype=torch.bfloat16, pin=True)
+    noise_d, z_d = noise_h.to(dev), z_h.to(dev)
+    out_h = torch.empty(total, N, T, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        local = nb.denoise(head, sched, z_d, noise_d)
+        return nb.gather_shards(local, total)
+
+    def step_e2e():
+        n_d = noise_h.to(dev, non_blocking=True)
+        zz = z_h.to(dev, non_blocking=True)
+        local = nb.denoise(head, sched, zz, n_d)
+        full = nb.gather_shards(local, total)
+        out_h.copy_(full, non_blocking=True)
+        return full
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ops.launch_count_reset()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1) / steps
+        launches = ops.launch_count()
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    ms, launches, clocks = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    value = total / (ms * 1e-3)
+    e2e_value = total / (ms_e2e * 1e-3)
+
+    # dominant kernel alone: the AdaLN GEMM (M x 20D x D) on the tcgen05 kernel
+    pk = peaks()
+    gemm = None
+    try:
+        M = B * N
+        A = torch.randn(M, D, device=dev).bfloat16()
+        W = (torch.randn(20 * D, D, device=dev) / D**0.5).bfloat16()
+        bias = torch.zeros(20 * D, device=dev)
+        for _ in range(2):
+            ops.debug_gemm(A, W, bias, "tcgen05", "bias")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            ops.debug_gemm(A, W, bias, "tcgen05", "bias")
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / reps
+        tf = 2.0 * M * 20 * D * D / (gms * 1e-3) / 1e12
+        gemm = {"kernel": "nova::tc::gemm_kernel (tcgen05, M x 20D x D, bias epilogue)", "M": M, "N": 20 * D, "K": D,
+                "ms": gms, "achieved": tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": tf / pk["burst"],
+                "peak_source": pk["source"] + " burst (kernel timed alone)"}
+        del A, W, bias
+    except Exception as e:  # report, never hide
+        gemm = {"error": str(e)[:300]}
+
+    if rank == 0:
+        flops = algorithmic_flops(D, B * N)  # per GPU per step
+        achieved = flops / (ms * 1e-3) / 1e12
+        line = {
+            "metric": "point_clouds_per_sec", "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "points": N, "width": D, "depth": DEPTH,
+                       "diffusion_steps": S_STEPS, "clouds_per_gpu": B, "rows_per_head_call": B * N,
+                       "parallelism": f"dp{world} (clouds sharded, one all-gather of outputs)",
+                       "l2": "inputs larger than L2: per-step activations 6 x M x D x 2 B = "
+                             f"{6 * B * N * D * 2 / 1e6:.0f} MB + AdaLN stats {B * N * 20 * D * 2 / 1e6:.0f} MB stream through HBM"},
+            "head_tokens_per_s": value * N,
+            "token_steps_per_s": value * N * S_STEPS,
+            "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(noise_h.numel() * 4 + z_h.numel() * 2) * world,
+                    "d2h_bytes_per_step": int(out_h.numel() * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["sustained"], "traffic": None,
+                         "what": "whole sampling step per GPU: algorithmic FLOP (BASELINE.md section 3) / device time",
+                         "peak_source": pk["source"] + " sustained bf16 (timed inside a long step)",
+                         "frac_of_burst": achieved / pk["burst"]},
+            "gemm": gemm,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            sample_clouds = 1
+            v, secs = cpu_baseline_run(D, N, sample_clouds, threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "clouds/s", "cores": threads, "kind": "port", "seconds": secs,
+                "sample": f"{sample_clouds} cloud x {N} tokens x {S_STEPS} steps, fp32, oracle/loop.py denoise "
+                          "(the reference's algorithm, condition projection not hoisted)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+/*
+ * nova_b200.h -- C ABI of libnova_b200.so: the B200 (sm_100a) implementation of
+ * NOVA_pointcloud's per-token diffusion-head sampling path and Chamfer scorer.
+ *
+ * The reference (zailaiyiwan123/NOVA_pointcloud) is pure Python and has no FFI; the
+ * entry points below are what a binding for this path replaces, one by one:
+ *
+ *   nova_head_create/load/destroy  DiffusionMLP.__init__ + load_state_dict
+ *                                  (diffnext/models/diffusion_mlp.py:81-87; key set SURVEY.md A.2)
+ *   nova_head_forward              DiffusionMLP.forward(x, timestep, z, pred_ids)
+ *                                  (diffnext/models/diffusion_mlp.py:89-99)
+ *   nova_head_sample               Transformer3DModel.denoise: the S-step loop of
+ *                                  head -> GuidanceScaler.scale -> FlowMatchEuler step
+ *                                  (diffnext/models/transformers/transformer_3d.py:102-113,
+ *                                   diffnext/models/guidance_scaler.py:46-87,
+ *                                   diffnext/schedulers/scheduling_cfm.py:125-140)
+ *   nova_euler_step                FlowMatchEulerDiscreteScheduler.step
+ *                                  (diffnext/schedulers/scheduling_cfm.py:134-137)
+ *   nova_chamfer_nn                the nearest-neighbour primitive under chamfer_distance
+ *                                  (demo.py:38-55), distChamfer (train_newloss.py:316-349) and
+ *                                  compute_chamfer_distance (test_optimize.py:354-383)
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NOVA_ERR_* otherwise;
+ *     nova_last_error() returns a thread-local message for the last failure.
+ *   - no exceptions, no CPU fallback, no hidden device allocation except the packed
+ *     weights owned by a head handle; scratch space is a caller-provided workspace.
+ *   - all data pointers are DEVICE pointers unless a parameter says "host";
+ *     tensors are row-major and contiguous; `stream` is a cudaStream_t passed as void*.
+ *   - no call synchronises the device; errors from asynchronous work surface on the
+ *     caller's next synchronisation, as with any CUDA launch.
+ *   - a head handle is immutable after nova_head_load: concurrent calls on different
+ *     streams with different workspaces are safe.
+ *   - token layout: one row per token, T = C*p*p values ordered (p_h, p_w, C) with the
+ *     channel fastest, exactly PatchEmbed.patchify (diffnext/models/embeddings.py:152-154).
+ */
+#ifndef NOVA_B200_H_
+#define NOVA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOVA_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NOVA_API __attribute__((visibility("default")))
+#else
+#define NOVA_API
+#endif
+
+enum nova_status {
+  NOVA_OK = 0,
+  NOVA_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  NOVA_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
+  NOVA_ERR_WORKSPACE = -3,   /* workspace too small */
+  NOVA_ERR_NOT_LOADED = -4,  /* weights missing */
+  NOVA_ERR_DEVICE = -5       /* not an sm_100 device */
+};
+
+enum nova_dtype {
+  NOVA_F32 = 0,  /* SIMT fp32 arithmetic: the <=1e-5 parity mode */
+  NOVA_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: the fast path */
+};
+
+typedef struct nova_head nova_head_t; /* opaque */
+
+typedef struct nova_head_config {
+  int32_t depth;      /* residual blocks (6 for mlp_d6w*, 3 for mlp_d3w1280) */
+  int32_t width;      /* D, head width; multiple of 256, <= 2048 */
+  int32_t cond_width; /* Dc, width of the condition z; multiple of 64 */
+  int32_t token_dim;  /* T = C*p*p (3 for xyz points, 16 for the registry default); <= 64 */
+  int32_t dtype;      /* nova_dtype: arithmetic type of the handle */
+} nova_head_config;
+
+/* guidance for nova_head_sample (GuidanceScaler two-pass form) */
+typedef struct nova_guidance {
+  float scale;  /* <= 1: off. > 1: z holds [cond; uncond] (2x rows), v = vu + (vc - vu)*scale */
+  float trunc;  /* > 0: guidance is switched off once timestep < trunc (guidance_scaler.py:59-65) */
+  float renorm; /* < 1: v *= clamp(|vc| / |v|, renorm, 1), norms per cloud (guidance_scaler.py:67-72) */
+} nova_guidance;
+
+NOVA_API const char* nova_last_error(void);
+NOVA_API int nova_abi_version(void);
+/* 0 if the current device can run this library (compute capability 10.x), else NOVA_ERR_DEVICE. */
+NOVA_API int nova_device_check(void);
+
+NOVA_API int nova_head_create(const nova_head_config* cfg, nova_head_t** out);
+NOVA_API int nova_head_destroy(nova_head_t* h);
+NOVA_API int nova_head_get_config(const nova_head_t* h, nova_head_config* out);
+
+/*
+ * Load weights given in the reference's state_dict naming and shapes:
+ * nn.Linear weights are (out,in); patch_embed.proj.weight is (D,C,p,p) and is permuted
+ * to token order here; the 7 AdaLN projections are concatenated into one (20D,D) operand.
+ * `src_dtype` (nova_dtype) is the element type of every array; `ptrs` are DEVICE pointers.
+ * All 14 + 8*depth keys must be present; patch size p is taken as sqrt(T / C) from shapes.
+ */
+NOVA_API int nova_head_load(nova_head_t* h, int32_t n, const char* const* names, const void* const* ptrs,
+                   const int64_t* numels, int32_t src_dtype, int32_t channels, void* stream);
+
+/* Bytes of scratch needed for a call over `rows` head rows (M' = guidance passes x tokens). */
+NOVA_API size_t nova_head_workspace_bytes(const nova_head_t* h, int64_t rows, int32_t num_steps);
+
+/*
+ * One velocity prediction.
+ *   x_tok   [Bx, N, T] fp32   token-layout latent (Bx = B, or B/2 when rows pair up for guidance)
+ *   t       [B] or [B, n] fp32 timesteps (t_per_token != 0 selects the per-token form)
+ *   z       [B, N, Dc]        condition, element type = handle dtype
+ *   pred_ids[B, n] int64 or NULL; NULL means every token (n == N)
+ *   v_out   [B, n, T] fp32    velocity of the selected tokens (compact; the caller scatters)
+ */
+NOVA_API int nova_head_forward(const nova_head_t* h, const float* x_tok, const float* t, int32_t t_per_token,
+                      const void* z, const int64_t* pred_ids, int64_t B, int64_t Bx, int64_t N, int64_t n,
+                      float* v_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The fused sampling loop (denoise): S Euler steps of the head with the condition
+ * projection hoisted out of the loop and the latent kept in fp32.
+ *   noise_tok [Bx, N, T] fp32   initial latent, token layout
+ *   z         [B, N, Dc]        B = Bx (no guidance) or 2*Bx ([cond; uncond])
+ *   pred_ids  [B, n] int64 or NULL (rows of the second half must repeat the first half)
+ *   timesteps [S] host fp32, sigmas [S+1] host fp64  (the scheduler's own values)
+ *   x_out     [Bx, N, T] fp32   patchify(x_S).  Tokens outside pred_ids follow the
+ *                               reference's x <- x + dt*x recurrence (two roundings per step).
+ */
+NOVA_API int nova_head_sample(const nova_head_t* h, const float* noise_tok, const void* z, const int64_t* pred_ids,
+                     int64_t B, int64_t Bx, int64_t N, int64_t n, const float* timesteps_host,
+                     const double* sigmas_host, int32_t num_steps, const nova_guidance* guidance,
+                     float* x_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* prev = model_output * dt + sample, elementwise, two roundings in `dtype` (nova_dtype). */
+NOVA_API int nova_euler_step(const void* model_output, const void* sample, double dt, void* prev, int64_t numel,
+                    int32_t dtype, void* stream);
+
+/*
+ * Chamfer primitive: for every point of a its nearest neighbour in b and vice versa.
+ *   a [B, N, 3] fp32, b [B, M, 3] fp32
+ *   d1 [B, N] fp32 = min_j |a_i - b_j|  (Euclidean, NOT squared), idx1 [B, N] int32 or NULL
+ *   d2 [B, M] fp32 = min_i |a_i - b_j|,                           idx2 [B, M] int32 or NULL
+ * Exact difference form sum((x-y)^2) in fp32 (not the |x|^2+|y|^2-2xy matrix form).
+ */
+NOVA_API int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_t N, int64_t M, float* d1, float* d2,
+                    int32_t* idx1, int32_t* idx2, void* stream);
+
+/* Kernels launched by this library in the calling thread since the last reset (for bench.py). */
+NOVA_API int64_t nova_launch_count(void);
+NOVA_API void nova_launch_count_reset(void);
+
+/*
+ * Test hook: C[M,N] = epilogue(A[M,K] W[N,K]^T + bias) with one named GEMM implementation.
+ *   impl 0 = SIMT, 1 = tcgen05 (bf16 only); epilogue 0 = bias, 1 = bias + SiLU.
+ *   A, W, C are bf16 (dtype NOVA_BF16) or fp32 (NOVA_F32); bias fp32 [N] or NULL.
+ */
+NOVA_API int nova_debug_gemm(const void* A, const void* W, const float* bias, void* C, int64_t M, int64_t N, int64_t K,
+                    int32_t dtype, int32_t impl, int32_t epilogue, void* stream);
+
+/* Test hook: the 4 host-mapped words a tcgen05 kernel writes before trapping on a barrier timeout. */
+NOVA_API int nova_debug_words(uint32_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOVA_B200_H_ */

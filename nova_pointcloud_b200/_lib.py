@@ -1,0 +1,110 @@
+"""ctypes binding of libnova_b200.so (the C ABI declared in include/nova_b200.h).
+
+There is no fallback: if the library cannot be built/loaded every product call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libnova_b200.so")
+
+NOVA_F32, NOVA_BF16 = 0, 1
+EPI_BIAS, EPI_BIAS_SILU = 0, 1
+
+# every symbol include/nova_b200.h declares
+EXPORTS = [
+    "nova_last_error", "nova_abi_version", "nova_device_check", "nova_head_create", "nova_head_destroy",
+    "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
+    "nova_head_sample", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
+    "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words",
+]
+
+
+class HeadConfig(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("width", C.c_int32), ("cond_width", C.c_int32),
+                ("token_dim", C.c_int32), ("dtype", C.c_int32)]
+
+
+class Guidance(C.Structure):
+    _fields_ = [("scale", C.c_float), ("trunc", C.c_float), ("renorm", C.c_float)]
+
+
+class NovaError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    lib.nova_last_error.restype = C.c_char_p
+    lib.nova_last_error.argtypes = []
+    lib.nova_abi_version.restype = C.c_int
+    lib.nova_device_check.restype = C.c_int
+    lib.nova_head_create.restype = C.c_int
+    lib.nova_head_create.argtypes = [C.POINTER(HeadConfig), C.POINTER(vp)]
+    lib.nova_head_destroy.restype = C.c_int
+    lib.nova_head_destroy.argtypes = [vp]
+    lib.nova_head_get_config.restype = C.c_int
+    lib.nova_head_get_config.argtypes = [vp, C.POINTER(HeadConfig)]
+    lib.nova_head_load.restype = C.c_int
+    lib.nova_head_load.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i64), i32, i32, vp]
+    lib.nova_head_workspace_bytes.restype = sz
+    lib.nova_head_workspace_bytes.argtypes = [vp, i64, i32]
+    lib.nova_head_forward.restype = C.c_int
+    lib.nova_head_forward.argtypes = [vp, vp, vp, i32, vp, vp, i64, i64, i64, i64, vp, vp, sz, vp]
+    lib.nova_head_sample.restype = C.c_int
+    lib.nova_head_sample.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_double), i32, C.POINTER(Guidance), vp, vp, sz, vp]
+    lib.nova_euler_step.restype = C.c_int
+    lib.nova_euler_step.argtypes = [vp, vp, C.c_double, vp, i64, i32, vp]
+    lib.nova_chamfer_nn.restype = C.c_int
+    lib.nova_chamfer_nn.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp]
+    lib.nova_launch_count.restype = i64
+    lib.nova_launch_count.argtypes = []
+    lib.nova_launch_count_reset.restype = None
+    lib.nova_launch_count_reset.argtypes = []
+    lib.nova_debug_gemm.restype = C.c_int
+    lib.nova_debug_gemm.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
+    lib.nova_debug_words.restype = C.c_int
+    lib.nova_debug_words.argtypes = [C.POINTER(C.c_uint32)]
+
+
+def lib():
+    """Load (building first if the sources are newer) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH) or os.environ.get("NOVA_B200_REBUILD"):
+                from . import build as _build
+
+                _build.build(force=bool(os.environ.get("NOVA_B200_REBUILD")))
+            try:
+                handle = C.CDLL(LIB_PATH)
+            except OSError as e:  # fail loudly: there is no other implementation
+                raise NovaError(f"cannot load {LIB_PATH}: {e}") from e
+            _declare(handle)
+            if handle.nova_abi_version() != 1:
+                raise NovaError("libnova_b200.so ABI version mismatch; rebuild with python -m nova_pointcloud_b200.build")
+            _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib().nova_last_error().decode("utf-8", "replace")
+        raise NovaError(f"{what or 'libnova_b200'} failed (status {status}): {msg}")
+
+
+def debug_words():
+    arr = (C.c_uint32 * 4)()
+    lib().nova_debug_words(arr)
+    return [int(v) for v in arr]

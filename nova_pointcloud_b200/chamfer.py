@@ -1,0 +1,76 @@
+"""Chamfer distance on the GPU: one CUDA nearest-neighbour primitive, the reference's three reductions.
+
+* ``chamfer_distance``          -- variant A, /root/reference/demo.py:38-55 (the canonical definition)
+* ``dist_chamfer`` / ``robust_chamfer_distance`` -- variant B, /root/reference/train_newloss.py:316-349,381-384
+* ``compute_chamfer_distance``  -- variant C, /root/reference/test_optimize.py:354-383
+
+All distances come from ``torch.ops.nova_b200.chamfer_nn`` (exact difference form, fp32); the
+per-point transforms and means on top are elementwise glue.
+"""
+
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from ._lib import NovaError
+
+
+def _as_cuda_batch(x, device=None) -> Tuple[torch.Tensor, bool]:
+    t = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
+    single = t.dim() == 2
+    t = t.unsqueeze(0) if single else t
+    if t.device.type != "cuda":
+        if not torch.cuda.is_available():
+            raise NovaError("Chamfer distance runs on CUDA (sm_100a) only; there is no CPU path")
+        t = t.to(device or "cuda")
+    return t.float().contiguous(), single
+
+
+def chamfer_nn(a, b):
+    """(d1, d2, idx1, idx2): per-point nearest-neighbour Euclidean distances both ways."""
+    a, _ = _as_cuda_batch(a)
+    b, _ = _as_cuda_batch(b, a.device)
+    return torch.ops.nova_b200.chamfer_nn(a, b)
+
+
+def chamfer_distance(points1, points2):
+    """Variant A: mean_i min_j |p_i-q_j| + mean_j min_i |p_i-q_j|.  (N,3),(M,3) -> float; batched -> (B,) tensor."""
+    a, single = _as_cuda_batch(points1)
+    b, _ = _as_cuda_batch(points2, a.device)
+    d1, d2, _, _ = torch.ops.nova_b200.chamfer_nn(a, b)
+    cd = d1.double().mean(dim=1) + d2.double().mean(dim=1)
+    return float(cd[0]) if single else cd
+
+
+def _unit_sphere(x: torch.Tensor) -> torch.Tensor:
+    x = x.clamp(-1.0, 1.0)
+    return x / x.norm(dim=-1, keepdim=True).clamp(min=1e-8)
+
+
+def dist_chamfer(a, b):
+    """Variant B: clamp to [-1,1], project onto the unit sphere, exp(clamp(log(min d))) means -> (dl, dr)."""
+    a, _ = _as_cuda_batch(a)
+    b, _ = _as_cuda_batch(b, a.device)
+    d1, d2, _, _ = torch.ops.nova_b200.chamfer_nn(_unit_sphere(a), _unit_sphere(b))
+    f = lambda m: (m.clamp(min=1e-8) + 1e-8).log().clamp(-10, 10).exp().mean()
+    return f(d1), f(d2)
+
+
+def robust_chamfer_distance(pred, gt):
+    dl, dr = dist_chamfer(pred, gt)
+    return (dl.mean() + dr.mean()) / 2
+
+
+def compute_chamfer_distance(pred, target):
+    """Variant C: clamp +-5, truncate to the common point count, density-weighted means, clamp [0,10]."""
+    p, _ = _as_cuda_batch(pred)
+    t, _ = _as_cuda_batch(target, p.device)
+    p, t = p.clamp(-5.0, 5.0), t.clamp(-5.0, 5.0)
+    n = min(p.shape[1], t.shape[1])
+    m1, m2, _, _ = torch.ops.nova_b200.chamfer_nn(p[:, :n].contiguous(), t[:, :n].contiguous())
+    d1 = (m1 * (1.0 / (m1 + 1e-6))).mean(dim=1)
+    d2 = (m2 * (1.0 / (m2 + 1e-6))).mean(dim=1)
+    return (d1 + d2).mean().clamp(0.0, 10.0)

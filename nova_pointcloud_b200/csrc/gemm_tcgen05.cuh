@@ -1,0 +1,351 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N])
+//
+//   A, W : bf16, K-major (row-major with K contiguous) -- nn.Linear's (out,in) weight is
+//          already the K-major "B" operand, activations are the K-major "A" operand.
+//   acc  : fp32 in tensor memory, double buffered (2 x 256 columns = all 512 TMEM columns)
+//   C    : bf16, written straight from registers (each epilogue thread owns one row).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0    TMA producer   (one lane): cp.async.bulk.tensor 2D loads, 128B swizzle,
+//                            4-stage ring of {A 128x64, W 256x64} tiles, mbarrier tx counts
+//   warp 1    MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16,
+//                            tcgen05.commit releases smem stages / publishes accumulators
+//   warp 2    TMEM allocator (tcgen05.alloc / dealloc)
+//   warps 4-7 epilogue       tcgen05.ld 32x32b -> bias (+SiLU) -> bf16 -> global
+//
+// Every mbarrier wait is bounded: on timeout the kernel records where it was stuck in a
+// host-mapped debug word and traps, so a protocol bug surfaces as a CUDA error, not a hang.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"  // Epilogue enum
+
+namespace nova {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;                // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: after ~4 s without progress record (code, block) in the host-mapped debug
+// words and trap, so a protocol bug is a CUDA error instead of a hung GPU.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t* dbg, uint32_t code) {
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+      if (dbg) {
+        dbg[0] = 0xDEAD0000u | code;
+        dbg[1] = blockIdx.x;
+        dbg[2] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* dbg, uint32_t code) {
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, dbg, code);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* t) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(t)) : "memory");
+}
+// 2D tiled TMA load: coordinates are (c0 = innermost/K element index, c1 = row index).
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* t, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(t)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand tile written by TMA with 128B swizzle:
+// rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major.
+// Field layout follows cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1,
+// b=BF16 [10,13)=1, both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct EpiParams {
+  const float* bias;  // [N] or nullptr
+  bf16* C;
+  int64_t ldc;
+  int M, N, K;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const EpiParams p, uint32_t* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4 * 32);  // every epilogue thread arrives
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------------------------------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = (tile / num_n) * BM, n_idx = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, dbg, 0x100u | stage);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          tma_load_2d(&tmap_a, full_bar(stage), sa, kb * BK, m_idx);
+          tma_load_2d(&tmap_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_idx);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t buf_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(buf), buf_phase ^ 1u, dbg, 0x200u | buf);  // epilogue drained this buffer
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase, dbg, 0x300u | stage);  // TMA bytes landed
+          tcgen05_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t a_desc = make_smem_desc_sw128(sa);
+          const uint64_t b_desc = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16 B units
+            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));  // accumulator complete
+        if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_idx = (tile / num_n) * BM, n_idx = (tile % num_n) * BN;
+      mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf);
+      tcgen05_fence_after();
+      const int row = m_idx + q * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      bf16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_idx + c * 32;
+        if (row < p.M && n0 < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns -> one 16 B store each
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int n = n0 + g * 8 + j;
+              float x = __uint_as_float(r[g * 8 + j]);
+              if (p.bias != nullptr && n < p.N) x += __ldg(p.bias + n);
+              if (EPI == EPI_BIAS_SILU) x = silu(x);
+              v[j] = x;
+            }
+            const int n = n0 + g * 8;
+            if (n + 8 <= p.N) {
+              store8(crow + n, v);
+            } else {
+              for (int j = 0; j < 8 && n + j < p.N; ++j) crow[n + j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+// K-major bf16 matrix [rows, K] with row stride ld (elements) -> 2D tiled map, 128 B swizzle,
+// box = {64 elements of K, box_rows}.  Out-of-bounds elements are zero-filled by TMA.
+int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows);
+uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (device pointer)
+extern uint32_t* g_debug_host;  // the same words, host pointer
+int num_sms();
+
+template <int EPI>
+int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
+               int M, int N, int K, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap ta, tb;
+  NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
+  NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, BN));
+  EpiParams p{bias, C, ldc, M, N, K};
+  const int tiles = static_cast<int>(ceil_div(M, BM) * ceil_div(N, BN));
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, debug_word());
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
+inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
+                  int M, int N, int K, int epi, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return NOVA_OK;
+  NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tcgen05 gemm: K, lda, ldw must be multiples of 8");
+  NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0,
+               "tcgen05 gemm: operands must be 16-byte aligned");
+  return epi == EPI_BIAS ? launch_epi<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
+                         : launch_epi<EPI_BIAS_SILU>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+}
+
+}  // namespace tc
+}  // namespace nova

@@ -1,0 +1,552 @@
+// The diffusion head (DiffusionMLP) and its fused sampling loop on sm_100a.
+//
+// One head step over M rows (reference: diffnext/models/diffusion_mlp.py:89-99):
+//
+//   prep      a = silu(c + temb_s),  x = PatchEmbed(x_tok)                      [row-wise]
+//   G_ada     st = a W_ada^T + b_ada        all 3*depth+2 AdaLN statistics in ONE GEMM, N = 20 D
+//   row       h = LN(x)(1+scale_0)+shift_0                                       [row-wise]
+//   per block G_fc1  u1 = silu(h P1^T + p1)
+//             G_fc2  u2 = u1 P2^T + p2
+//             row    x += LN_aff(u2) * gate_i ;  h = LN(x)(1+scale_{i+1})+shift_{i+1}
+//   last row  ... y = LN(x)(1+scale_f)+shift_f ; v = y H^T + h0 ; x_tok += dt v  (Euler fused)
+//
+// Step-invariant work is hoisted out of the S-step loop (an algorithmic change, not a port):
+// c = condition_proj(z) once per call, temb_s = timestep_proj(freq(t_s)) as an [S, D] table.
+// GEMMs run on tcgen05 tensor cores (bf16 handle) or the SIMT fp32 kernel (fp32 handle).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tcgen05.cuh"
+#include "rowwise.cuh"
+
+using namespace nova;
+
+namespace {
+constexpr int MAX_DEPTH = 16;
+constexpr int MAX_STEPS = 256;
+}  // namespace
+
+struct nova_head {
+  nova_head_config cfg{};
+  int channels = 0;
+  bool loaded = false;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  // GEMM operands in the handle's activation type
+  void* w_c1 = nullptr;   // [D, Dc]
+  void* w_c2 = nullptr;   // [D, D]
+  void* w_ada = nullptr;  // [(3 depth + 2) D, D]: per block scale|shift|gate, then final scale|shift
+  void* w_fc1[MAX_DEPTH] = {};
+  void* w_fc2[MAX_DEPTH] = {};
+  // fp32 side parameters
+  float *b_c1 = nullptr, *b_c2 = nullptr, *b_ada = nullptr;
+  float *b_fc1[MAX_DEPTH] = {}, *b_fc2[MAX_DEPTH] = {}, *gamma[MAX_DEPTH] = {}, *beta[MAX_DEPTH] = {};
+  float *w_t1 = nullptr, *b_t1 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr;
+  float *w_patch = nullptr, *b_patch = nullptr, *w_head = nullptr, *b_head = nullptr;
+  bool use_simt_gemm = false;  // NOVA_B200_GEMM=simt: isolate tcgen05 problems (bf16 handle only)
+
+  int D() const { return cfg.width; }
+  int Dc() const { return cfg.cond_width; }
+  int T() const { return cfg.token_dim; }
+  int n_ada() const { return (3 * cfg.depth + 2) * cfg.width; }
+  size_t esize() const { return cfg.dtype == NOVA_BF16 ? 2 : 4; }
+};
+
+namespace {
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  void* take(size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  }
+};
+
+struct Workspace {
+  void *c, *a, *x, *h, *u1, *u2, *st, *zsel;
+  float *v, *xsel, *thid, *temb, *tdev;
+  size_t bytes;
+};
+
+Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
+  const size_t M = static_cast<size_t>(rows > 0 ? rows : 1), D = h->D(), es = h->esize();
+  const size_t R = M > static_cast<size_t>(steps) ? M : static_cast<size_t>(steps);
+  Carver cv(base);
+  Workspace w{};
+  w.c = cv.take(M * D * es);
+  w.a = cv.take(M * D * es);
+  w.x = cv.take(M * D * es);
+  w.h = cv.take(M * D * es);
+  w.u1 = cv.take(M * D * es);
+  w.u2 = cv.take(M * D * es);
+  w.st = cv.take(M * h->n_ada() * es);
+  w.zsel = cv.take(M * h->Dc() * es);
+  w.v = static_cast<float*>(cv.take(M * h->T() * sizeof(float)));
+  w.xsel = static_cast<float*>(cv.take(M * h->T() * sizeof(float)));
+  w.thid = static_cast<float*>(cv.take(R * D * sizeof(float)));
+  w.temb = static_cast<float*>(cv.take(R * D * sizeof(float)));
+  w.tdev = static_cast<float*>(cv.take(R * sizeof(float)));
+  w.bytes = cv.off;
+  return w;
+}
+
+template <typename AT>
+int gemm(const nova_head* h, const AT* A, int64_t lda, const AT* W, int64_t ldw, const float* bias, AT* C, int64_t ldc,
+         int64_t M, int N, int K, int epi, cudaStream_t s);
+template <>
+int gemm<float>(const nova_head*, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
+                int64_t ldc, int64_t M, int N, int K, int epi, cudaStream_t s) {
+  return simt::launch<float, float, true>(A, lda, W, ldw, bias, C, ldc, (int)M, N, K, epi, s);
+}
+template <>
+int gemm<bf16>(const nova_head* h, const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C,
+               int64_t ldc, int64_t M, int N, int K, int epi, cudaStream_t s) {
+  if (h->use_simt_gemm) return simt::launch<bf16, bf16, false>(A, lda, W, ldw, bias, C, ldc, (int)M, N, K, epi, s);
+  return tc::launch(A, lda, W, ldw, bias, C, ldc, (int)M, N, K, epi, s);
+}
+
+struct TimeList {
+  float v[MAX_STEPS];
+};
+__global__ void fill_times_kernel(float* dst, const TimeList tl, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = tl.v[i];
+}
+
+// temb[r, :] = timestep_proj(freq_embed(t[r])) for R timesteps already on the device
+int time_embedding(const nova_head* h, const float* t_dev, int64_t R, const Workspace& w, cudaStream_t s) {
+  const int D = h->D();
+  NOVA_REQUIRE(R <= 65535 * 64ll, "too many distinct timesteps (%lld)", (long long)R);
+  for (int64_t r0 = 0; r0 < R; r0 += 65535) {  // gridDim.y limit
+    const int64_t rn = (R - r0) < 65535 ? (R - r0) : 65535;
+    dim3 grid((unsigned)ceil_div(D, rw::WARPS), (unsigned)rn);
+    rw::temb_fc1_kernel<<<grid, rw::THREADS, 0, s>>>(t_dev + r0, (int)rn, h->w_t1, h->b_t1, w.thid + r0 * D, D);
+    NOVA_CHECK_LAUNCH();
+    rw::temb_fc2_kernel<<<grid, rw::THREADS, 0, s>>>(w.thid + r0 * D, (int)rn, h->w_t2, h->b_t2, w.temb + r0 * D, D);
+    NOVA_CHECK_LAUNCH();
+  }
+  return NOVA_OK;
+}
+
+// c = condition_proj(z_rows)  (two GEMMs; u1 is the scratch for the hidden layer)
+template <typename AT>
+int cond_embedding(const nova_head* h, const AT* z_rows, int64_t M, const Workspace& w, cudaStream_t s) {
+  const int D = h->D(), Dc = h->Dc();
+  NOVA_PROPAGATE(gemm<AT>(h, z_rows, Dc, static_cast<const AT*>(h->w_c1), Dc, h->b_c1, static_cast<AT*>(w.u1), D, M, D,
+                          Dc, EPI_BIAS_SILU, s));
+  return gemm<AT>(h, static_cast<const AT*>(w.u1), D, static_cast<const AT*>(h->w_c2), D, h->b_c2,
+                  static_cast<AT*>(w.c), D, M, D, D, EPI_BIAS, s);
+}
+
+struct StepIO {
+  int64_t M;           // head rows this step
+  int64_t rows_per_t;  // rows sharing one time embedding
+  int64_t t_offset;    // first row of temb to use
+  const float* x_tok;  // [x_rows, T] latent of the selected tokens
+  int64_t x_rows;      // row m reads latent row m % x_rows (guidance passes share the latent)
+  float* v_out;        // [M, T] or nullptr
+  float* xt_out;       // Euler-updated latent [M, T] or nullptr (then xt_in = x_tok)
+  float dt;
+};
+
+template <typename AT>
+int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStream_t s) {
+  const int D = h->D(), T = h->T(), depth = h->cfg.depth;
+  const int64_t M = io.M;
+  if (M <= 0) return NOVA_OK;
+  {
+    const int64_t nvec = M * (D / 8);
+    if (h->cfg.dtype == NOVA_F32)
+      rw::prep_kernel<AT, true><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(
+          static_cast<const AT*>(w.c), w.temb, io.rows_per_t, io.t_offset, io.x_tok, io.x_rows, h->w_patch, h->b_patch,
+          static_cast<AT*>(w.a), static_cast<AT*>(w.x), M, D, T);
+    else
+      rw::prep_kernel<AT, false><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(
+          static_cast<const AT*>(w.c), w.temb, io.rows_per_t, io.t_offset, io.x_tok, io.x_rows, h->w_patch, h->b_patch,
+          static_cast<AT*>(w.a), static_cast<AT*>(w.x), M, D, T);
+    NOVA_CHECK_LAUNCH();
+  }
+  const int n_ada = h->n_ada();
+  NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.a), D, static_cast<const AT*>(h->w_ada), D, h->b_ada,
+                          static_cast<AT*>(w.st), n_ada, M, n_ada, D, EPI_BIAS, s));
+  rw::RowParams p{};
+  p.M = M; p.D = D; p.T = T;
+  p.x_in = w.x; p.x_out = w.x; p.u = w.u2; p.st = w.st; p.ldst = n_ada; p.h_out = w.h;
+  p.Wh = h->w_head; p.bh = h->b_head;
+  p.v_out = io.v_out; p.xt_in = io.x_tok; p.xt_out = io.xt_out; p.dt = io.dt;
+  const int64_t final_off = static_cast<int64_t>(3) * depth * D;
+  p.scale_off = depth > 0 ? 0 : final_off;
+  NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/false, /*out=*/depth > 0 ? 0 : 1, s));
+  for (int i = 0; i < depth; ++i) {
+    NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.h), D, static_cast<const AT*>(h->w_fc1[i]), D, h->b_fc1[i],
+                            static_cast<AT*>(w.u1), D, M, D, D, EPI_BIAS_SILU, s));
+    NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.u1), D, static_cast<const AT*>(h->w_fc2[i]), D, h->b_fc2[i],
+                            static_cast<AT*>(w.u2), D, M, D, D, EPI_BIAS, s));
+    const bool last = (i + 1 == depth);
+    p.gate_off = static_cast<int64_t>(3) * i * D + 2 * D;
+    p.gamma = h->gamma[i];
+    p.beta = h->beta[i];
+    p.scale_off = last ? final_off : static_cast<int64_t>(3) * (i + 1) * D;
+    NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/true, /*out=*/last ? 1 : 0, s));
+  }
+  return NOVA_OK;
+}
+
+int check_call(const nova_head* h, int64_t B, int64_t Bx, int64_t N, int64_t n, const void* ws, size_t ws_bytes,
+               int steps, const char* who) {
+  NOVA_REQUIRE(h != nullptr, "%s: null handle", who);
+  if (!h->loaded) {
+    set_error("%s: weights not loaded", who);
+    return NOVA_ERR_NOT_LOADED;
+  }
+  NOVA_REQUIRE(B >= 0 && N >= 0 && n >= 0 && n <= N, "%s: bad sizes B=%lld N=%lld n=%lld", who, (long long)B,
+               (long long)N, (long long)n);
+  NOVA_REQUIRE(Bx == B || 2 * Bx == B, "%s: x batch %lld must equal or halve z batch %lld", who, (long long)Bx,
+               (long long)B);
+  NOVA_REQUIRE(B * n < (1ll << 31), "%s: too many rows", who);
+  const size_t need = nova_head_workspace_bytes(h, B * n, steps);
+  if (B * n > 0 && (ws == nullptr || ws_bytes < need)) {
+    set_error("%s: workspace %zu bytes < required %zu", who, ws_bytes, need);
+    return NOVA_ERR_WORKSPACE;
+  }
+  NOVA_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
+  if (h->cfg.dtype == NOVA_BF16 && !h->use_simt_gemm) NOVA_PROPAGATE(nova_device_check());
+  return NOVA_OK;
+}
+
+template <typename AT>
+int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_per_token, const AT* z,
+                 const int64_t* pred_ids, int64_t B, int64_t Bx, int64_t N, int64_t n, float* v_out, void* ws,
+                 cudaStream_t s) {
+  const int64_t M = B * n;
+  if (M == 0) return NOVA_OK;
+  const int T = h->T(), Dc = h->Dc();
+  const int64_t R = t_per_token ? M : B;
+  Workspace w = carve(h, ws, M, 0);
+  const AT* z_rows = z;
+  if (pred_ids) {
+    const int64_t nvec = M * (Dc / 8);
+    rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, pred_ids, static_cast<AT*>(w.zsel), B, N,
+                                                                           n, Dc);
+    NOVA_CHECK_LAUNCH();
+    z_rows = static_cast<const AT*>(w.zsel);
+  }
+  const float* x_rows = x_tok;
+  if (pred_ids || Bx != B) {
+    rw::gather_tok_kernel<<<(unsigned)ceil_div(M * T, 256), 256, 0, s>>>(x_tok, pred_ids, w.xsel, B, Bx, N, n, T);
+    NOVA_CHECK_LAUNCH();
+    x_rows = w.xsel;
+  }
+  NOVA_PROPAGATE(time_embedding(h, t, R, w, s));
+  NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));
+  StepIO io{M, t_per_token ? 1 : n, 0, x_rows, M, v_out, nullptr, 0.f};
+  return head_step<AT>(h, w, io, s);
+}
+
+template <typename AT>
+int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const int64_t* pred_ids, int64_t B, int64_t Bx,
+                int64_t N, int64_t n, const float* timesteps, const double* sigmas, int S, const nova_guidance* g,
+                float* x_out, void* ws, cudaStream_t s) {
+  const int T = h->T(), Dc = h->Dc();
+  const int64_t M = B * n, Mx = Bx * n;
+  const bool guided = g != nullptr && g->scale > 1.0f;
+  TimeList dts{};
+  for (int i = 0; i < S; ++i) dts.v[i] = static_cast<float>(sigmas[i + 1] - sigmas[i]);
+  if (pred_ids && n < N) {  // tokens outside the set: x <- x*dt + x per step
+    const int64_t numel = Bx * N * T;
+    Workspace w0 = carve(h, ws, M, S);
+    fill_times_kernel<<<1, MAX_STEPS, 0, s>>>(w0.tdev, dts, S);
+    NOVA_CHECK_LAUNCH();
+    rw::unpredicted_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, s>>>(noise_tok, x_out, numel, w0.tdev, S);
+    NOVA_CHECK_LAUNCH();
+  }
+  if (M == 0) return NOVA_OK;
+  Workspace w = carve(h, ws, M, S);
+  const AT* z_rows = z;
+  if (pred_ids) {
+    const int64_t nvec = M * (Dc / 8);
+    rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, pred_ids, static_cast<AT*>(w.zsel), B, N,
+                                                                           n, Dc);
+    NOVA_CHECK_LAUNCH();
+    z_rows = static_cast<const AT*>(w.zsel);
+  }
+  // latent of the selected tokens, fp32, resident in the workspace for all S steps
+  rw::gather_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(noise_tok, pred_ids, w.xsel, Bx, Bx, N, n, T);
+  NOVA_CHECK_LAUNCH();
+  TimeList tl{};
+  for (int i = 0; i < S; ++i) tl.v[i] = timesteps[i];
+  fill_times_kernel<<<1, MAX_STEPS, 0, s>>>(w.tdev, tl, S);
+  NOVA_CHECK_LAUNCH();
+  NOVA_PROPAGATE(time_embedding(h, w.tdev, S, w, s));
+  NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));  // hoisted: step-invariant
+  bool active = guided;
+  for (int i = 0; i < S; ++i) {
+    if (active && g->trunc > 0.f && timesteps[i] < g->trunc) active = false;  // maybe_disable
+    StepIO io{};
+    io.rows_per_t = M + 1;  // every row uses temb row t_offset
+    io.t_offset = i;
+    io.x_tok = w.xsel;
+    io.x_rows = Mx;
+    io.dt = dts.v[i];
+    if (active) {
+      io.M = M;
+      io.v_out = w.v;
+      NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
+      rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, s>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt);
+      NOVA_CHECK_LAUNCH();
+    } else {
+      io.M = Mx;  // guidance off (or truncated): only the conditional rows run
+      io.xt_out = w.xsel;
+      NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
+    }
+  }
+  rw::scatter_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(w.xsel, pred_ids, x_out, Bx, N, n, T);
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
+template <typename TS, typename TD>
+int convert(const void* src, TD* dst, int64_t numel, cudaStream_t s) {
+  rw::convert_kernel<TS, TD><<<(unsigned)ceil_div(numel, 256), 256, 0, s>>>(static_cast<const TS*>(src), dst, numel);
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+// source element type is a run-time value, destination is float or the handle's activation type
+int convert_to_float(const void* src, int src_dtype, float* dst, int64_t numel, cudaStream_t s) {
+  return src_dtype == NOVA_F32 ? convert<float, float>(src, dst, numel, s) : convert<bf16, float>(src, dst, numel, s);
+}
+int convert_to_act(const nova_head* h, const void* src, int src_dtype, void* dst, int64_t numel, cudaStream_t s) {
+  if (h->cfg.dtype == NOVA_F32) return convert_to_float(src, src_dtype, static_cast<float*>(dst), numel, s);
+  return src_dtype == NOVA_F32 ? convert<float, bf16>(src, static_cast<bf16*>(dst), numel, s)
+                               : convert<bf16, bf16>(src, static_cast<bf16*>(dst), numel, s);
+}
+
+}  // namespace
+
+extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) {
+  NOVA_REQUIRE(cfg && out, "nova_head_create: null argument");
+  NOVA_REQUIRE(cfg->depth >= 0 && cfg->depth <= MAX_DEPTH, "nova_head_create: depth %d out of range", cfg->depth);
+  NOVA_REQUIRE(cfg->width > 0 && cfg->width % 256 == 0 && cfg->width <= 2048,
+               "nova_head_create: width %d must be a multiple of 256, <= 2048", cfg->width);
+  NOVA_REQUIRE(cfg->cond_width > 0 && cfg->cond_width % 64 == 0, "nova_head_create: cond_width %d must be a multiple of 64",
+               cfg->cond_width);
+  NOVA_REQUIRE(cfg->token_dim > 0 && cfg->token_dim <= rw::MAX_T, "nova_head_create: token_dim %d out of range",
+               cfg->token_dim);
+  NOVA_REQUIRE(cfg->dtype == NOVA_F32 || cfg->dtype == NOVA_BF16, "nova_head_create: unknown dtype %d", cfg->dtype);
+  nova_head* h = new (std::nothrow) nova_head();
+  NOVA_REQUIRE(h != nullptr, "nova_head_create: out of host memory");
+  h->cfg = *cfg;
+  const char* env = std::getenv("NOVA_B200_GEMM");
+  h->use_simt_gemm = env != nullptr && std::strcmp(env, "simt") == 0;
+
+  const size_t D = cfg->width, Dc = cfg->cond_width, T = cfg->token_dim, es = h->esize();
+  Carver cv(nullptr);
+  auto plan = [&](Carver& c) {
+    h->w_c1 = c.take(D * Dc * es);
+    h->w_c2 = c.take(D * D * es);
+    h->w_ada = c.take(static_cast<size_t>(h->n_ada()) * D * es);
+    for (int i = 0; i < cfg->depth; ++i) {
+      h->w_fc1[i] = c.take(D * D * es);
+      h->w_fc2[i] = c.take(D * D * es);
+    }
+    auto f = [&](size_t n) { return static_cast<float*>(c.take(n * sizeof(float))); };
+    h->b_c1 = f(D); h->b_c2 = f(D); h->b_ada = f(h->n_ada());
+    for (int i = 0; i < cfg->depth; ++i) {
+      h->b_fc1[i] = f(D); h->b_fc2[i] = f(D); h->gamma[i] = f(D); h->beta[i] = f(D);
+    }
+    h->w_t1 = f(D * 256); h->b_t1 = f(D); h->w_t2 = f(D * D); h->b_t2 = f(D);
+    h->w_patch = f(D * T); h->b_patch = f(D); h->w_head = f(T * D); h->b_head = f(T);
+  };
+  plan(cv);
+  h->arena_bytes = cv.off;
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e != cudaSuccess) {
+    set_error("nova_head_create: cudaMalloc(%zu) failed: %s", h->arena_bytes, cudaGetErrorString(e));
+    delete h;
+    return NOVA_ERR_CUDA;
+  }
+  Carver real(h->arena);
+  plan(real);
+  *out = h;
+  return NOVA_OK;
+}
+
+extern "C" int nova_head_destroy(nova_head_t* h) {
+  if (!h) return NOVA_OK;
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return NOVA_OK;
+}
+
+extern "C" int nova_head_get_config(const nova_head_t* h, nova_head_config* out) {
+  NOVA_REQUIRE(h && out, "nova_head_get_config: null argument");
+  *out = h->cfg;
+  return NOVA_OK;
+}
+
+extern "C" int nova_head_load(nova_head_t* h, int32_t n, const char* const* names, const void* const* ptrs,
+                              const int64_t* numels, int32_t src_dtype, int32_t channels, void* stream) {
+  NOVA_REQUIRE(h && names && ptrs && numels, "nova_head_load: null argument");
+  NOVA_REQUIRE(src_dtype == NOVA_F32 || src_dtype == NOVA_BF16, "nova_head_load: unknown src_dtype %d", src_dtype);
+  const int D = h->D(), Dc = h->Dc(), T = h->T(), depth = h->cfg.depth;
+  NOVA_REQUIRE(channels > 0 && T % channels == 0, "nova_head_load: channels %d does not divide token_dim %d", channels, T);
+  const int p = static_cast<int>(std::lround(std::sqrt(static_cast<double>(T / channels))));
+  NOVA_REQUIRE(p * p * channels == T, "nova_head_load: token_dim %d is not channels*p*p", T);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t es = h->esize();
+  int seen = 0;
+  const int expected = 14 + 8 * depth;
+  for (int k = 0; k < n; ++k) {
+    const std::string name(names[k]);
+    const void* src = ptrs[k];
+    const int64_t numel = numels[k];
+    NOVA_REQUIRE(src != nullptr, "nova_head_load: null pointer for %s", name.c_str());
+    auto want = [&](int64_t expect) -> bool {
+      if (numel != expect) set_error("nova_head_load: %s has %lld elements, expected %lld", name.c_str(), (long long)numel,
+                                     (long long)expect);
+      return numel == expect;
+    };
+    int rc = NOVA_OK;
+    bool known = true;
+    if (name == "patch_embed.proj.weight") {
+      if (!want((int64_t)D * T)) return NOVA_ERR_INVALID;
+      const unsigned grid = (unsigned)ceil_div((int64_t)D * T, 256);
+      if (src_dtype == NOVA_F32)
+        rw::permute_patch_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), h->w_patch, D, channels, p);
+      else
+        rw::permute_patch_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(src), h->w_patch, D, channels, p);
+      NOVA_CHECK_LAUNCH();
+    } else if (name == "patch_embed.proj.bias") {
+      if (!want(D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_patch, D, s);
+    } else if (name == "time_cond_embed.timestep_proj.fc1.weight") {
+      if (!want((int64_t)D * 256)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->w_t1, numel, s);
+    } else if (name == "time_cond_embed.timestep_proj.fc1.bias") {
+      if (!want(D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_t1, D, s);
+    } else if (name == "time_cond_embed.timestep_proj.fc2.weight") {
+      if (!want((int64_t)D * D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->w_t2, numel, s);
+    } else if (name == "time_cond_embed.timestep_proj.fc2.bias") {
+      if (!want(D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_t2, D, s);
+    } else if (name == "time_cond_embed.condition_proj.fc1.weight") {
+      if (!want((int64_t)D * Dc)) return NOVA_ERR_INVALID;
+      rc = convert_to_act(h, src, src_dtype, h->w_c1, numel, s);
+    } else if (name == "time_cond_embed.condition_proj.fc1.bias") {
+      if (!want(D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_c1, D, s);
+    } else if (name == "time_cond_embed.condition_proj.fc2.weight") {
+      if (!want((int64_t)D * D)) return NOVA_ERR_INVALID;
+      rc = convert_to_act(h, src, src_dtype, h->w_c2, numel, s);
+    } else if (name == "time_cond_embed.condition_proj.fc2.bias") {
+      if (!want(D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_c2, D, s);
+    } else if (name == "norm.proj.weight") {
+      if (!want((int64_t)2 * D * D)) return NOVA_ERR_INVALID;
+      rc = convert_to_act(h, src, src_dtype, static_cast<uint8_t*>(h->w_ada) + (size_t)3 * depth * D * D * es, numel, s);
+    } else if (name == "norm.proj.bias") {
+      if (!want((int64_t)2 * D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_ada + (size_t)3 * depth * D, numel, s);
+    } else if (name == "head.weight") {
+      if (!want((int64_t)T * D)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->w_head, numel, s);
+    } else if (name == "head.bias") {
+      if (!want(T)) return NOVA_ERR_INVALID;
+      rc = convert_to_float(src, src_dtype, h->b_head, T, s);
+    } else if (name.rfind("blocks.", 0) == 0) {
+      const size_t dot = name.find('.', 7);
+      NOVA_REQUIRE(dot != std::string::npos, "nova_head_load: malformed key %s", name.c_str());
+      const int i = std::atoi(name.substr(7, dot - 7).c_str());
+      NOVA_REQUIRE(i >= 0 && i < depth, "nova_head_load: block index out of range in %s", name.c_str());
+      const std::string leaf = name.substr(dot + 1);
+      if (leaf == "norm1.proj.weight") {
+        if (!want((int64_t)3 * D * D)) return NOVA_ERR_INVALID;
+        rc = convert_to_act(h, src, src_dtype, static_cast<uint8_t*>(h->w_ada) + (size_t)3 * i * D * D * es, numel, s);
+      } else if (leaf == "norm1.proj.bias") {
+        if (!want((int64_t)3 * D)) return NOVA_ERR_INVALID;
+        rc = convert_to_float(src, src_dtype, h->b_ada + (size_t)3 * i * D, numel, s);
+      } else if (leaf == "proj.fc1.weight") {
+        if (!want((int64_t)D * D)) return NOVA_ERR_INVALID;
+        rc = convert_to_act(h, src, src_dtype, h->w_fc1[i], numel, s);
+      } else if (leaf == "proj.fc1.bias") {
+        if (!want(D)) return NOVA_ERR_INVALID;
+        rc = convert_to_float(src, src_dtype, h->b_fc1[i], D, s);
+      } else if (leaf == "proj.fc2.weight") {
+        if (!want((int64_t)D * D)) return NOVA_ERR_INVALID;
+        rc = convert_to_act(h, src, src_dtype, h->w_fc2[i], numel, s);
+      } else if (leaf == "proj.fc2.bias") {
+        if (!want(D)) return NOVA_ERR_INVALID;
+        rc = convert_to_float(src, src_dtype, h->b_fc2[i], D, s);
+      } else if (leaf == "norm2.weight") {
+        if (!want(D)) return NOVA_ERR_INVALID;
+        rc = convert_to_float(src, src_dtype, h->gamma[i], D, s);
+      } else if (leaf == "norm2.bias") {
+        if (!want(D)) return NOVA_ERR_INVALID;
+        rc = convert_to_float(src, src_dtype, h->beta[i], D, s);
+      } else {
+        known = false;
+      }
+    } else {
+      known = false;
+    }
+    NOVA_REQUIRE(known, "nova_head_load: unexpected key %s", name.c_str());
+    NOVA_PROPAGATE(rc);
+    ++seen;
+  }
+  NOVA_REQUIRE(seen == expected, "nova_head_load: got %d keys, the reference state_dict has %d", seen, expected);
+  h->channels = channels;
+  h->loaded = true;
+  return NOVA_OK;
+}
+
+extern "C" size_t nova_head_workspace_bytes(const nova_head_t* h, int64_t rows, int32_t num_steps) {
+  if (!h || rows < 0) return 0;
+  return carve(h, nullptr, rows, num_steps).bytes;
+}
+
+extern "C" int nova_head_forward(const nova_head_t* h, const float* x_tok, const float* t, int32_t t_per_token,
+                                 const void* z, const int64_t* pred_ids, int64_t B, int64_t Bx, int64_t N, int64_t n,
+                                 float* v_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NOVA_PROPAGATE(check_call(h, B, Bx, N, n, workspace, workspace_bytes, 0, "nova_head_forward"));
+  NOVA_REQUIRE(pred_ids != nullptr || n == N, "nova_head_forward: n must equal N without pred_ids");
+  if (B * n == 0) return NOVA_OK;
+  NOVA_REQUIRE(x_tok && t && z && v_out, "nova_head_forward: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->cfg.dtype == NOVA_F32)
+    return forward_impl<float>(h, x_tok, t, t_per_token, static_cast<const float*>(z), pred_ids, B, Bx, N, n, v_out,
+                               workspace, s);
+  return forward_impl<bf16>(h, x_tok, t, t_per_token, static_cast<const bf16*>(z), pred_ids, B, Bx, N, n, v_out, workspace,
+                            s);
+}
+
+extern "C" int nova_head_sample(const nova_head_t* h, const float* noise_tok, const void* z, const int64_t* pred_ids,
+                                int64_t B, int64_t Bx, int64_t N, int64_t n, const float* timesteps_host,
+                                const double* sigmas_host, int32_t num_steps, const nova_guidance* guidance, float* x_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  NOVA_REQUIRE(num_steps >= 0 && num_steps <= MAX_STEPS, "nova_head_sample: num_steps %d out of range [0, %d]", num_steps,
+               MAX_STEPS);
+  NOVA_PROPAGATE(check_call(h, B, Bx, N, n, workspace, workspace_bytes, num_steps, "nova_head_sample"));
+  NOVA_REQUIRE(pred_ids != nullptr || n == N, "nova_head_sample: n must equal N without pred_ids");
+  const bool guided = guidance != nullptr && guidance->scale > 1.0f;
+  NOVA_REQUIRE(guided ? (B == 2 * Bx) : (B == Bx), "nova_head_sample: z batch %lld does not match guidance (x batch %lld)",
+               (long long)B, (long long)Bx);
+  if (Bx * N == 0) return NOVA_OK;
+  NOVA_REQUIRE(noise_tok && z && x_out && (num_steps == 0 || (timesteps_host && sigmas_host)),
+               "nova_head_sample: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->cfg.dtype == NOVA_F32)
+    return sample_impl<float>(h, noise_tok, static_cast<const float*>(z), pred_ids, B, Bx, N, n, timesteps_host,
+                              sigmas_host, num_steps, guidance, x_out, workspace, s);
+  return sample_impl<bf16>(h, noise_tok, static_cast<const bf16*>(z), pred_ids, B, Bx, N, n, timesteps_host, sigmas_host,
+                           num_steps, guidance, x_out, workspace, s);
+}

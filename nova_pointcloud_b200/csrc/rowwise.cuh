@@ -1,0 +1,366 @@
+// Row-wise (HBM-bound) kernels of the diffusion head: everything between the GEMMs.
+// One warp owns one token row; a row of D = VPL*256 values lives in registers
+// (VPL 16-byte vectors per lane), so each activation is read once and written once.
+//
+// Reference arithmetic (file:line into /root/reference):
+//   time embedding        diffnext/models/diffusion_mlp.py:65-75
+//   AdaLN-zero modulate   diffnext/models/normalization.py:34-36   (LN eps 1e-6, no affine)
+//   block tail            diffnext/models/diffusion_mlp.py:53      (LN eps 1e-5 affine, * gate + x)
+//   head + Euler          diffnext/models/diffusion_mlp.py:98, diffnext/schedulers/scheduling_cfm.py:136
+#pragma once
+
+#include "common.cuh"
+
+namespace nova {
+namespace rw {
+
+constexpr int WARPS = 8;           // rows per CTA
+constexpr int THREADS = WARPS * 32;
+constexpr int MAX_T = 64;
+
+// ------------------------------------------------------------------ time embedding
+// hidden[r, d] = silu(b1[d] + sum_k emb(t_r)[k] * W1[d, k]),  emb = [cos(t f), sin(t f)], 256 wide
+static __global__ void __launch_bounds__(THREADS)
+temb_fc1_kernel(const float* __restrict__ t, int R, const float* __restrict__ W1, const float* __restrict__ b1,
+                float* __restrict__ hidden, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.y;
+  const int d = blockIdx.x * WARPS + warp;
+  if (d >= D) return;
+  const float tv = t[r];
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = lane + 32 * i;  // 0..127
+    const float f = expf(static_cast<float>(k) * (-9.210340371976184f / 128.0f));
+    float s, c;
+    sincosf(tv * f, &s, &c);
+    acc = fmaf(c, W1[(int64_t)d * 256 + k], acc);
+    acc = fmaf(s, W1[(int64_t)d * 256 + 128 + k], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) hidden[(int64_t)r * D + d] = silu_accurate(acc + b1[d]);
+}
+// temb[r, d] = b2[d] + sum_k hidden[r, k] * W2[d, k]
+static __global__ void __launch_bounds__(THREADS)
+temb_fc2_kernel(const float* __restrict__ hidden, int R, const float* __restrict__ W2,
+                const float* __restrict__ b2, float* __restrict__ temb, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.y;
+  const int d = blockIdx.x * WARPS + warp;
+  if (d >= D) return;
+  float acc = 0.f;
+  for (int k = lane * 4; k < D; k += 128) {
+    const float4 h = *reinterpret_cast<const float4*>(hidden + (int64_t)r * D + k);
+    const float4 w = *reinterpret_cast<const float4*>(W2 + (int64_t)d * D + k);
+    acc = fmaf(h.x, w.x, acc);
+    acc = fmaf(h.y, w.y, acc);
+    acc = fmaf(h.z, w.z, acc);
+    acc = fmaf(h.w, w.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) temb[(int64_t)r * D + d] = acc + b2[d];
+}
+
+// ------------------------------------------------------------------ gather rows by pred_ids
+// dst[b*n + j, :] = src[b*N + ids[b*n + j], :]   (W elements per row, 8 per thread)
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, const int64_t* __restrict__ ids, T* __restrict__ dst,
+                                   int64_t B, int64_t N, int64_t n, int W) {
+  const int64_t vec_per_row = W / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n * vec_per_row) return;
+  const int64_t row = i / vec_per_row, v = i % vec_per_row;
+  const int64_t b = row / n;
+  const int64_t srow = b * N + (ids ? ids[row] : row % n);
+  float tmp[8];
+  load8(src + srow * W + v * 8, tmp);
+  store8(dst + row * W + v * 8, tmp);
+}
+// small fp32 rows (token latent, T values): dst[b*n+j, :] = src[(b % Bx)*N + ids[b*n+j], :]
+static __global__ void
+gather_tok_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids,
+                                  float* __restrict__ dst, int64_t B, int64_t Bx, int64_t N, int64_t n, int T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n * T) return;
+  const int64_t row = i / T, c = i % T;
+  const int64_t b = row / n;
+  const int64_t tok = ids ? ids[row] : row % n;
+  dst[i] = src[((b % Bx) * N + tok) * T + c];
+}
+
+// ------------------------------------------------------------------ step prologue
+// a[m, :] = silu(c[m, :] + temb[tsel(m), :])            -> A operand of the AdaLN GEMM
+// x[m, :] = bp + Wp * x_tok[m % x_rows, :]               (PatchEmbed with K = T)
+// tsel(m) = (m / rows_per_t) * t_stride + t_offset
+template <typename AT, bool ACCURATE>
+__global__ void __launch_bounds__(256)
+prep_kernel(const AT* __restrict__ c, const float* __restrict__ temb, int64_t rows_per_t, int64_t t_offset,
+            const float* __restrict__ x_tok, int64_t x_rows, const float* __restrict__ Wp,
+            const float* __restrict__ bp, AT* __restrict__ a, AT* __restrict__ x, int64_t M, int D, int T) {
+  const int64_t vec_per_row = D / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * vec_per_row) return;
+  const int64_t m = i / vec_per_row;
+  const int d0 = static_cast<int>(i % vec_per_row) * 8;
+  const float* te = temb + ((m / rows_per_t) + t_offset) * D + d0;
+  float cv[8], av[8], xv[8];
+  load8(c + m * D + d0, cv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s = cv[j] + te[j];
+    av[j] = ACCURATE ? silu_accurate(s) : silu(s);
+  }
+  store8(a + m * D + d0, av);
+  const float* xt = x_tok + (m % x_rows) * T;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float acc = bp[d0 + j];
+    for (int t = 0; t < T; ++t) acc = fmaf(xt[t], Wp[(int64_t)(d0 + j) * T + t], acc);
+    xv[j] = acc;
+  }
+  store8(x + m * D + d0, xv);
+}
+
+// ------------------------------------------------------------------ the fused row kernel
+struct RowParams {
+  int64_t M;
+  int D, T;
+  const void* x_in;    // [M, D]   residual stream
+  void* x_out;         // [M, D]   (written when HAS_PREV)
+  const void* u;       // [M, D]   fc2 output of the finished block (HAS_PREV)
+  const void* st;      // [M, ldst] all AdaLN statistics of this step
+  int64_t ldst;
+  int64_t gate_off;    // column of the finished block's gate
+  int64_t scale_off;   // column of the next modulation's scale; shift follows at +D
+  const float* gamma;  // norm2 weight / bias of the finished block
+  const float* beta;
+  void* h_out;         // [M, D]   modulated activations (OUT == 0)
+  // OUT == 1: head + Euler
+  const float* Wh;     // [T, D]
+  const float* bh;     // [T]
+  float* v_out;        // [M, T] or nullptr
+  const float* xt_in;  // [M, T] latent (Euler) or nullptr
+  float* xt_out;       // [M, T]
+  float dt;
+};
+
+template <int VPL>
+__device__ __forceinline__ void row_stats(const float (&v)[VPL][8], float inv_d, float eps, float& mean,
+                                          float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      q = fmaf(d, d, q);
+    }
+  rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+}
+
+// HAS_PREV: x <- LN_affine(u; 1e-5) * gate + x        (tail of the block that just ran)
+// then      y  = LN(x; 1e-6) * (1 + scale) + shift     (AdaLN of the next consumer)
+// OUT == 0: h_out <- y.   OUT == 1: v = Wh y + bh; optional Euler update of the latent.
+template <typename AT, int VPL, bool HAS_PREV, int OUT>
+__global__ void __launch_bounds__(THREADS)
+row_kernel(const RowParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= p.M) return;
+  const int D = p.D;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  const AT* xin = static_cast<const AT*>(p.x_in) + row * D;
+  const AT* st = static_cast<const AT*>(p.st) + row * p.ldst;
+
+  float x[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) load8(xin + (i * 32 + lane) * 8, x[i]);
+
+  if (HAS_PREV) {
+    const AT* uin = static_cast<const AT*>(p.u) + row * D;
+    float u[VPL][8];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) load8(uin + (i * 32 + lane) * 8, u[i]);
+    float mean, rstd;
+    row_stats<VPL>(u, inv_d, 1e-5f, mean, rstd);
+    AT* xout = static_cast<AT*>(p.x_out) + row * D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int e = (i * 32 + lane) * 8;
+      float g[8], ga[8], be[8];
+      load8(st + p.gate_off + e, g);
+      load8(p.gamma + e, ga);
+      load8(p.beta + e, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float ln = fmaf((u[i][j] - mean) * rstd, ga[j], be[j]);
+        x[i][j] = fmaf(ln, g[j], x[i][j]);
+      }
+      if (OUT == 0) store8(xout + e, x[i]);
+    }
+  }
+
+  float mean, rstd;
+  row_stats<VPL>(x, inv_d, 1e-6f, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int e = (i * 32 + lane) * 8;
+    float sc[8], sh[8];
+    load8(st + p.scale_off + e, sc);
+    load8(st + p.scale_off + D + e, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[i][j] = fmaf((x[i][j] - mean) * rstd, 1.0f + sc[j], sh[j]);
+    if (OUT == 0) store8(static_cast<AT*>(p.h_out) + row * D + e, x[i]);
+  }
+
+  if (OUT == 1) {
+    for (int t = 0; t < p.T; ++t) {
+      const float* w = p.Wh + (int64_t)t * D;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float wv[8];
+        load8(w + (i * 32 + lane) * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(x[i][j], wv[j], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float v = acc + p.bh[t];
+        if (p.v_out) p.v_out[row * p.T + t] = v;
+        if (p.xt_out) p.xt_out[row * p.T + t] = __fadd_rn(__fmul_rn(v, p.dt), p.xt_in[row * p.T + t]);
+      }
+    }
+  }
+}
+
+template <typename AT, int VPL>
+int launch_row_vpl(const RowParams& p, bool has_prev, int out, cudaStream_t stream) {
+  const unsigned grid = (unsigned)ceil_div(p.M, WARPS);
+  if (has_prev && out == 0) row_kernel<AT, VPL, true, 0><<<grid, THREADS, 0, stream>>>(p);
+  else if (has_prev && out == 1) row_kernel<AT, VPL, true, 1><<<grid, THREADS, 0, stream>>>(p);
+  else if (!has_prev && out == 0) row_kernel<AT, VPL, false, 0><<<grid, THREADS, 0, stream>>>(p);
+  else row_kernel<AT, VPL, false, 1><<<grid, THREADS, 0, stream>>>(p);
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
+template <typename AT>
+int launch_row(const RowParams& p, bool has_prev, int out, cudaStream_t stream) {
+  if (p.M <= 0) return NOVA_OK;
+  switch (p.D / 256) {
+    case 1: return launch_row_vpl<AT, 1>(p, has_prev, out, stream);
+    case 2: return launch_row_vpl<AT, 2>(p, has_prev, out, stream);
+    case 3: return launch_row_vpl<AT, 3>(p, has_prev, out, stream);
+    case 4: return launch_row_vpl<AT, 4>(p, has_prev, out, stream);
+    case 5: return launch_row_vpl<AT, 5>(p, has_prev, out, stream);
+    case 6: return launch_row_vpl<AT, 6>(p, has_prev, out, stream);
+    case 7: return launch_row_vpl<AT, 7>(p, has_prev, out, stream);
+    case 8: return launch_row_vpl<AT, 8>(p, has_prev, out, stream);
+    default: break;
+  }
+  set_error("unsupported head width %d (multiple of 256, <= 2048)", p.D);
+  return NOVA_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------ latent bookkeeping
+// Guided Euler update over one cloud per CTA (needs per-cloud norms for renorm):
+//   v = vu + (vc - vu) * s;  v *= clamp(|vc| / |v|, renorm, 1) if renorm < 1;  x += dt * v
+// vc = v2[b], vu = v2[B + b], each [n*T]; x_sel [B, n*T].
+static __global__ void __launch_bounds__(256)
+cfg_euler_kernel(const float* __restrict__ v2, float* __restrict__ x_sel, int64_t B, int64_t len, float scale,
+                 float renorm, float dt) {
+  __shared__ float red[2][8];
+  const int64_t b = blockIdx.x;
+  const float* vc = v2 + b * len;
+  const float* vu = v2 + (B + b) * len;
+  float* x = x_sel + b * len;
+  float ratio = 1.0f;
+  if (renorm < 1.0f) {
+    float sc = 0.f, sv = 0.f;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+      const float c = vc[i], u = vu[i];
+      const float v = fmaf(c - u, scale, u);
+      sc = fmaf(c, c, sc);
+      sv = fmaf(v, v, sv);
+    }
+    sc = warp_sum(sc);
+    sv = warp_sum(sv);
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = sc;
+      red[1][threadIdx.x >> 5] = sv;
+    }
+    __syncthreads();
+    float tc = 0.f, tv = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      tc += red[0][w];
+      tv += red[1][w];
+    }
+    ratio = fminf(fmaxf(sqrtf(tc) / sqrtf(tv), renorm), 1.0f);
+  }
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+    const float c = vc[i], u = vu[i];
+    const float v = fmaf(c - u, scale, u) * ratio;
+    x[i] = __fadd_rn(__fmul_rn(v, dt), x[i]);
+  }
+}
+
+// out[b, tok, :] for predicted tokens <- x_sel;  (pred_ids == nullptr: plain copy)
+static __global__ void
+scatter_tok_kernel(const float* __restrict__ x_sel, const int64_t* __restrict__ ids,
+                                   float* __restrict__ out, int64_t Bx, int64_t N, int64_t n, int T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bx * n * T) return;
+  const int64_t row = i / T, c = i % T;
+  const int64_t b = row / n;
+  const int64_t tok = ids ? ids[row] : row % n;
+  out[(b * N + tok) * T + c] = x_sel[i];
+}
+// Tokens outside pred_ids: the head returns its own input there, so the reference's loop
+// does x <- x*dt + x every step (two roundings); reproduce that recurrence exactly.
+static __global__ void
+unpredicted_kernel(const float* __restrict__ noise, float* __restrict__ out, int64_t numel,
+                                   const float* __restrict__ dts, int S) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  float x = noise[i];
+  for (int s = 0; s < S; ++s) x = __fadd_rn(__fmul_rn(x, dts[s]), x);
+  out[i] = x;
+}
+
+template <typename T>
+__global__ void euler_kernel(const T* __restrict__ v, const T* __restrict__ x, T* __restrict__ out, int64_t numel,
+                             float dt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  // model_output.mul(dt).add_(sample): the product is rounded to the tensor dtype first.
+  const T prod = from_float<T>(__fmul_rn(to_float(v[i]), dt));
+  out[i] = from_float<T>(__fadd_rn(to_float(prod), to_float(x[i])));
+}
+
+// fp32 -> AT / permuting copies used when packing weights
+template <typename TS, typename TD>
+__global__ void convert_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t numel) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < numel) dst[i] = from_float<TD>(to_float(src[i]));
+}
+// Conv2d weight (D, C, p, p) -> token order (D, p, p, C)
+template <typename TS>
+__global__ void permute_patch_kernel(const TS* __restrict__ src, float* __restrict__ dst, int D, int C, int p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = C * p * p;
+  if (i >= (int64_t)D * T) return;
+  const int d = static_cast<int>(i / T), r = static_cast<int>(i % T);
+  const int c = r % C, pw = (r / C) % p, ph = r / (C * p);
+  dst[i] = to_float(src[((int64_t)(d * C + c) * p + ph) * p + pw]);
+}
+
+}  // namespace rw
+}  // namespace nova

@@ -1,0 +1,161 @@
+// Library runtime: error string, launch counter, device check, TMA tensor-map encoding,
+// the host-mapped debug words of the tcgen05 kernels, and the small C-ABI entry points.
+#include <cuda.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tcgen05.cuh"
+#include "rowwise.cuh"
+
+namespace nova {
+
+static thread_local char g_error[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+namespace tc {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return NOVA_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld K=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)K, (long long)ld);
+    return NOVA_ERR_CUDA;
+  }
+  return NOVA_OK;
+}
+
+uint32_t* debug_word() {
+  static uint32_t* dev = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    uint32_t* host = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host), 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess) {
+      std::memset(host, 0, 4 * sizeof(uint32_t));
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host, 0) != cudaSuccess) dev = nullptr;
+      g_debug_host = host;
+    }
+  });
+  return dev;
+}
+uint32_t* g_debug_host = nullptr;
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace tc
+}  // namespace nova
+
+using namespace nova;
+
+extern "C" const char* nova_last_error(void) { return g_error; }
+extern "C" int nova_abi_version(void) { return NOVA_B200_ABI_VERSION; }
+extern "C" int64_t nova_launch_count(void) { return g_launches; }
+extern "C" void nova_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int nova_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  NOVA_CHECK_CUDA(cudaGetDevice(&dev));
+  NOVA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  NOVA_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    set_error("libnova_b200 is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+    return NOVA_ERR_DEVICE;
+  }
+  return NOVA_OK;
+}
+
+// Debug words of the last tcgen05 barrier timeout: [0] = 0xDEAD0000 | code, [1] = block, [2] = parity.
+extern "C" int nova_debug_words(uint32_t* out4) {
+  if (!out4) return NOVA_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) out4[i] = tc::g_debug_host ? tc::g_debug_host[i] : 0u;
+  return NOVA_OK;
+}
+
+extern "C" int nova_euler_step(const void* model_output, const void* sample, double dt, void* prev, int64_t numel,
+                               int32_t dtype, void* stream) {
+  NOVA_REQUIRE(model_output && sample && prev && numel >= 0, "nova_euler_step: bad arguments");
+  if (numel == 0) return NOVA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)ceil_div(numel, 256);
+  // dt is a Python float in the reference; torch multiplies a tensor by a Python scalar after
+  // converting the scalar to the tensor's opmath type (fp32 for both fp32 and bf16 tensors).
+  const float dtf = static_cast<float>(dt);
+  if (dtype == NOVA_F32)
+    rw::euler_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(model_output),
+                                                 static_cast<const float*>(sample), static_cast<float*>(prev), numel, dtf);
+  else if (dtype == NOVA_BF16)
+    rw::euler_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(model_output), static_cast<const bf16*>(sample),
+                                                static_cast<bf16*>(prev), numel, dtf);
+  else {
+    set_error("nova_euler_step: unknown dtype %d", dtype);
+    return NOVA_ERR_INVALID;
+  }
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
+extern "C" int nova_debug_gemm(const void* A, const void* W, const float* bias, void* C, int64_t M, int64_t N, int64_t K,
+                               int32_t dtype, int32_t impl, int32_t epilogue, void* stream) {
+  NOVA_REQUIRE(A && W && C && M >= 0 && N >= 0 && K > 0, "nova_debug_gemm: bad arguments");
+  NOVA_REQUIRE(epilogue == EPI_BIAS || epilogue == EPI_BIAS_SILU, "nova_debug_gemm: unknown epilogue %d", epilogue);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == NOVA_F32) {
+    NOVA_REQUIRE(impl == 0, "nova_debug_gemm: fp32 runs on the SIMT kernel only");
+    return simt::launch<float, float, true>(static_cast<const float*>(A), K, static_cast<const float*>(W), K, bias,
+                                            static_cast<float*>(C), N, (int)M, (int)N, (int)K, epilogue, s);
+  }
+  NOVA_REQUIRE(dtype == NOVA_BF16, "nova_debug_gemm: unknown dtype %d", dtype);
+  if (impl == 0)
+    return simt::launch<bf16, bf16, false>(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, bias,
+                                           static_cast<bf16*>(C), N, (int)M, (int)N, (int)K, epilogue, s);
+  NOVA_PROPAGATE(nova_device_check());
+  return tc::launch(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, bias, static_cast<bf16*>(C), N,
+                    (int)M, (int)N, (int)K, epilogue, s);
+}

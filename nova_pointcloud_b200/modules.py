@@ -1,0 +1,165 @@
+"""Drop-in module surface of the reference's diffusion head, backed by libnova_b200.so.
+
+``DiffusionMLP(depth, embed_dim, cond_dim, patch_size=2, image_dim=4)`` keeps the
+reference's constructor, ``forward(x, timestep, z, pred_ids=None)`` signature, sub-module
+names and therefore its ``state_dict`` key set (14 + 8*depth keys), so a
+reference checkpoint loads unchanged (/root/reference/diffnext/models/diffusion_mlp.py:78-99).
+The sub-modules below only *hold parameters* in the reference's layout and initialise them
+like the reference does (torch defaults, same construction order => same draws for a given
+seed); all arithmetic runs in the CUDA library through ``torch.ops.nova_b200``.  There is
+no eager fallback: on a CPU tensor ``forward`` raises.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import NovaError
+
+
+class PatchEmbed(nn.Module):
+    """Parameter holder + layout helpers of the reference PatchEmbed (embeddings.py:139-166)."""
+
+    def __init__(self, image_dim, embed_dim, patch_size):
+        super().__init__()
+        self.height = self.width = None
+        self.image_dim, self.patch_size = image_dim, patch_size
+        self.proj = nn.Conv2d(image_dim, embed_dim, patch_size, patch_size)
+
+    @property
+    def hw(self) -> Tuple[int, int]:
+        return self.height, self.width
+
+    def set_hw(self, x: torch.Tensor):
+        if x.dim() == 4:
+            self.height, self.width = x.size(-2) // self.patch_size, x.size(-1) // self.patch_size
+
+    def patchify(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,C,H*p,W*p) -> (B,N,p*p*C), channel fastest (embeddings.py:152-154)."""
+        p = self.patch_size
+        x = x.reshape(-1, self.image_dim, self.height, p, self.width, p)
+        return x.permute(0, 2, 4, 3, 5, 1).flatten(1, 2).flatten(2, 4).contiguous()
+
+    def unpatchify(self, x: torch.Tensor) -> torch.Tensor:
+        """Inverse of :meth:`patchify` (embeddings.py:156-158)."""
+        p = self.patch_size
+        x = x.reshape(-1, self.height, self.width, p, p, self.image_dim)
+        return x.permute(0, 5, 1, 3, 2, 4).flatten(2, 3).flatten(3, 4).contiguous()
+
+
+class Projector(nn.Module):
+    """fc1 / fc2 parameter pair (diffusion_mlp.py:26-36)."""
+
+    def __init__(self, dim, mlp_dim=None, out_dim=None):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, mlp_dim or dim)
+        self.fc2 = nn.Linear(mlp_dim or dim, out_dim or dim)
+
+
+class AdaLayerNormZero(nn.Module):
+    """AdaLN-zero projection parameters (normalization.py:24-32); LayerNorm itself has none."""
+
+    def __init__(self, dim, rank=None, num_stats=2, eps=1e-6):
+        super().__init__()
+        if rank:
+            raise NovaError("low-rank AdaLN (rank != None) is not on the diffusion-head path")
+        self.proj = nn.Linear(dim, num_stats * dim)
+        self.num_stats, self.eps = num_stats, eps
+
+
+class DiffusionBlock(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dim, self.mlp_checkpointing = dim, False  # attribute poked by training pipelines
+        self.norm1 = AdaLayerNormZero(dim, num_stats=3, eps=1e-6)
+        self.proj, self.norm2 = Projector(dim, dim, dim), nn.LayerNorm(dim)
+
+
+class TimeCondEmbed(nn.Module):
+    def __init__(self, cond_dim, embed_dim, freq_dim=256):
+        super().__init__()
+        if freq_dim != 256:
+            raise NovaError("the CUDA head is built for freq_dim = 256 (the reference default)")
+        self.timestep_proj = Projector(freq_dim, embed_dim, embed_dim)
+        self.condition_proj = Projector(cond_dim, embed_dim, embed_dim)
+        self.freq_dim = freq_dim
+
+
+class DiffusionMLP(nn.Module):
+    """Diffusion MLP head; same surface as the reference class, CUDA-only arithmetic."""
+
+    def __init__(self, depth, embed_dim, cond_dim, patch_size=2, image_dim=4):
+        super().__init__()
+        self.patch_embed = PatchEmbed(image_dim, embed_dim, patch_size)
+        self.time_cond_embed = TimeCondEmbed(cond_dim, embed_dim)
+        self.blocks = nn.ModuleList(DiffusionBlock(embed_dim) for _ in range(depth))
+        self.norm = AdaLayerNormZero(embed_dim, num_stats=2, eps=1e-6)
+        self.head = nn.Linear(embed_dim, patch_size**2 * image_dim)
+        self.depth, self.embed_dim, self.cond_dim = depth, embed_dim, cond_dim
+        self.token_dim = patch_size**2 * image_dim
+        self._handle: Optional[ops.HeadHandle] = None
+        self._handle_key = None
+
+    # ------------------------------------------------------------------ handle management
+    def _weights_key(self):
+        ps = list(self.parameters())
+        return (ps[0].device, ps[0].dtype, tuple((p.data_ptr(), p._version) for p in ps))
+
+    def handle(self) -> ops.HeadHandle:
+        """The packed-weights handle for the parameters' current device / dtype / values.
+
+        Re-packed automatically after ``load_state_dict``, ``.to()`` or in-place updates.
+        """
+        key = self._weights_key()
+        if self._handle is None or key != self._handle_key:
+            device, dtype = key[0], key[1]
+            if device.type != "cuda":
+                raise NovaError("DiffusionMLP (nova_pointcloud_b200) runs on CUDA only: move the module to a B200 "
+                                "with .cuda(); there is no CPU implementation")
+            if self._handle is not None:
+                self._handle.close()
+            h = ops.HeadHandle(self.depth, self.embed_dim, self.cond_dim, self.token_dim, dtype, device)
+            h.load(self.state_dict(), channels=self.patch_embed.image_dim)
+            self._handle, self._handle_key = h, key
+        return self._handle
+
+    @property
+    def dtype(self):
+        return self.head.weight.dtype
+
+    @property
+    def device(self):
+        return self.head.weight.device
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, x, timestep, z, pred_ids=None) -> torch.Tensor:
+        """Velocity prediction (diffusion_mlp.py:89-99).
+
+        x: (B,C,H*p,W*p) image layout; timestep (B,) or (B,N); z (B,N,Dc); pred_ids (B,n,1) int64.
+        Returns (B,N,T) in the module dtype; with ``pred_ids`` the rows that are not listed
+        carry the patchified input, exactly like the reference's scatter into ``patchify(x)``.
+        """
+        if x.dim() != 4:
+            raise NovaError("pre-embedded (B,N,D) inputs are not supported: pass the (B,C,H*p,W*p) latent")
+        self.patch_embed.set_hw(x)
+        tok = self.patch_embed.patchify(x)
+        h = self.handle()
+        zz = z.to(self.dtype)
+        ids = None if pred_ids is None else pred_ids.reshape(pred_ids.shape[0], -1)
+        v = torch.ops.nova_b200.head_forward(tok.float(), timestep.float(), zz, ids, h.id).to(z.dtype)
+        if pred_ids is None:
+            return v
+        return tok.to(v.dtype).scatter(1, pred_ids.expand(-1, -1, v.size(-1)), v)
+
+    def sample_tokens(self, noise_tok, z, timesteps, sigmas, pred_ids=None, guidance_scale=1.0, guidance_trunc=0.0,
+                      guidance_renorm=1.0) -> torch.Tensor:
+        """Fused denoise loop on token layout: (Bx,N,T) fp32 noise -> (Bx,N,T) fp32 sample."""
+        h = self.handle()
+        ids = None if pred_ids is None else pred_ids.reshape(pred_ids.shape[0], -1)
+        return torch.ops.nova_b200.head_sample(noise_tok.float(), z.to(self.dtype), ids, h.id,
+                                               [float(t) for t in timesteps], [float(s) for s in sigmas],
+                                               float(guidance_scale), float(guidance_trunc), float(guidance_renorm))

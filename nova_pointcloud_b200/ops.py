@@ -1,0 +1,228 @@
+"""PyTorch custom ops (``torch.ops.nova_b200.*``) over the C ABI of libnova_b200.so.
+
+CUDA only by construction: the ops are registered for ``device_types="cuda"`` and there is no
+CPU, Triton or eager implementation behind them -- calling them on CPU tensors raises.
+torch supplies device memory and the current stream; all arithmetic happens in the library.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import NOVA_BF16, NOVA_F32, Guidance, HeadConfig, NovaError, check
+
+_DTYPES = {torch.float32: NOVA_F32, torch.bfloat16: NOVA_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class HeadHandle:
+    """Owner of one ``nova_head_t``: packed weights of a DiffusionMLP on one device."""
+
+    _registry: Dict[int, "HeadHandle"] = {}
+    _next_id = 1
+
+    def __init__(self, depth: int, width: int, cond_width: int, token_dim: int, dtype: torch.dtype, device):
+        if dtype not in _DTYPES:
+            raise NovaError(f"unsupported head dtype {dtype}; use torch.float32 or torch.bfloat16")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NovaError("nova_pointcloud_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.dtype = dtype
+        self.cfg = HeadConfig(depth, width, cond_width, token_dim, _DTYPES[dtype])
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().nova_head_create(C.byref(self.cfg), C.byref(self._h)), "nova_head_create")
+        self.id = HeadHandle._next_id
+        HeadHandle._next_id += 1
+        HeadHandle._registry[self.id] = self
+
+    @classmethod
+    def get(cls, hid: int) -> "HeadHandle":
+        try:
+            return cls._registry[hid]
+        except KeyError:
+            raise NovaError(f"unknown head handle {hid}") from None
+
+    def load(self, state_dict: Dict[str, torch.Tensor], channels: int):
+        """Pack a reference-layout ``state_dict`` (any float dtype, any device) into the handle."""
+        names, keep = [], []
+        src_dtype = torch.bfloat16 if all(v.dtype == torch.bfloat16 for v in state_dict.values()) else torch.float32
+        for k, v in state_dict.items():
+            names.append(k.encode())
+            keep.append(v.detach().to(device=self.device, dtype=src_dtype).contiguous())
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in keep])
+        c_numels = (C.c_int64 * n)(*[t.numel() for t in keep])
+        with torch.cuda.device(self.device):
+            check(_lib.lib().nova_head_load(self._h, n, c_names, c_ptrs, c_numels, _DTYPES[src_dtype], channels,
+                                            _stream()), "nova_head_load")
+            torch.cuda.current_stream().synchronize()  # `keep` may be freed after this returns
+
+    def workspace(self, rows: int, steps: int) -> torch.Tensor:
+        nbytes = _lib.lib().nova_head_workspace_bytes(self._h, rows, steps)
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+
+    def close(self):
+        if self._h:
+            _lib.lib().nova_head_destroy(self._h)
+            self._h = C.c_void_p()
+        HeadHandle._registry.pop(self.id, None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _check_inputs(h: HeadHandle, x_tok, z, pred_ids):
+    T, Dc = h.cfg.token_dim, h.cfg.cond_width
+    if x_tok.dim() != 3 or x_tok.shape[-1] != T:
+        raise NovaError(f"x_tok must be (Bx, N, {T}); got {tuple(x_tok.shape)}")
+    if z.dim() != 3 or z.shape[-1] != Dc or z.shape[1] != x_tok.shape[1]:
+        raise NovaError(f"z must be (B, N={x_tok.shape[1]}, {Dc}); got {tuple(z.shape)}")
+    if z.dtype != h.dtype:
+        raise NovaError(f"z dtype {z.dtype} does not match the head's {h.dtype}")
+    if pred_ids is not None and (pred_ids.dim() != 2 or pred_ids.shape[0] != z.shape[0] or pred_ids.dtype != torch.int64):
+        raise NovaError(f"pred_ids must be int64 (B={z.shape[0]}, n); got {tuple(pred_ids.shape)} {pred_ids.dtype}")
+
+
+@torch.library.custom_op("nova_b200::head_forward", mutates_args=(), device_types="cuda")
+def head_forward(x_tok: torch.Tensor, t: torch.Tensor, z: torch.Tensor, pred_ids: Optional[torch.Tensor],
+                 handle: int) -> torch.Tensor:
+    """Velocity of the selected tokens, (B, n, T) fp32.  See nova_head_forward in nova_b200.h."""
+    h = HeadHandle.get(handle)
+    _check_inputs(h, x_tok, z, pred_ids)
+    x_tok = x_tok.contiguous().float()
+    z = z.contiguous()
+    t = t.contiguous().float()
+    B, N = z.shape[0], z.shape[1]
+    Bx = x_tok.shape[0]
+    n = N if pred_ids is None else pred_ids.shape[1]
+    per_token = 1 if t.dim() == 2 else 0
+    if per_token and tuple(t.shape) != (B, n):
+        raise NovaError(f"per-token timesteps must be (B, n)=({B}, {n}); got {tuple(t.shape)}")
+    if not per_token and t.numel() != B:
+        raise NovaError(f"timestep must have B={B} entries; got {tuple(t.shape)}")
+    ids = None if pred_ids is None else pred_ids.contiguous()
+    out = torch.empty(B, n, h.cfg.token_dim, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        ws = h.workspace(B * n, 0)
+        check(_lib.lib().nova_head_forward(h._h, _ptr(x_tok), _ptr(t), per_token, _ptr(z), _ptr(ids), B, Bx, N, n,
+                                           _ptr(out), _ptr(ws), ws.numel(), _stream()), "nova_head_forward")
+    return out
+
+
+@head_forward.register_fake
+def _(x_tok, t, z, pred_ids, handle):
+    n = z.shape[1] if pred_ids is None else pred_ids.shape[1]
+    return x_tok.new_empty((z.shape[0], n, x_tok.shape[-1]), dtype=torch.float32)
+
+
+@torch.library.custom_op("nova_b200::head_sample", mutates_args=(), device_types="cuda")
+def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[torch.Tensor], handle: int,
+                timesteps: Sequence[float], sigmas: Sequence[float], guidance_scale: float, guidance_trunc: float,
+                guidance_renorm: float) -> torch.Tensor:
+    """The fused S-step denoise loop, (Bx, N, T) fp32.  See nova_head_sample in nova_b200.h."""
+    h = HeadHandle.get(handle)
+    _check_inputs(h, noise_tok, z, pred_ids)
+    S = len(timesteps)
+    if len(sigmas) != S + 1:
+        raise NovaError(f"sigmas must have len(timesteps)+1 = {S + 1} entries; got {len(sigmas)}")
+    noise_tok = noise_tok.contiguous().float()
+    z = z.contiguous()
+    B, N = z.shape[0], z.shape[1]
+    Bx = noise_tok.shape[0]
+    n = N if pred_ids is None else pred_ids.shape[1]
+    ids = None if pred_ids is None else pred_ids.contiguous()
+    c_t = (C.c_float * max(S, 1))(*[float(v) for v in timesteps])
+    c_s = (C.c_double * (S + 1))(*[float(v) for v in sigmas])
+    g = Guidance(float(guidance_scale), float(guidance_trunc), float(guidance_renorm))
+    out = torch.empty(Bx, N, h.cfg.token_dim, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        ws = h.workspace(B * n, S)
+        check(_lib.lib().nova_head_sample(h._h, _ptr(noise_tok), _ptr(z), _ptr(ids), B, Bx, N, n, c_t, c_s, S,
+                                          C.byref(g), _ptr(out), _ptr(ws), ws.numel(), _stream()), "nova_head_sample")
+    return out
+
+
+@head_sample.register_fake
+def _(noise_tok, z, pred_ids, handle, timesteps, sigmas, guidance_scale, guidance_trunc, guidance_renorm):
+    return noise_tok.new_empty(noise_tok.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("nova_b200::euler_step", mutates_args=(), device_types="cuda")
+def euler_step(model_output: torch.Tensor, sample: torch.Tensor, dt: float) -> torch.Tensor:
+    """prev = model_output * dt + sample with the reference's two roundings (scheduling_cfm.py:136)."""
+    if model_output.dtype not in _DTYPES or sample.dtype != model_output.dtype or sample.shape != model_output.shape:
+        raise NovaError("euler_step: model_output and sample must share shape and be both fp32 or both bf16")
+    v, x = model_output.contiguous(), sample.contiguous()
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        check(_lib.lib().nova_euler_step(_ptr(v), _ptr(x), float(dt), _ptr(out), v.numel(), _DTYPES[v.dtype], _stream()),
+              "nova_euler_step")
+    return out
+
+
+@euler_step.register_fake
+def _(model_output, sample, dt):
+    return torch.empty_like(model_output)
+
+
+@torch.library.custom_op("nova_b200::chamfer_nn", mutates_args=(), device_types="cuda")
+def chamfer_nn(a: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Nearest-neighbour distances both ways: (d1 (B,N), d2 (B,M), idx1 int32, idx2 int32)."""
+    if a.dim() != 3 or b.dim() != 3 or a.shape[-1] != 3 or b.shape[-1] != 3 or a.shape[0] != b.shape[0]:
+        raise NovaError(f"chamfer_nn expects (B,N,3) and (B,M,3); got {tuple(a.shape)} and {tuple(b.shape)}")
+    a, b = a.contiguous().float(), b.contiguous().float()
+    B, N, M = a.shape[0], a.shape[1], b.shape[1]
+    d1 = torch.empty(B, N, dtype=torch.float32, device=a.device)
+    d2 = torch.empty(B, M, dtype=torch.float32, device=a.device)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=a.device)
+    i2 = torch.empty(B, M, dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.lib().nova_chamfer_nn(_ptr(a), _ptr(b), B, N, M, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2), _stream()),
+              "nova_chamfer_nn")
+    return d1, d2, i1, i2
+
+
+@chamfer_nn.register_fake
+def _(a, b):
+    B, N, M = a.shape[0], a.shape[1], b.shape[1]
+    return (a.new_empty((B, N), dtype=torch.float32), a.new_empty((B, M), dtype=torch.float32),
+            a.new_empty((B, N), dtype=torch.int32), a.new_empty((B, M), dtype=torch.int32))
+
+
+def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: str, epilogue: str) -> torch.Tensor:
+    """Test hook over nova_debug_gemm: epi(A W^T + bias) with the named GEMM kernel."""
+    impl_id = {"simt": 0, "tcgen05": 1}[impl]
+    epi_id = {"bias": _lib.EPI_BIAS, "bias_silu": _lib.EPI_BIAS_SILU}[epilogue]
+    A, W = A.contiguous(), W.contiguous()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    b = None if bias is None else bias.contiguous().float()
+    with torch.cuda.device(A.device):
+        check(_lib.lib().nova_debug_gemm(_ptr(A), _ptr(W), _ptr(b), _ptr(out), M, N, K, _DTYPES[A.dtype], impl_id, epi_id,
+                                         _stream()), "nova_debug_gemm")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().nova_launch_count())
+
+
+def launch_count_reset():
+    _lib.lib().nova_launch_count_reset()

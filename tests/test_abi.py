@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/nova_b200.h declares;
+the product surface refuses to run without CUDA (no CPU fallback)."""
+
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nova_b200.h")).read()
+    return sorted(set(re.findall(r"NOVA_API[^;(]*?\b(nova_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nova_pointcloud_b200 import _lib
+
+    lib = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 16
+    assert sorted(_lib.EXPORTS) == names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.nova_abi_version() == 1
+
+
+def test_header_has_no_torch_or_cxx_types():
+    text = open(os.path.join(ROOT, "include", "nova_b200.h")).read()
+    assert "torch" not in text.lower().replace("pytorch", "") and "std::" not in text and "at::" not in text
+
+
+def test_sass_is_blackwell_native():
+    """The shipped library carries tcgen05 / TMA / TMEM instructions (B200_PROFILING.md evidence table)."""
+    import shutil
+    import subprocess
+
+    from nova_pointcloud_b200 import _lib
+
+    _lib.lib()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_fails_loudly_without_cuda():
+    import nova_pointcloud_b200 as nb
+
+    head = nb.DiffusionMLP(1, 256, 64, patch_size=1, image_dim=3)
+    with pytest.raises(nb.NovaError):
+        head(torch.zeros(1, 3, 4, 1), torch.zeros(1), torch.zeros(1, 4, 64))
+    with pytest.raises(NotImplementedError):
+        torch.ops.nova_b200.chamfer_nn(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    with pytest.raises(nb.NovaError):
+        nb.chamfer_distance(torch.zeros(4, 3), torch.zeros(4, 3))
+    with pytest.raises(NotImplementedError):
+        torch.ops.nova_b200.euler_step(torch.zeros(4), torch.zeros(4), 0.1)
+
+
+def test_product_does_not_import_oracle():
+    """oracle/ is test infrastructure: nothing in the package may reference it."""
+    pkg = os.path.join(ROOT, "nova_pointcloud_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

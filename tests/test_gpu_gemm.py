@@ -1,0 +1,70 @@
+"""GPU: the GEMM kernels alone (SIMT fp32/bf16 and tcgen05 bf16) against torch matmul, through
+the C ABI's nova_debug_gemm.  Ragged M/N/K exercise TMA out-of-bounds zero fill and masking."""
+
+import pytest
+import torch
+
+from gpu_util import relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_gemm(A, W, bias, epi):
+    out = A.float() @ W.float().t()
+    if bias is not None:
+        out = out + bias.float()
+    return torch.nn.functional.silu(out) if epi == "bias_silu" else out
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (130, 70, 100), (257, 513, 256)])
+@pytest.mark.parametrize("epi", ["bias", "bias_silu"])
+def test_simt_fp32(M, N, K, epi):
+    from nova_pointcloud_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K**0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = ops.debug_gemm(A, W, b, "simt", epi)
+    ref = ref_gemm(A.double(), W.double(), b.double(), epi) if False else ref_gemm(A, W, b, epi)
+    assert relmax(out, ref.double() if False else ref) < 2e-6
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("M,N,K", [
+    (128, 256, 64),       # exactly one tile, one k-block
+    (128, 256, 256),      # 4 k-blocks: the full smem ring once
+    (128, 256, 1024),     # ring wraps 4 times (phase bits)
+    (256, 512, 512),      # 4 tiles
+    (1000, 768, 768),     # ragged M
+    (300, 200, 104),      # ragged everything, K not a multiple of 64
+    (20000, 1024, 256),   # more tiles than SMs: persistent loop + TMEM double buffering
+    (64, 15360, 768),     # N = 20 D of the AdaLN GEMM
+])
+@pytest.mark.parametrize("epi", ["bias", "bias_silu"])
+def test_bf16_gemm(impl, M, N, K, epi):
+    from nova_pointcloud_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    out = ops.debug_gemm(A, W, b, impl, epi)
+    torch.cuda.synchronize()
+    ref = ref_gemm(A, W, b, epi)
+    # bf16 output rounding: 2^-9 relative per element
+    err = (out.float() - ref).abs()
+    tol = 2.0**-8 * ref.abs() + 1e-2
+    assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
+
+
+def test_tcgen05_no_bias_and_repeatability():
+    from nova_pointcloud_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(512, 512, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(768, 512, device="cuda", generator=g) / 512**0.5).bfloat16()
+    o1 = ops.debug_gemm(A, W, None, "tcgen05", "bias")
+    o2 = ops.debug_gemm(A, W, None, "tcgen05", "bias")
+    assert torch.equal(o1, o2)
+    assert relmax(o1.float(), A.float() @ W.float().t()) < 1e-2
