@@ -3,7 +3,8 @@
 //   A, W : bf16, K-major (row-major with K contiguous) -- nn.Linear's (out,in) weight is
 //          already the K-major "B" operand, activations are the K-major "A" operand.
 //   acc  : fp32 in tensor memory, double buffered (2 x 256 columns = all 512 TMEM columns)
-//   C    : bf16, written straight from registers (each epilogue thread owns one row).
+//   C    : bf16, staged per epilogue warp in swizzled shared memory and written by TMA stores
+//          (full 128 B lines, out-of-bounds rows/columns clipped by the tensor map).
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0    TMA producer   (one lane): cp.async.bulk.tensor 2D loads, 128B swizzle,
@@ -11,7 +12,8 @@
 //   warp 1    MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16,
 //                            tcgen05.commit releases smem stages / publishes accumulators
 //   warp 2    TMEM allocator (tcgen05.alloc / dealloc)
-//   warps 4-7 epilogue       tcgen05.ld 32x32b -> bias (+SiLU) -> bf16 -> global
+//   warps 4-7 epilogue       tcgen05.ld 32x32b -> bias (+SiLU) -> bf16 -> st.shared (128B swizzle)
+//                            -> cp.async.bulk.tensor store of 32 x 64 sub-tiles, double buffered
 //
 // Every mbarrier wait is bounded: on timeout the kernel records where it was stuck in a
 // host-mapped debug word and traps, so a protocol bug surfaces as a CUDA error, not a hang.
@@ -32,7 +34,12 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int C_CHUNK = 64;                                   // output columns per TMA store (128 B rows)
+constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;                  // one warp's 32 x 64 bf16 sub-tile: 4 KB
+constexpr int OFF_CSTAGE = STAGES * STAGE_BYTES;               // 4 warps x 2 buffers x 4 KB
+constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;     // 2 x BN fp32 bias tiles
+constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256;                      // 231 680 B <= 227 KB
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -108,6 +115,25 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* t, uint32_t bar, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(t)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2D tiled TMA store (shared -> global), bulk-group completion; out-of-bounds parts are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(t)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
                : "memory");
@@ -166,26 +192,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 
 struct EpiParams {
   const float* bias;  // [N] or nullptr
-  bf16* C;
-  int64_t ldc;
   int M, N, K;
 };
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const EpiParams p, uint32_t* dbg) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+            const __grid_constant__ CUtensorMap tmap_c, const EpiParams p, uint32_t* dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = smem_raw;
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) {
+    if (dbg && threadIdx.x == 0) { dbg[0] = 0xDEAD0A11u; dbg[1] = base; __threadfence_system(); }
+    __trap();
+  }
+  const uint32_t bar_base = base + OFF_BAR;
   // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
@@ -195,6 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -259,48 +287,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int buf = 0;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access == its 32-row slice of the tile
+    const int tid_e = threadIdx.x - EPI_WARP0 * 32;
+    const uint32_t cbuf = base + OFF_CSTAGE + static_cast<uint32_t>(q) * 2u * C_BUF_BYTES;
+    float* bias_all = reinterpret_cast<float*>(smem + OFF_BIAS);
+    int buf = 0, cpar = 0, it = 0;
     uint32_t buf_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_idx = (tile / num_n) * BM, n_idx = (tile % num_n) * BN;
+      float* bias_s = bias_all + (it & 1) * BN;
+      for (int j = tid_e; j < BN; j += 128)
+        bias_s[j] = (p.bias != nullptr && n_idx + j < p.N) ? __ldg(p.bias + n_idx + j) : 0.f;
+      epi_bar_sync();  // bias tile visible to the 4 epilogue warps (double buffered across tiles)
       mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf);
       tcgen05_fence_after();
-      const int row = m_idx + q * 32 + lane;
+      const int m0 = m_idx + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-      bf16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
+      for (int cc = 0; cc < BN / C_CHUNK; ++cc) {
+        const int n0 = n_idx + cc * C_CHUNK;
+        if (m0 >= p.M || n0 >= p.N) break;  // warp-uniform: nothing of this sub-tile is in bounds
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_row + cc * C_CHUNK, ra);
+        tmem_ld_32x32(t_row + cc * C_CHUNK + 32, rb);
+        if (lane == 0) tma_store_wait_read<1>();  // the store that last used this staging buffer has read it
+        __syncwarp();
         tmem_ld_wait();
-        const int n0 = n_idx + c * 32;
-        if (row < p.M && n0 < p.N) {
+        const uint32_t dst = cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
+        const float* bs = bias_s + cc * C_CHUNK;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns -> one 16 B store each
-            float v[8];
+        for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks of this thread's 128 B row, XOR-swizzled
+          uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int n = n0 + g * 8 + j;
-              float x = __uint_as_float(r[g * 8 + j]);
-              if (p.bias != nullptr && n < p.N) x += __ldg(p.bias + n);
-              if (EPI == EPI_BIAS_SILU) x = silu(x);
-              v[j] = x;
-            }
-            const int n = n0 + g * 8;
-            if (n + 8 <= p.N) {
-              store8(crow + n, v);
-            } else {
-              for (int j = 0; j < 8 && n + j < p.N; ++j) crow[n + j] = __float2bfloat16_rn(v[j]);
-            }
+          for (int h = 0; h < 4; ++h) {
+            const int e = c * 8 + 2 * h;  // compile-time after unrolling: picks ra or rb statically
+            float x0 = __uint_as_float(e < 32 ? ra[e & 31] : rb[e & 31]) + bs[e];
+            float x1 = __uint_as_float(e < 32 ? ra[(e + 1) & 31] : rb[(e + 1) & 31]) + bs[e + 1];
+            if (EPI == EPI_BIAS_SILU) { x0 = silu(x0); x1 = silu(x1); }
+            w[h] = pack_bf16x2(x0, x1);
           }
+          st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
         }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_c, cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES, n0, m0);
+          tma_store_commit();
+        }
+        cpar ^= 1;
       }
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(buf));
+      mbar_arrive(tempty_bar(buf));  // all tcgen05.ld of this accumulator have completed
       if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
     }
+    if (lane == 0) tma_store_wait_read<0>();  // staging memory must outlive the last stores' reads
   }
+  __syncwarp();  // lanes of the single-lane roles reconverge before the CTA-wide barrier
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -313,6 +355,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // K-major bf16 matrix [rows, K] with row stride ld (elements) -> 2D tiled map, 128 B swizzle,
 // box = {64 elements of K, box_rows}.  Out-of-bounds elements are zero-filled by TMA.
 int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows);
+// The same encoding serves the output: [M, N] row-major, box = {64 columns, 32 rows} per TMA store.
 uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (device pointer)
 extern uint32_t* g_debug_host;  // the same words, host pointer
 int num_sms();
@@ -325,13 +368,14 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
     NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc_;
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
   NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, BN));
-  EpiParams p{bias, C, ldc, M, N, K};
+  NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, N, ldc, 32));
+  EpiParams p{bias, M, N, K};
   const int tiles = static_cast<int>(ceil_div(M, BM) * ceil_div(N, BN));
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, debug_word());
+  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc_, p, debug_word());
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }

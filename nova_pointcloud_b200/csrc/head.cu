@@ -93,7 +93,8 @@ Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
   w.xsel = static_cast<float*>(cv.take(M * h->T() * sizeof(float)));
   w.thid = static_cast<float*>(cv.take(R * D * sizeof(float)));
   w.temb = static_cast<float*>(cv.take(R * D * sizeof(float)));
-  w.tdev = static_cast<float*>(cv.take(R * sizeof(float)));
+  // times [MAX_STEPS] | per-cloud sumsq [<= M] | per-step per-cloud renorm ratios [steps * M]
+  w.tdev = static_cast<float*>(cv.take((R + MAX_STEPS + M * (static_cast<size_t>(steps) + 1)) * sizeof(float)));
   w.bytes = cv.off;
   return w;
 }
@@ -163,15 +164,13 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   const int64_t M = io.M;
   if (M <= 0) return NOVA_OK;
   {
-    const int64_t nvec = M * (D / 8);
+    const unsigned grid = (unsigned)ceil_div(M, rw::WARPS);
     if (h->cfg.dtype == NOVA_F32)
-      rw::prep_kernel<AT, true><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(
-          static_cast<const AT*>(w.c), w.temb, io.rows_per_t, io.t_offset, io.x_tok, io.x_rows, h->w_patch, h->b_patch,
-          static_cast<AT*>(w.a), static_cast<AT*>(w.x), M, D, T);
+      rw::prep_kernel<AT, true><<<grid, rw::THREADS, 0, s>>>(static_cast<const AT*>(w.c), w.temb, io.rows_per_t,
+                                                             io.t_offset, static_cast<AT*>(w.a), M, D);
     else
-      rw::prep_kernel<AT, false><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(
-          static_cast<const AT*>(w.c), w.temb, io.rows_per_t, io.t_offset, io.x_tok, io.x_rows, h->w_patch, h->b_patch,
-          static_cast<AT*>(w.a), static_cast<AT*>(w.x), M, D, T);
+      rw::prep_kernel<AT, false><<<grid, rw::THREADS, 0, s>>>(static_cast<const AT*>(w.c), w.temb, io.rows_per_t,
+                                                              io.t_offset, static_cast<AT*>(w.a), M, D);
     NOVA_CHECK_LAUNCH();
   }
   const int n_ada = h->n_ada();
@@ -180,6 +179,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   rw::RowParams p{};
   p.M = M; p.D = D; p.T = T;
   p.x_in = w.x; p.x_out = w.x; p.u = w.u2; p.st = w.st; p.ldst = n_ada; p.h_out = w.h;
+  p.x_tok = io.x_tok; p.x_rows = io.x_rows; p.Wp = h->w_patch; p.bp = h->b_patch;
   p.Wh = h->w_head; p.bh = h->b_head;
   p.v_out = io.v_out; p.xt_in = io.x_tok; p.xt_out = io.xt_out; p.dt = io.dt;
   const int64_t final_off = static_cast<int64_t>(3) * depth * D;
@@ -260,15 +260,21 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   const bool guided = g != nullptr && g->scale > 1.0f;
   TimeList dts{};
   for (int i = 0; i < S; ++i) dts.v[i] = static_cast<float>(sigmas[i + 1] - sigmas[i]);
-  if (pred_ids && n < N) {  // tokens outside the set: x <- x*dt + x per step
+  const bool has_unpred = pred_ids != nullptr && n < N;
+  auto unpredicted = [&](const Workspace& wk, const float* ratios) -> int {
+    // tokens outside the set: x <- (ratio*x)*dt + x per step (ratio == 1 without guidance renorm)
     const int64_t numel = Bx * N * T;
-    Workspace w0 = carve(h, ws, M, S);
-    fill_times_kernel<<<1, MAX_STEPS, 0, s>>>(w0.tdev, dts, S);
+    fill_times_kernel<<<1, MAX_STEPS, 0, s>>>(wk.tdev, dts, S);
     NOVA_CHECK_LAUNCH();
-    rw::unpredicted_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, s>>>(noise_tok, x_out, numel, w0.tdev, S);
+    rw::unpredicted_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, s>>>(noise_tok, x_out, numel, N * T, Bx, wk.tdev,
+                                                                         ratios, S);
     NOVA_CHECK_LAUNCH();
+    return NOVA_OK;
+  };
+  if (M == 0) {
+    if (has_unpred) NOVA_PROPAGATE(unpredicted(carve(h, ws, M, S), nullptr));
+    return NOVA_OK;
   }
-  if (M == 0) return NOVA_OK;
   Workspace w = carve(h, ws, M, S);
   const AT* z_rows = z;
   if (pred_ids) {
@@ -287,6 +293,17 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(time_embedding(h, w.tdev, S, w, s));
   NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));  // hoisted: step-invariant
+  // renorm with pred_ids: the reference's norms include the unpredicted rows of the latent
+  // and the head output is scaled as a whole, so those rows and their norm evolve per cloud.
+  const bool renorm_extra = guided && g->renorm < 1.0f && has_unpred;
+  float* extra_sumsq = w.tdev + MAX_STEPS;     // [Bx]
+  float* ratios = w.tdev + MAX_STEPS + Bx;     // [S, Bx]
+  if (renorm_extra) {
+    rw::unpred_sumsq_kernel<<<(unsigned)Bx, 256, 0, s>>>(noise_tok, w.xsel, N * T, n * T, extra_sumsq);
+    NOVA_CHECK_LAUNCH();
+    rw::fill_kernel<<<(unsigned)ceil_div(Bx * S, 256), 256, 0, s>>>(ratios, Bx * S, 1.0f);
+    NOVA_CHECK_LAUNCH();
+  }
   bool active = guided;
   for (int i = 0; i < S; ++i) {
     if (active && g->trunc > 0.f && timesteps[i] < g->trunc) active = false;  // maybe_disable
@@ -300,7 +317,9 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
       io.M = M;
       io.v_out = w.v;
       NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
-      rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, s>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt);
+      rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, s>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt,
+                                                        renorm_extra ? extra_sumsq : nullptr,
+                                                        renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
       NOVA_CHECK_LAUNCH();
     } else {
       io.M = Mx;  // guidance off (or truncated): only the conditional rows run
@@ -308,6 +327,7 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
       NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
     }
   }
+  if (has_unpred) NOVA_PROPAGATE(unpredicted(w, renorm_extra ? ratios : nullptr));
   rw::scatter_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(w.xsel, pred_ids, x_out, Bx, N, n, T);
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;

@@ -90,44 +90,42 @@ gather_tok_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids
 }
 
 // ------------------------------------------------------------------ step prologue
-// a[m, :] = silu(c[m, :] + temb[tsel(m), :])            -> A operand of the AdaLN GEMM
-// x[m, :] = bp + Wp * x_tok[m % x_rows, :]               (PatchEmbed with K = T)
-// tsel(m) = (m / rows_per_t) * t_stride + t_offset
+// a[m, :] = silu(c[m, :] + temb[tsel(m), :])   -> A operand of the AdaLN GEMM;  one warp per row
+// tsel(m) = m / rows_per_t + t_offset
 template <typename AT, bool ACCURATE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(THREADS)
 prep_kernel(const AT* __restrict__ c, const float* __restrict__ temb, int64_t rows_per_t, int64_t t_offset,
-            const float* __restrict__ x_tok, int64_t x_rows, const float* __restrict__ Wp,
-            const float* __restrict__ bp, AT* __restrict__ a, AT* __restrict__ x, int64_t M, int D, int T) {
-  const int64_t vec_per_row = D / 8;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * vec_per_row) return;
-  const int64_t m = i / vec_per_row;
-  const int d0 = static_cast<int>(i % vec_per_row) * 8;
-  const float* te = temb + ((m / rows_per_t) + t_offset) * D + d0;
-  float cv[8], av[8], xv[8];
-  load8(c + m * D + d0, cv);
+            AT* __restrict__ a, int64_t M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
+  if (m >= M) return;
+  const float* te = temb + ((m / rows_per_t) + t_offset) * D;
+  const AT* cr = c + m * D;
+  AT* ar = a + m * D;
+  for (int e = lane * 8; e < D; e += 256) {
+    float cv[8], tv[8], av[8];
+    load8(cr + e, cv);
+    load8(te + e, tv);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float s = cv[j] + te[j];
-    av[j] = ACCURATE ? silu_accurate(s) : silu(s);
+    for (int j = 0; j < 8; ++j) {
+      const float s = cv[j] + tv[j];
+      av[j] = ACCURATE ? silu_accurate(s) : silu(s);
+    }
+    store8(ar + e, av);
   }
-  store8(a + m * D + d0, av);
-  const float* xt = x_tok + (m % x_rows) * T;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float acc = bp[d0 + j];
-    for (int t = 0; t < T; ++t) acc = fmaf(xt[t], Wp[(int64_t)(d0 + j) * T + t], acc);
-    xv[j] = acc;
-  }
-  store8(x + m * D + d0, xv);
 }
 
 // ------------------------------------------------------------------ the fused row kernel
 struct RowParams {
   int64_t M;
   int D, T;
-  const void* x_in;    // [M, D]   residual stream
-  void* x_out;         // [M, D]   (written when HAS_PREV)
+  const void* x_in;    // [M, D]   residual stream (HAS_PREV)
+  void* x_out;         // [M, D]   residual stream out
+  // !HAS_PREV: the residual stream starts as PatchEmbed(x_tok): x = bp + Wp x_tok[m % x_rows]
+  const float* x_tok;  // [x_rows, T]
+  int64_t x_rows;
+  const float* Wp;     // [D, T] token-order patch-embed weight
+  const float* bp;     // [D]
   const void* u;       // [M, D]   fc2 output of the finished block (HAS_PREV)
   const void* st;      // [M, ldst] all AdaLN statistics of this step
   int64_t ldst;
@@ -176,12 +174,32 @@ row_kernel(const RowParams p) {
   if (row >= p.M) return;
   const int D = p.D;
   const float inv_d = 1.0f / static_cast<float>(D);
-  const AT* xin = static_cast<const AT*>(p.x_in) + row * D;
   const AT* st = static_cast<const AT*>(p.st) + row * p.ldst;
 
   float x[VPL][8];
+  if (HAS_PREV) {
+    const AT* xin = static_cast<const AT*>(p.x_in) + row * D;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) load8(xin + (i * 32 + lane) * 8, x[i]);
+    for (int i = 0; i < VPL; ++i) load8(xin + (i * 32 + lane) * 8, x[i]);
+  } else {
+    // PatchEmbed with K = T (embeddings.py:146,165): too skinny for a GEMM, fused here
+    const float* xt = p.x_tok + (row % p.x_rows) * p.T;
+    AT* xout = static_cast<AT*>(p.x_out) + row * D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int e = (i * 32 + lane) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float acc = p.bp[e + j];
+        for (int t = 0; t < p.T; ++t) acc = fmaf(xt[t], p.Wp[(int64_t)(e + j) * p.T + t], acc);
+        x[i][j] = acc;
+      }
+      if (OUT == 0) {
+        store8(xout + e, x[i]);
+        load8(xout + e, x[i]);  // continue from the stored (rounded) residual, like every later block
+      }
+    }
+  }
 
   if (HAS_PREV) {
     const AT* uin = static_cast<const AT*>(p.u) + row * D;
@@ -274,9 +292,12 @@ int launch_row(const RowParams& p, bool has_prev, int out, cudaStream_t stream) 
 // Guided Euler update over one cloud per CTA (needs per-cloud norms for renorm):
 //   v = vu + (vc - vu) * s;  v *= clamp(|vc| / |v|, renorm, 1) if renorm < 1;  x += dt * v
 // vc = v2[b], vu = v2[B + b], each [n*T]; x_sel [B, n*T].
+// The reference takes the renorm norms over the head's full (N, T) output, in which tokens outside
+// pred_ids carry the latent itself for both passes (diffusion_mlp.py:99): `extra_sumsq[b] * extra_scale`
+// adds that contribution (sum of squares of the unpredicted latent rows at this step) to both norms.
 static __global__ void __launch_bounds__(256)
 cfg_euler_kernel(const float* __restrict__ v2, float* __restrict__ x_sel, int64_t B, int64_t len, float scale,
-                 float renorm, float dt) {
+                 float renorm, float dt, float* __restrict__ extra_sumsq, float* __restrict__ ratio_out) {
   __shared__ float red[2][8];
   const int64_t b = blockIdx.x;
   const float* vc = v2 + b * len;
@@ -303,12 +324,52 @@ cfg_euler_kernel(const float* __restrict__ v2, float* __restrict__ x_sel, int64_
       tc += red[0][w];
       tv += red[1][w];
     }
+    if (extra_sumsq != nullptr) {
+      tc += extra_sumsq[b];
+      tv += extra_sumsq[b];
+    }
     ratio = fminf(fmaxf(sqrtf(tc) / sqrtf(tv), renorm), 1.0f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // the reference scales the WHOLE head output by ratio, including the rows that only carry the
+      // latent: those rows then move as x <- x + dt*ratio*x, and so does their sum of squares.
+      if (extra_sumsq != nullptr) {
+        const float gr = 1.0f + dt * ratio;
+        extra_sumsq[b] *= gr * gr;
+      }
+      if (ratio_out != nullptr) ratio_out[b] = ratio;
+    }
   }
   for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
     const float c = vc[i], u = vu[i];
     const float v = fmaf(c - u, scale, u) * ratio;
     x[i] = __fadd_rn(__fmul_rn(v, dt), x[i]);
+  }
+}
+
+// extra[b] = sum(noise[b]^2 over all N*T) - sum(x_sel[b]^2 over the n*T selected), in double
+static __global__ void __launch_bounds__(256)
+unpred_sumsq_kernel(const float* __restrict__ noise, const float* __restrict__ x_sel, int64_t all_len,
+                    int64_t sel_len, float* __restrict__ extra) {
+  __shared__ double red[8];
+  const int64_t b = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < all_len; i += blockDim.x) {
+    const double v = noise[b * all_len + i];
+    acc += v * v;
+  }
+  for (int64_t i = threadIdx.x; i < sel_len; i += blockDim.x) {
+    const double v = x_sel[b * sel_len + i];
+    acc -= v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    extra[b] = static_cast<float>(t > 0.0 ? t : 0.0);
   }
 }
 
@@ -326,13 +387,23 @@ scatter_tok_kernel(const float* __restrict__ x_sel, const int64_t* __restrict__ 
 // Tokens outside pred_ids: the head returns its own input there, so the reference's loop
 // does x <- x*dt + x every step (two roundings); reproduce that recurrence exactly.
 static __global__ void
-unpredicted_kernel(const float* __restrict__ noise, float* __restrict__ out, int64_t numel,
-                                   const float* __restrict__ dts, int S) {
+unpredicted_kernel(const float* __restrict__ noise, float* __restrict__ out, int64_t numel, int64_t per_cloud,
+                   int64_t Bx, const float* __restrict__ dts, const float* __restrict__ ratios, int S) {
+  // With guidance renorm the head output (these rows included) is first scaled by the per-cloud
+  // ratio of that step: ratios[s * Bx + b]; nullptr means 1.
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= numel) return;
+  const int64_t b = i / per_cloud;
   float x = noise[i];
-  for (int s = 0; s < S; ++s) x = __fadd_rn(__fmul_rn(x, dts[s]), x);
+  for (int s = 0; s < S; ++s) {
+    const float v = ratios ? __fmul_rn(x, ratios[s * Bx + b]) : x;
+    x = __fadd_rn(__fmul_rn(v, dts[s]), x);
+  }
   out[i] = x;
+}
+static __global__ void fill_kernel(float* __restrict__ dst, int64_t n, float value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = value;
 }
 
 template <typename T>

@@ -1,0 +1,17 @@
+#!/bin/bash
+# One gpurun call: every GPU test file in its own process (a trapped kernel poisons only its own
+# CUDA context), then smoke and a short bench.  Logs land in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-.}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+rc=0
+for f in test_gpu_gemm test_gpu_chamfer test_gpu_head test_gpu_pipeline; do
+  timeout 900 python -m pytest tests/$f.py -q -m gpu -x --tb=short -s > gpurun_out/$f.log 2>&1
+  echo "$f exit $?" | tee -a gpurun_out/summary.txt
+  tail -5 gpurun_out/$f.log
+done
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/summary.txt
+tail -3 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?" | tee -a gpurun_out/summary.txt
+tail -2 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
