@@ -110,10 +110,13 @@ def test_sample_fp32_end_to_end(mode):
     out = nb.denoise(head, sched, zz.cuda(), x.cuda(), gs, None, None if ids is None else ids.cuda())
     assert out.shape == ref.shape
     assert relmax(out, ref) < 5e-5  # 25 compounded steps
-    if ids is not None:  # unpredicted rows: noise * prod(1+dt), reproduced to the last bit
+    if ids is not None:  # unpredicted rows: x <- (ratio x) dt + x per step, ratio == 1 without renorm
         mask = torch.ones(2, 40, dtype=torch.bool)
         mask.scatter_(1, pred_ids[..., 0], False)
-        assert torch.equal(out.cpu()[mask], ref[mask])
+        if mode == "cfg_renorm":  # the per-cloud ratio itself carries fp32 rounding differences
+            assert torch.allclose(out.cpu()[mask], ref[mask], rtol=1e-5, atol=1e-7)
+        else:  # reproduced to the last bit
+            assert torch.equal(out.cpu()[mask], ref[mask])
 
 
 @pytest.mark.parametrize("shift,steps", [(3.0, 10), (1.0, 1)])
