@@ -152,7 +152,8 @@ NOVA_API void nova_launch_count_reset(void);
 
 /*
  * Test hook: C[M,N] = epilogue(A[M,K] W[N,K]^T + bias) with one named GEMM implementation.
- *   impl 0 = SIMT, 1 = tcgen05 (bf16 only); epilogue 0 = bias, 1 = bias + SiLU.
+ *   impl 0 = SIMT, 1 = tcgen05 cta_group::1, 2 = tcgen05 cta_group::2 (CTA pairs), 3 = tcgen05 default
+ *   (1-3 bf16 only); epilogue 0 = bias, 1 = bias + SiLU.
  *   A, W, C are bf16 (dtype NOVA_BF16) or fp32 (NOVA_F32); bias fp32 [N] or NULL.
  */
 NOVA_API int nova_debug_gemm(const void* A, const void* W, const float* bias, void* C, int64_t M, int64_t N, int64_t K,

@@ -27,19 +27,28 @@
 namespace nova {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;   // BM = rows per CTA, BN = tile columns
 constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;                // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int TMEM_COLS = 512;
-constexpr int C_CHUNK = 64;                                   // output columns per TMA store (128 B rows)
-constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;                  // one warp's 32 x 64 bf16 sub-tile: 4 KB
-constexpr int OFF_CSTAGE = STAGES * STAGE_BYTES;               // 4 warps x 2 buffers x 4 KB
-constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;     // 2 x BN fp32 bias tiles
-constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256;                      // 231 680 B <= 227 KB
+constexpr int C_CHUNK = 64;                               // output columns per TMA store (128 B rows)
+constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;             // one warp's 32 x 64 bf16 sub-tile: 4 KB
+
+// Per-CTA shared-memory plan for cta_group CG (1: one CTA per 128x256 tile, 2: a CTA pair per
+// 256x256 tile, each CTA holding its 128 rows of A and HALF of the W tile).
+template <int CG>
+struct Plan {
+  static constexpr int B_ROWS = BN / CG;                         // W rows this CTA loads per stage
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;          // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB / 32 KB
+  static constexpr int STAGES = CG == 1 ? 4 : 6;                 // 192 KB of operand ring either way
+  static constexpr int OFF_CSTAGE = STAGES * STAGE_BYTES;        // 4 warps x 2 buffers x 4 KB
+  static constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;  // 2 x BN fp32 bias tiles
+  static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;               // 231 680 B <= 227 KB
+  static constexpr int UMMA_M = BM * CG;
+};
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -134,13 +143,68 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {  // issued by the same warp id in both CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// ---- CTA-pair (cta_group::2) helpers; encodings follow cute/arch/copy_sm100_tma.hpp and
+// cutlass/arch/barrier.h (SM100_TMA_2SM_LOAD_2D, umma_arrive_multicast_2x1SM, ClusterBarrier::arrive)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit: address of the pair's even CTA
+// TMA load issued by either CTA of a pair; the transaction bytes land on the LEADER's mbarrier.
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* t, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(t)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs of the pair once prior MMAs retire
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  const uint16_t mask = 0x3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 rem;\n\t"
+      "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -195,10 +259,12 @@ struct EpiParams {
   int M, N, K;
 };
 
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const EpiParams p, uint32_t* dbg) {
+  using P = Plan<CG>;
+  constexpr int STAGES = P::STAGES, STAGE_BYTES = P::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = smem_raw;
   const uint32_t base = smem_u32(smem_raw);
@@ -206,16 +272,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (dbg && threadIdx.x == 0) { dbg[0] = 0xDEAD0A11u; dbg[1] = base; __threadfence_system(); }
     __trap();
   }
-  const uint32_t bar_base = base + OFF_BAR;
+  const uint32_t bar_base = base + P::OFF_BAR;
   // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P::OFF_BAR + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the CTA pair
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
+  const int num_m = (p.M + BM * CG - 1) / (BM * CG), num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (p.K + BK - 1) / BK;
 
@@ -226,50 +294,57 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx; TMA bytes of the whole pair
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit arrival (multicast to both CTAs when CG == 2)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4 * 32);  // every epilogue thread arrives
+      mbar_init(tempty_bar(b), CG * 4 * 32);  // every epilogue thread of every CTA of the group arrives
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+  if (warp == 2) tmem_alloc<CG>(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // peer barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------------------------------------- TMA producer
+    if (lane == 0) {  // ---------------------------------------------- TMA producer (both CTAs of a pair)
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = (tile / num_n) * BM, n_idx = (tile % num_n) * BN;
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        const int m_idx = (tile / num_n) * (BM * CG) + static_cast<int>(rank) * BM;
+        const int n_idx = (tile % num_n) * BN + static_cast<int>(rank) * P::B_ROWS;  // CG == 2: my half of W
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, dbg, 0x100u | stage);
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = base + stage * STAGE_BYTES;
-          tma_load_2d(&tmap_a, full_bar(stage), sa, kb * BK, m_idx);
-          tma_load_2d(&tmap_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_idx);
+          if (CG == 1) {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(&tmap_a, full_bar(stage), sa, kb * BK, m_idx);
+            tma_load_2d(&tmap_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_idx);
+          } else {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            tma_load_2d_2sm(&tmap_a, full_bar(stage), sa, kb * BK, m_idx);
+            tma_load_2d_2sm(&tmap_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_idx);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {  // --------------------------------- MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = make_idesc_bf16(P::UMMA_M, BN);
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(buf), buf_phase ^ 1u, dbg, 0x200u | buf);  // epilogue drained this buffer
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        mbar_wait(tempty_bar(buf), buf_phase ^ 1u, dbg, 0x200u | buf);  // epilogues drained this buffer
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar(stage), phase, dbg, 0x300u | stage);  // TMA bytes landed
+          mbar_wait(full_bar(stage), phase, dbg, 0x300u | stage);  // TMA bytes landed (both CTAs)
           tcgen05_fence_after();
           const uint32_t sa = base + stage * STAGE_BYTES;
           const uint64_t a_desc = make_smem_desc_sw128(sa);
@@ -277,24 +352,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16 B units
-            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            if (CG == 1) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
+            else umma_f16_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
           }
-          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          if (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_2sm(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));  // accumulator complete
+        if (CG == 1) umma_commit(tfull_bar(buf)); else umma_commit_2sm(tfull_bar(buf));  // accumulator complete
         if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
       }
     }
-  } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue
+  } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue (every CTA: its 128 rows)
     const int q = warp & 3;  // TMEM lane quarter this warp may access == its 32-row slice of the tile
     const int tid_e = threadIdx.x - EPI_WARP0 * 32;
-    const uint32_t cbuf = base + OFF_CSTAGE + static_cast<uint32_t>(q) * 2u * C_BUF_BYTES;
-    float* bias_all = reinterpret_cast<float*>(smem + OFF_BIAS);
+    const uint32_t cbuf = base + P::OFF_CSTAGE + static_cast<uint32_t>(q) * 2u * C_BUF_BYTES;
+    float* bias_all = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     int buf = 0, cpar = 0, it = 0;
     uint32_t buf_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_idx = (tile / num_n) * BM, n_idx = (tile % num_n) * BN;
+    for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
+      const int m_idx = (tile / num_n) * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
       float* bias_s = bias_all + (it & 1) * BN;
       for (int j = tid_e; j < BN; j += 128)
         bias_s[j] = (p.bias != nullptr && n_idx + j < p.N) ? __ldg(p.bias + n_idx + j) : 0.f;
@@ -337,17 +414,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         cpar ^= 1;
       }
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(buf));  // all tcgen05.ld of this accumulator have completed
+      // all tcgen05.ld of this accumulator have completed: hand the buffer back to the MMA issuer
+      if (CG == 1) mbar_arrive(tempty_bar(buf)); else mbar_arrive_cluster(tempty_bar(buf), 0u);
       if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging memory must outlive the last stores' reads
   }
   __syncwarp();  // lanes of the single-lane roles reconverge before the CTA-wide barrier
   tcgen05_fence_before();
-  __syncthreads();
+  // CG == 2: neither CTA may exit (or free TMEM) while the pair's MMAs can still touch its smem / TMEM
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -359,36 +438,56 @@ int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K,
 uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (device pointer)
 extern uint32_t* g_debug_host;  // the same words, host pointer
 int num_sms();
+int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
 
-template <int EPI>
+template <int EPI, int CG>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream) {
+  using P = Plan<CG>;
   static bool attr_done = false;
   if (!attr_done) {
-    NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         P::SMEM_BYTES));
     attr_done = true;
   }
   CUtensorMap ta, tb, tc_;
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
-  NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, BN));
+  NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, P::B_ROWS));
   NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, N, ldc, 32));
   EpiParams p{bias, M, N, K};
-  const int tiles = static_cast<int>(ceil_div(M, BM) * ceil_div(N, BN));
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc_, p, debug_word());
+  const int tiles = static_cast<int>(ceil_div(M, BM * CG) * ceil_div(N, BN));
+  const int groups = tiles < num_sms() / CG ? tiles : num_sms() / CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = P::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG>, ta, tb, tc_, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
 
+// cta_group selection: 0 = automatic (CTA pairs once there are at least 2 x 128 rows), 1, 2
 inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
-                  int M, int N, int K, int epi, cudaStream_t stream) {
+                  int M, int N, int K, int epi, cudaStream_t stream, int cta_group = 0) {
   if (M <= 0 || N <= 0) return NOVA_OK;
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tcgen05 gemm: K, lda, ldw must be multiples of 8");
   NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0,
                "tcgen05 gemm: operands must be 16-byte aligned");
-  return epi == EPI_BIAS ? launch_epi<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
-                         : launch_epi<EPI_BIAS_SILU>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  if (cta_group == 0) cta_group = default_cta_group(M);
+  if (cta_group == 2)
+    return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
+                           : launch_epi<EPI_BIAS_SILU, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
+                         : launch_epi<EPI_BIAS_SILU, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
 }
 
 }  // namespace tc

@@ -2,6 +2,7 @@
 // the host-mapped debug words of the tcgen05 kernels, and the small C-ABI entry points.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -89,6 +90,17 @@ int num_sms() {
   return sms;
 }
 
+int default_cta_group(int M) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* env = std::getenv("NOVA_B200_CTA_GROUP");
+    forced = env ? std::atoi(env) : 0;
+    if (forced != 1 && forced != 2) forced = 0;
+  }
+  if (forced) return forced;
+  return M > BM ? 2 : 1;  // a CTA pair needs more than one 128-row slab to be worth it
+}
+
 }  // namespace tc
 }  // namespace nova
 
@@ -155,7 +167,9 @@ extern "C" int nova_debug_gemm(const void* A, const void* W, const float* bias, 
   if (impl == 0)
     return simt::launch<bf16, bf16, false>(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, bias,
                                            static_cast<bf16*>(C), N, (int)M, (int)N, (int)K, epilogue, s);
+  NOVA_REQUIRE(impl >= 1 && impl <= 3, "nova_debug_gemm: unknown impl %d", impl);
   NOVA_PROPAGATE(nova_device_check());
+  // impl 1 = tcgen05 cta_group::1, 2 = tcgen05 cta_group::2 (CTA pairs), 3 = library default
   return tc::launch(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, bias, static_cast<bf16*>(C), N,
-                    (int)M, (int)N, (int)K, epilogue, s);
+                    (int)M, (int)N, (int)K, epilogue, s, impl == 3 ? 0 : impl);
 }

@@ -207,7 +207,7 @@ def _(a, b):
 
 def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: str, epilogue: str) -> torch.Tensor:
     """Test hook over nova_debug_gemm: epi(A W^T + bias) with the named GEMM kernel."""
-    impl_id = {"simt": 0, "tcgen05": 1}[impl]
+    impl_id = {"simt": 0, "tcgen05_1cta": 1, "tcgen05_2cta": 2, "tcgen05": 3}[impl]
     epi_id = {"bias": _lib.EPI_BIAS, "bias_silu": _lib.EPI_BIAS_SILU}[epilogue]
     A, W = A.contiguous(), W.contiguous()
     M, K = A.shape

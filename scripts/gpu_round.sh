@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
-for f in test_gpu_gemm test_gpu_chamfer test_gpu_head test_gpu_pipeline; do
+for f in test_gpu_gemm test_gpu_gemm_2cta test_gpu_chamfer test_gpu_head test_gpu_pipeline; do
   timeout 900 python -m pytest tests/$f.py -q -m gpu -x --tb=short -s > gpurun_out/$f.log 2>&1
   echo "$f exit $?" | tee -a gpurun_out/summary.txt
   tail -5 gpurun_out/$f.log
@@ -15,3 +15,13 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?" | tee -a gpurun_out/summary.txt
 tail -2 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
+NOVA_B200_CTA_GROUP=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1cta.log 2> gpurun_out/bench_1cta.err; echo "bench 1cta exit $?" | tee -a gpurun_out/summary.txt
+python - <<'PY'
+import json
+for f in ("gpurun_out/bench.log", "gpurun_out/bench_1cta.log"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "ms/step", round(d["ms_per_step"], 2), "frac", round(d["roofline"]["frac"], 3), "gemm", d["gemm"])
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
