@@ -49,6 +49,12 @@ struct nova_head {
   float *w_t1 = nullptr, *b_t1 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr;
   float *w_patch = nullptr, *b_patch = nullptr, *w_head = nullptr, *b_head = nullptr;
   bool use_simt_gemm = false;  // NOVA_B200_GEMM=simt: isolate tcgen05 problems (bf16 handle only)
+  // Optional second stream (NOVA_B200_STREAMS=2): nova_head_sample splits the rows into two halves whose
+  // chains run on two streams so row-wise (HBM-bound) kernels could overlap the other half's GEMMs.
+  // Measured on B200 (round 1): no gain -- a resident persistent GEMM CTA (231 KB smem, max-shared
+  // carveout) does not share its SM with other kernels' CTAs -- so the default is one stream.
+  cudaStream_t side = nullptr;
+  bool two_streams = false;
 
   int D() const { return cfg.width; }
   int Dc() const { return cfg.cond_width; }
@@ -75,6 +81,19 @@ struct Workspace {
   float *v, *xsel, *thid, *temb, *tdev;
   size_t bytes;
 };
+
+// The same buffers seen from row `row0` on: rows are independent, so a contiguous slice of the rows
+// can run the whole step chain on its own stream.
+Workspace row_view(const nova_head* h, const Workspace& w, int64_t row0) {
+  const size_t D = h->D(), es = h->esize(), r = static_cast<size_t>(row0);
+  auto adv = [&](void* p, size_t row_bytes) { return static_cast<void*>(static_cast<uint8_t*>(p) + r * row_bytes); };
+  Workspace v = w;
+  v.c = adv(w.c, D * es); v.a = adv(w.a, D * es); v.x = adv(w.x, D * es); v.h = adv(w.h, D * es);
+  v.u1 = adv(w.u1, D * es); v.u2 = adv(w.u2, D * es); v.st = adv(w.st, h->n_ada() * es);
+  v.v = w.v + r * h->T();
+  v.xsel = w.xsel + r * h->T();
+  return v;
+}
 
 Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
   const size_t M = static_cast<size_t>(rows > 0 ? rows : 1), D = h->D(), es = h->esize();
@@ -292,7 +311,6 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   fill_times_kernel<<<1, MAX_STEPS, 0, s>>>(w.tdev, tl, S);
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(time_embedding(h, w.tdev, S, w, s));
-  NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));  // hoisted: step-invariant
   // renorm with pred_ids: the reference's norms include the unpredicted rows of the latent
   // and the head output is scaled as a whole, so those rows and their norm evolve per cloud.
   const bool renorm_extra = guided && g->renorm < 1.0f && has_unpred;
@@ -304,27 +322,70 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
     rw::fill_kernel<<<(unsigned)ceil_div(Bx * S, 256), 256, 0, s>>>(ratios, Bx * S, 1.0f);
     NOVA_CHECK_LAUNCH();
   }
-  bool active = guided;
-  for (int i = 0; i < S; ++i) {
-    if (active && g->trunc > 0.f && timesteps[i] < g->trunc) active = false;  // maybe_disable
-    StepIO io{};
-    io.rows_per_t = M + 1;  // every row uses temb row t_offset
-    io.t_offset = i;
-    io.x_tok = w.xsel;
-    io.x_rows = Mx;
-    io.dt = dts.v[i];
-    if (active) {
-      io.M = M;
-      io.v_out = w.v;
-      NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
-      rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, s>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt,
-                                                        renorm_extra ? extra_sumsq : nullptr,
-                                                        renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
-      NOVA_CHECK_LAUNCH();
+  if (!guided) {
+    // Unguided: every row is independent for the whole loop.  Split the rows into two halves and run
+    // each half's chain (hoisted condition projection + S steps) on its own stream, so that the HBM-bound
+    // row kernels of one half overlap the tensor-bound GEMMs of the other.
+    auto run_rows = [&](int64_t row0, int64_t rows, cudaStream_t st) -> int {
+      const Workspace wv = row_view(h, w, row0);
+      NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows + row0 * Dc, rows, wv, st));  // hoisted: step-invariant
+      for (int i = 0; i < S; ++i) {
+        StepIO io{};
+        io.M = rows;
+        io.rows_per_t = rows + 1;  // every row uses temb row t_offset
+        io.t_offset = i;
+        io.x_tok = wv.xsel;
+        io.x_rows = rows;
+        io.xt_out = wv.xsel;  // Euler update fused into the last row kernel, latent stays fp32
+        io.dt = dts.v[i];
+        NOVA_PROPAGATE(head_step<AT>(h, wv, io, st));
+      }
+      return NOVA_OK;
+    };
+    const bool split = h->two_streams && h->side != nullptr && M >= 4096;
+    if (!split) {
+      NOVA_PROPAGATE(run_rows(0, M, s));
     } else {
-      io.M = Mx;  // guidance off (or truncated): only the conditional rows run
-      io.xt_out = w.xsel;
-      NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
+      const int64_t M0 = ceil_div(M / 2, 256) * 256;
+      cudaEvent_t fork = nullptr, join = nullptr;
+      NOVA_CHECK_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+      NOVA_CHECK_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+      int rc = NOVA_OK;
+      if (cudaEventRecord(fork, s) != cudaSuccess || cudaStreamWaitEvent(h->side, fork, 0) != cudaSuccess) rc = NOVA_ERR_CUDA;
+      if (rc == NOVA_OK) rc = run_rows(M0, M - M0, h->side);
+      if (rc == NOVA_OK) rc = run_rows(0, M0, s);
+      // always re-join, even on error, so the caller's stream never races the side stream
+      if (cudaEventRecord(join, h->side) != cudaSuccess || cudaStreamWaitEvent(s, join, 0) != cudaSuccess) {
+        if (rc == NOVA_OK) { set_error("nova_head_sample: stream join failed"); rc = NOVA_ERR_CUDA; }
+      }
+      cudaEventDestroy(fork);
+      cudaEventDestroy(join);
+      NOVA_PROPAGATE(rc);
+    }
+  } else {
+    NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));  // hoisted: step-invariant
+    bool active = true;
+    for (int i = 0; i < S; ++i) {
+      if (active && g->trunc > 0.f && timesteps[i] < g->trunc) active = false;  // maybe_disable
+      StepIO io{};
+      io.rows_per_t = M + 1;  // every row uses temb row t_offset
+      io.t_offset = i;
+      io.x_tok = w.xsel;
+      io.x_rows = Mx;
+      io.dt = dts.v[i];
+      if (active) {
+        io.M = M;
+        io.v_out = w.v;
+        NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
+        rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, s>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt,
+                                                          renorm_extra ? extra_sumsq : nullptr,
+                                                          renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
+        NOVA_CHECK_LAUNCH();
+      } else {
+        io.M = Mx;  // guidance truncated: only the conditional rows run from here on
+        io.xt_out = w.xsel;
+        NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
+      }
     }
   }
   if (has_unpred) NOVA_PROPAGATE(unpredicted(w, renorm_extra ? ratios : nullptr));
@@ -366,6 +427,8 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   h->cfg = *cfg;
   const char* env = std::getenv("NOVA_B200_GEMM");
   h->use_simt_gemm = env != nullptr && std::strcmp(env, "simt") == 0;
+  const char* env_streams = std::getenv("NOVA_B200_STREAMS");
+  h->two_streams = env_streams != nullptr && std::atoi(env_streams) == 2;
 
   const size_t D = cfg->width, Dc = cfg->cond_width, T = cfg->token_dim, es = h->esize();
   Carver cv(nullptr);
@@ -395,12 +458,14 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   }
   Carver real(h->arena);
   plan(real);
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) h->side = nullptr;
   *out = h;
   return NOVA_OK;
 }
 
 extern "C" int nova_head_destroy(nova_head_t* h) {
   if (!h) return NOVA_OK;
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->arena) cudaFree(h->arena);
   delete h;
   return NOVA_OK;

@@ -15,10 +15,11 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?" | tee -a gpurun_out/summary.txt
 tail -2 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
-NOVA_B200_CTA_GROUP=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1cta.log 2> gpurun_out/bench_1cta.err; echo "bench 1cta exit $?" | tee -a gpurun_out/summary.txt
+NOVA_B200_STREAMS=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1stream.log 2> gpurun_out/bench_1stream.err; echo "bench 1stream exit $?" | tee -a gpurun_out/summary.txt
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload cfg3-2048 > gpurun_out/bench_cfg3_2048.log 2> gpurun_out/bench_cfg3_2048.err; echo "bench cfg3-2048 exit $?" | tee -a gpurun_out/summary.txt
 python - <<'PY'
 import json
-for f in ("gpurun_out/bench.log", "gpurun_out/bench_1cta.log"):
+for f in ("gpurun_out/bench.log", "gpurun_out/bench_1stream.log", "gpurun_out/bench_cfg3_2048.log"):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "ms/step", round(d["ms_per_step"], 2), "frac", round(d["roofline"]["frac"], 3), "gemm", d["gemm"])
