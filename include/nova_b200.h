@@ -151,6 +151,15 @@ NOVA_API int64_t nova_launch_count(void);
 NOVA_API void nova_launch_count_reset(void);
 
 /*
+ * In-situ kernel timing for bench.py: while enabled (per calling thread), CUDA events are recorded on
+ * the launching stream around every launch of these kernel classes:
+ *   0 = AdaLN GEMM (M x 20D x D), 1 = other GEMMs (fc1 / fc2 / condition), 2 = row kernels, 3 = prep, 4 = other.
+ * nova_profile_read sums the elapsed ms and launches per class (arrays of >= 5 entries), then clears.
+ */
+NOVA_API int nova_profile_enable(int32_t on);
+NOVA_API int nova_profile_read(double* ms_by_class, int64_t* launches_by_class, int32_t n_classes);
+
+/*
  * Test hook: C[M,N] = epilogue(A[M,K] W[N,K]^T + bias) with one named GEMM implementation.
  *   impl 0 = SIMT, 1 = tcgen05 cta_group::1, 2 = tcgen05 cta_group::2 (CTA pairs), 3 = tcgen05 default
  *   (1-3 bf16 only); epilogue 0 = bias, 1 = bias + SiLU.

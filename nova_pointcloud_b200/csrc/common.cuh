@@ -16,6 +16,23 @@ namespace nova {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// In-situ kernel timing (nova_profile_*): CUDA events recorded around launches of one kernel class on
+// the launching stream, so bench.py can report per-kernel durations measured inside the real step.
+enum KernelClass : int { KC_GEMM_ADA = 0, KC_GEMM_FC = 1, KC_ROW = 2, KC_PREP = 3, KC_OTHER = 4, KC_COUNT = 5 };
+bool profile_enabled();
+void profile_begin(int kernel_class, cudaStream_t stream);
+void profile_end(cudaStream_t stream);
+struct ProfileScope {
+  cudaStream_t s;
+  bool on;
+  ProfileScope(int kernel_class, cudaStream_t stream) : s(stream), on(profile_enabled()) {
+    if (on) profile_begin(kernel_class, s);
+  }
+  ~ProfileScope() {
+    if (on) profile_end(s);
+  }
+};
+
 #define NOVA_CHECK_CUDA(expr)                                                                  \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \

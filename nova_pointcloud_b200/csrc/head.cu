@@ -183,6 +183,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   const int64_t M = io.M;
   if (M <= 0) return NOVA_OK;
   {
+    ProfileScope ps(KC_PREP, s);
     const unsigned grid = (unsigned)ceil_div(M, rw::WARPS);
     if (h->cfg.dtype == NOVA_F32)
       rw::prep_kernel<AT, true><<<grid, rw::THREADS, 0, s>>>(static_cast<const AT*>(w.c), w.temb, io.rows_per_t,
@@ -193,8 +194,11 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
     NOVA_CHECK_LAUNCH();
   }
   const int n_ada = h->n_ada();
-  NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.a), D, static_cast<const AT*>(h->w_ada), D, h->b_ada,
-                          static_cast<AT*>(w.st), n_ada, M, n_ada, D, EPI_BIAS, s));
+  {
+    ProfileScope ps(KC_GEMM_ADA, s);
+    NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.a), D, static_cast<const AT*>(h->w_ada), D, h->b_ada,
+                            static_cast<AT*>(w.st), n_ada, M, n_ada, D, EPI_BIAS, s));
+  }
   rw::RowParams p{};
   p.M = M; p.D = D; p.T = T;
   p.x_in = w.x; p.x_out = w.x; p.u = w.u2; p.st = w.st; p.ldst = n_ada; p.h_out = w.h;
@@ -203,17 +207,27 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   p.v_out = io.v_out; p.xt_in = io.x_tok; p.xt_out = io.xt_out; p.dt = io.dt;
   const int64_t final_off = static_cast<int64_t>(3) * depth * D;
   p.scale_off = depth > 0 ? 0 : final_off;
-  NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/false, /*out=*/depth > 0 ? 0 : 1, s));
+  {
+    ProfileScope ps(KC_ROW, s);
+    NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/false, /*out=*/depth > 0 ? 0 : 1, s));
+  }
   for (int i = 0; i < depth; ++i) {
-    NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.h), D, static_cast<const AT*>(h->w_fc1[i]), D, h->b_fc1[i],
-                            static_cast<AT*>(w.u1), D, M, D, D, EPI_BIAS_SILU, s));
-    NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.u1), D, static_cast<const AT*>(h->w_fc2[i]), D, h->b_fc2[i],
-                            static_cast<AT*>(w.u2), D, M, D, D, EPI_BIAS, s));
+    {
+      ProfileScope ps(KC_GEMM_FC, s);
+      NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.h), D, static_cast<const AT*>(h->w_fc1[i]), D, h->b_fc1[i],
+                              static_cast<AT*>(w.u1), D, M, D, D, EPI_BIAS_SILU, s));
+    }
+    {
+      ProfileScope ps(KC_GEMM_FC, s);
+      NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.u1), D, static_cast<const AT*>(h->w_fc2[i]), D, h->b_fc2[i],
+                              static_cast<AT*>(w.u2), D, M, D, D, EPI_BIAS, s));
+    }
     const bool last = (i + 1 == depth);
     p.gate_off = static_cast<int64_t>(3) * i * D + 2 * D;
     p.gamma = h->gamma[i];
     p.beta = h->beta[i];
     p.scale_off = last ? final_off : static_cast<int64_t>(3) * (i + 1) * D;
+    ProfileScope ps(KC_ROW, s);
     NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/true, /*out=*/last ? 1 : 0, s));
   }
   return NOVA_OK;

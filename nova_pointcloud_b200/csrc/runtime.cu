@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -23,6 +24,26 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+namespace {
+struct ProfileSpan {
+  int kernel_class;
+  cudaEvent_t start, stop;
+};
+thread_local bool g_profile_on = false;
+thread_local std::vector<ProfileSpan> g_spans;
+}  // namespace
+
+bool profile_enabled() { return g_profile_on; }
+void profile_begin(int kernel_class, cudaStream_t stream) {
+  ProfileSpan sp{kernel_class, nullptr, nullptr};
+  if (cudaEventCreate(&sp.start) != cudaSuccess || cudaEventCreate(&sp.stop) != cudaSuccess) return;
+  cudaEventRecord(sp.start, stream);
+  g_spans.push_back(sp);
+}
+void profile_end(cudaStream_t stream) {
+  if (!g_spans.empty()) cudaEventRecord(g_spans.back().stop, stream);
+}
 
 namespace tc {
 
@@ -110,6 +131,35 @@ extern "C" const char* nova_last_error(void) { return g_error; }
 extern "C" int nova_abi_version(void) { return NOVA_B200_ABI_VERSION; }
 extern "C" int64_t nova_launch_count(void) { return g_launches; }
 extern "C" void nova_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int nova_profile_enable(int32_t on) {
+  g_profile_on = on != 0;
+  return NOVA_OK;
+}
+
+// Sum the recorded spans per kernel class (ms) and clear them.  Synchronises on the recorded events.
+extern "C" int nova_profile_read(double* ms_by_class, int64_t* launches_by_class, int32_t n_classes) {
+  NOVA_REQUIRE(ms_by_class && launches_by_class && n_classes >= KC_COUNT, "nova_profile_read: need %d classes", KC_COUNT);
+  for (int i = 0; i < n_classes; ++i) {
+    ms_by_class[i] = 0.0;
+    launches_by_class[i] = 0;
+  }
+  int rc = NOVA_OK;
+  for (ProfileSpan& sp : g_spans) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(sp.stop) == cudaSuccess && cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess) {
+      ms_by_class[sp.kernel_class] += ms;
+      launches_by_class[sp.kernel_class] += 1;
+    } else {
+      rc = NOVA_ERR_CUDA;
+    }
+    cudaEventDestroy(sp.start);
+    cudaEventDestroy(sp.stop);
+  }
+  g_spans.clear();
+  if (rc != NOVA_OK) set_error("nova_profile_read: an event could not be read");
+  return rc;
+}
 
 extern "C" int nova_device_check(void) {
   int dev = 0, major = 0, minor = 0;

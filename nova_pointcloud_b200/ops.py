@@ -226,3 +226,19 @@ def launch_count() -> int:
 
 def launch_count_reset():
     _lib.lib().nova_launch_count_reset()
+
+
+KERNEL_CLASSES = ("gemm_ada", "gemm_fc", "row", "prep", "other")
+
+
+def profile_enable(on: bool):
+    """In-situ kernel timing (nova_profile_enable): CUDA events around each launch, per kernel class."""
+    check(_lib.lib().nova_profile_enable(1 if on else 0), "nova_profile_enable")
+
+
+def profile_read():
+    """{class: (total_ms, launches)} accumulated since the last read."""
+    ms = (C.c_double * 8)()
+    n = (C.c_int64 * 8)()
+    check(_lib.lib().nova_profile_read(ms, n, 8), "nova_profile_read")
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
