@@ -14,10 +14,14 @@ Printed JSON (one line, rank 0):
   value / ms_per_step : device-resident inputs, CUDA events on the launching stream, max over ranks
   e2e                 : same metric through the public API with pinned HOST buffers; H2D of the
                         noise + condition and D2H of the points inside the timed region
-  roofline            : bound = tensor; achieved = algorithmic FLOP per step (BASELINE.md section 3:
-                        F_min*B*N*S + 4*D^2*B*N, hoisted work not credited) / step time; peak =
-                        MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)
-  gemm                : the dominant kernel (tcgen05 GEMM, AdaLN shape M x 20D x D) timed alone
+  roofline            : the dominant kernel (tcgen05 AdaLN-statistics GEMM): algorithmic FLOP per launch /
+                        average launch duration measured in situ with CUDA events the library records on
+                        the launching stream around every launch; peak = MEASURED_PEAKS.json
+                        bf16_tflops_sustained (kernel timed inside a long step)
+  step_roofline       : whole step: algorithmic FLOP (F_min*B*N*S + 4*D^2*B*N,
+                        hoisted work not credited) / step time
+  kernel_shares       : in-situ share of the step per kernel class
+  gemm_alone          : the plain tcgen05 GEMM at M x 20D x D timed alone (burst regime)
   cpu_baseline        : the CPU oracle (port of the reference's torch code) on a bounded sample
 """
 
@@ -285,13 +289,16 @@ def main():
         ada_ms, ada_n = prof["gemm_ada"]
         ada_avg_ms = ada_ms / max(ada_n, 1)
         n_ada = (3 * DEPTH + 2) * D
-        ada_flops = 2.0 * B * N * n_ada * D  # algorithmic FLOP of one AdaLN GEMM launch (all of it is needed)
+        # algorithmic FLOP of the AdaLN-statistics GEMMs of one sampling step (all of it is needed), spread
+        # over the launches the library used for them (one N = 3D GEMM per block + one N = 2D final GEMM)
+        ada_flops_step = 2.0 * B * N * n_ada * D * S_STEPS
+        ada_flops = ada_flops_step * prof_steps / max(ada_n, 1)
         ada_tf = ada_flops / (ada_avg_ms * 1e-3) / 1e12 if ada_n else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath):  # dram bytes per launch from the committed ncu --set full capture
             with open(tpath) as f:
-                traffic = json.load(f).get(f"gemm_ada_M{B * N}_D{D}")
+                traffic = json.load(f).get(f"gemm_adaln_M{B * N}_D{D}")
         line = {
             "metric": "point_clouds_per_sec", "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -310,7 +317,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ada_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": ada_tf / pk["sustained"], "traffic": traffic,
-                         "kernel": "nova::tc::gemm_kernel<EPI_BIAS, cta_group 2>: AdaLN GEMM M x 20D x D (dominant kernel)",
+                         "kernel": "nova::tc::gemm_kernel<EPI_ADALN, cta_group 2>: AdaLN statistics GEMM M x 3D x D with the "
+                                   "LayerNorm modulation fused into its epilogue (dominant kernel)",
                          "flop_per_launch": ada_flops, "avg_launch_ms": ada_avg_ms, "launches_timed": ada_n,
                          "how": "CUDA events recorded by the library around every launch on the launching stream, "
                                 "inside real sampling steps (nova_profile_*)",

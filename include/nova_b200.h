@@ -168,6 +168,16 @@ NOVA_API int nova_profile_read(double* ms_by_class, int64_t* launches_by_class, 
 NOVA_API int nova_debug_gemm(const void* A, const void* W, const float* bias, void* C, int64_t M, int64_t N, int64_t K,
                     int32_t dtype, int32_t impl, int32_t epilogue, void* stream);
 
+/*
+ * Test hook: the AdaLN statistics GEMM with the modulation fused into its epilogue (bf16, tcgen05).
+ *   A [M,K], W [n_stats*D, K] and bias [n_stats*D] in the reference order (scale | shift | gate), x [M,D];
+ *   h_out [M,D] = LN(x; 1e-6)(1 + scale) + shift;  gate_out [M,D] = gate (n_stats == 3) or NULL (n_stats == 2).
+ * Synchronises the stream (it owns temporary buffers).
+ */
+NOVA_API int nova_debug_adaln_gemm(const void* A, const void* W, const float* bias, const void* x, void* h_out,
+                                   void* gate_out, int64_t M, int64_t D, int64_t K, int32_t n_stats,
+                                   int32_t cta_group, void* stream);
+
 /* Test hook: the 4 host-mapped words a tcgen05 kernel writes before trapping on a barrier timeout. */
 NOVA_API int nova_debug_words(uint32_t* out4);
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "nova_last_error", "nova_abi_version", "nova_device_check", "nova_head_create", "nova_head_destroy",
     "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
     "nova_head_sample", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
-    "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read",
+    "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
 ]
 
 
@@ -76,6 +76,8 @@ def _declare(lib):
     lib.nova_profile_enable.argtypes = [i32]
     lib.nova_profile_read.restype = C.c_int
     lib.nova_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]
+    lib.nova_debug_adaln_gemm.restype = C.c_int
+    lib.nova_debug_adaln_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
     lib.nova_debug_words.restype = C.c_int
     lib.nova_debug_words.argtypes = [C.POINTER(C.c_uint32)]
 

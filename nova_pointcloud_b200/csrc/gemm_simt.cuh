@@ -9,7 +9,8 @@
 
 namespace nova {
 
-enum Epilogue : int { EPI_BIAS = 0, EPI_BIAS_SILU = 1 };
+// EPI_ADALN exists on the tcgen05 kernel only (AdaLN statistics GEMM with the modulation fused in).
+enum Epilogue : int { EPI_BIAS = 0, EPI_BIAS_SILU = 1, EPI_ADALN = 2 };
 
 namespace simt {
 

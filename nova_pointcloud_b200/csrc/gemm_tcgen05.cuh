@@ -257,12 +257,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 struct EpiParams {
   const float* bias;  // [N] or nullptr
   int M, N, K;
+  // EPI_ADALN: W rows are packed per 128 features as [128 scale | 128 shift] ("mod" tiles, the first
+  // n_mod_tiles column tiles), followed by plain gate tiles.  A mod tile yields
+  //   h[:, f0:f0+128] = (x - mean) * rstd * (1 + scale) + shift      (normalization.py:34-36)
+  // through tmap_c; gate tiles go through tmap_c2 with bias only.
+  const bf16* x;          // [M, ldx] residual stream
+  int64_t ldx;
+  const float* rowstats;  // [M, 2] = (mean, rstd) of x, eps 1e-6
+  int n_mod_tiles;
 };
+
+__device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const __grid_constant__ CUtensorMap tmap_c, const EpiParams p, uint32_t* dbg) {
+            const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
+            const EpiParams p, uint32_t* dbg) {
   using P = Plan<CG>;
   constexpr int STAGES = P::STAGES, STAGE_BYTES = P::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024 B alignment
@@ -291,6 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
+    if (EPI == EPI_ADALN) prefetch_tmap(&tmap_c2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -376,42 +394,110 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int j = tid_e; j < BN; j += 128)
         bias_s[j] = (p.bias != nullptr && n_idx + j < p.N) ? __ldg(p.bias + n_idx + j) : 0.f;
       epi_bar_sync();  // bias tile visible to the 4 epilogue warps (double buffered across tiles)
+      const int tile_n = tile % num_n;
+      const int m0 = m_idx + q * 32;
+      const bool mod_tile = EPI == EPI_ADALN && tile_n < p.n_mod_tiles;
+      // AdaLN modulation tile: this thread's 128 features of x and its row statistics do not depend on the
+      // MMA, so they are requested BEFORE waiting for the accumulator and land while the tile is computed.
+      uint4 xv[EPI == EPI_ADALN ? 16 : 1];
+      float mean = 0.f, rstd = 0.f;
+      if (mod_tile) {
+        const int row = m0 + lane;
+        const bool valid = row < p.M;
+        const bf16* xrow = p.x + static_cast<int64_t>(valid ? row : 0) * p.ldx + tile_n * 128;
+#pragma unroll
+        for (int c = 0; c < (EPI == EPI_ADALN ? 16 : 1); ++c)
+          xv[c] = p.x != nullptr ? ld_global_nc_v4(xrow + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          const float2 st2 = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(row));
+          mean = st2.x;
+          rstd = st2.y;
+        }
+      }
       mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf);
       tcgen05_fence_after();
-      const int m0 = m_idx + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-#pragma unroll 1
-      for (int cc = 0; cc < BN / C_CHUNK; ++cc) {
-        const int n0 = n_idx + cc * C_CHUNK;
-        if (m0 >= p.M || n0 >= p.N) break;  // warp-uniform: nothing of this sub-tile is in bounds
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(t_row + cc * C_CHUNK, ra);
-        tmem_ld_32x32(t_row + cc * C_CHUNK + 32, rb);
-        if (lane == 0) tma_store_wait_read<1>();  // the store that last used this staging buffer has read it
-        __syncwarp();
-        tmem_ld_wait();
-        const uint32_t dst = cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
-        const float* bs = bias_s + cc * C_CHUNK;
+      if (mod_tile) {
+        // ---- TMEM columns [0,128) = scale, [128,256) = shift of features f0..f0+127
+        const int f0 = tile_n * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks of this thread's 128 B row, XOR-swizzled
-          uint32_t w[4];
+        for (int k = 0; k < 2; ++k) {  // 64 features -> one staging buffer -> one TMA store
+          if (m0 >= p.M) break;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t dst = cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int e = c * 8 + 2 * h;  // compile-time after unrolling: picks ra or rb statically
-            float x0 = __uint_as_float(e < 32 ? ra[e & 31] : rb[e & 31]) + bs[e];
-            float x1 = __uint_as_float(e < 32 ? ra[(e + 1) & 31] : rb[(e + 1) & 31]) + bs[e + 1];
-            if (EPI == EPI_BIAS_SILU) { x0 = silu(x0); x1 = silu(x1); }
-            w[h] = pack_bf16x2(x0, x1);
+          for (int sc = 0; sc < 2; ++sc) {  // 32-feature sub-chunks keep the register footprint bounded
+            const int fo = 64 * k + 32 * sc;  // feature offset inside the tile
+            uint32_t rs[32], rh[32];
+            tmem_ld_32x32(t_row + fo, rs);
+            tmem_ld_32x32(t_row + 128 + fo, rh);
+            tmem_ld_wait();
+            const float* bsc = bias_s + fo;
+            const float* bsh = bias_s + 128 + fo;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 xq = xv[EPI == EPI_ADALN ? (k * 2 + sc) * 4 + c : 0];
+              const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+              uint32_t w[4];
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) {
+                const int e = c * 8 + 2 * hh;
+                const float s0 = __uint_as_float(rs[e]) + bsc[e], s1 = __uint_as_float(rs[e + 1]) + bsc[e + 1];
+                const float h0 = __uint_as_float(rh[e]) + bsh[e], h1 = __uint_as_float(rh[e + 1]) + bsh[e + 1];
+                const float y0 = fmaf((bf16_lo(xw[hh]) - mean) * rstd, 1.0f + s0, h0);
+                const float y1 = fmaf((bf16_hi(xw[hh]) - mean) * rstd, 1.0f + s1, h1);
+                w[hh] = pack_bf16x2(y0, y1);
+              }
+              st_shared_v4(dst + (static_cast<uint32_t>((sc * 4 + c) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+            }
           }
-          st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES, f0 + 64 * k, m0);
+            tma_store_commit();
+          }
+          cpar ^= 1;
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmap_c, cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES, n0, m0);
-          tma_store_commit();
+      } else {
+        // ---- plain tile: bias (+SiLU); for EPI_ADALN these are the gate tiles, written through tmap_c2
+        const CUtensorMap* out_map = EPI == EPI_ADALN ? &tmap_c2 : &tmap_c;
+        const int out_n = EPI == EPI_ADALN ? (tile_n - p.n_mod_tiles) * BN : n_idx;
+        const int out_cols = EPI == EPI_ADALN ? p.N - p.n_mod_tiles * BN : p.N;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / C_CHUNK; ++cc) {
+          const int n0 = out_n + cc * C_CHUNK;
+          if (m0 >= p.M || n0 >= out_cols) break;  // warp-uniform: nothing of this sub-tile is in bounds
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32(t_row + cc * C_CHUNK, ra);
+          tmem_ld_32x32(t_row + cc * C_CHUNK + 32, rb);
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this staging buffer has read it
+          __syncwarp();
+          tmem_ld_wait();
+          const uint32_t dst = cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
+          const float* bs = bias_s + cc * C_CHUNK;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks of this thread's 128 B row, XOR-swizzled
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int e = c * 8 + 2 * h;  // compile-time after unrolling: picks ra or rb statically
+              float x0 = __uint_as_float(e < 32 ? ra[e & 31] : rb[e & 31]) + bs[e];
+              float x1 = __uint_as_float(e < 32 ? ra[(e + 1) & 31] : rb[(e + 1) & 31]) + bs[e + 1];
+              if (EPI == EPI_BIAS_SILU) { x0 = silu(x0); x1 = silu(x1); }
+              w[h] = pack_bf16x2(x0, x1);
+            }
+            st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(out_map, cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES, n0, m0);
+            tma_store_commit();
+          }
+          cpar ^= 1;
         }
-        cpar ^= 1;
       }
       tcgen05_fence_before();
       // all tcgen05.ld of this accumulator have completed: hand the buffer back to the MMA issuer
@@ -440,9 +526,18 @@ extern uint32_t* g_debug_host;  // the same words, host pointer
 int num_sms();
 int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
 
+struct AdaLNArgs {
+  const bf16* x = nullptr;   // [M, ldx]
+  int64_t ldx = 0;
+  const float* rowstats = nullptr;  // [M, 2]
+  bf16* gate = nullptr;      // [M, ldg], columns N - 2 * features
+  int64_t ldg = 0;
+  int features = 0;          // D: mod tiles cover 2 D weight rows
+};
+
 template <int EPI, int CG>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
-               int M, int N, int K, cudaStream_t stream) {
+               int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr) {
   using P = Plan<CG>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -450,11 +545,22 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
                                          P::SMEM_BYTES));
     attr_done = true;
   }
-  CUtensorMap ta, tb, tc_;
+  CUtensorMap ta, tb, tc_, tc2;
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
   NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, P::B_ROWS));
-  NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, N, ldc, 32));
-  EpiParams p{bias, M, N, K};
+  EpiParams p{};
+  p.bias = bias; p.M = M; p.N = N; p.K = K;
+  if (EPI == EPI_ADALN) {
+    // C = h [M, features] fed by the mod tiles; gate [M, N - 2 features] fed by the remaining tiles
+    NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, ada->features, ldc, 32));
+    const int gate_cols = N - 2 * ada->features;
+    if (gate_cols > 0) NOVA_PROPAGATE(make_tmap_kmajor(&tc2, ada->gate, M, gate_cols, ada->ldg, 32));
+    else tc2 = tc_;
+    p.x = ada->x; p.ldx = ada->ldx; p.rowstats = ada->rowstats; p.n_mod_tiles = 2 * ada->features / BN;
+  } else {
+    NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, N, ldc, 32));
+    tc2 = tc_;
+  }
   const int tiles = static_cast<int>(ceil_div(M, BM * CG) * ceil_div(N, BN));
   const int groups = tiles < num_sms() / CG ? tiles : num_sms() / CG;
   cudaLaunchConfig_t cfg{};
@@ -469,7 +575,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG>, ta, tb, tc_, p, debug_word()));
+  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG>, ta, tb, tc_, tc2, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
@@ -488,6 +594,24 @@ inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const 
                            : launch_epi<EPI_BIAS_SILU, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
   return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
                          : launch_epi<EPI_BIAS_SILU, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+}
+
+// AdaLN statistics GEMM with the modulation fused into the epilogue:
+//   W [2 features + gate_cols, K] packed per 128 features as [scale | shift], then gate rows;
+//   h [M, features] = LN(x)(1 + scale) + shift,  gate [M, gate_cols] = a W_gate^T + b_gate.
+inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* h_out,
+                        int64_t ldh, const AdaLNArgs& ada, int M, int N, int K, cudaStream_t stream,
+                        int cta_group = 0) {
+  if (M <= 0 || N <= 0) return NOVA_OK;
+  NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldh % 8 == 0 && ada.ldx % 8 == 0,
+               "tcgen05 adaln gemm: K and leading dimensions must be multiples of 8");
+  NOVA_REQUIRE(ada.features % 128 == 0 && (2 * ada.features) % BN == 0 && N >= 2 * ada.features && N % BN == 0,
+               "tcgen05 adaln gemm: features must be a multiple of 128 and N a multiple of %d", BN);
+  NOVA_REQUIRE(ada.rowstats && (N == 2 * ada.features || ada.gate), "tcgen05 adaln gemm: null operand");
+  if (cta_group == 0) cta_group = default_cta_group(M);
+  if (cta_group == 2)
+    return launch_epi<EPI_ADALN, 2>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada);
+  return launch_epi<EPI_ADALN, 1>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada);
 }
 
 }  // namespace tc

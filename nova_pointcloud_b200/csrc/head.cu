@@ -41,6 +41,11 @@ struct nova_head {
   void* w_c1 = nullptr;   // [D, Dc]
   void* w_c2 = nullptr;   // [D, D]
   void* w_ada = nullptr;  // [(3 depth + 2) D, D]: per block scale|shift|gate, then final scale|shift
+  // the same rows packed for the fused-AdaLN GEMM epilogue (bf16 handles): per block and per 128 features
+  // [128 scale | 128 shift], then that block's gate rows; final norm: [scale | shift] groups only
+  void* w_ada_il = nullptr;
+  float* b_ada_il = nullptr;
+  float* w_patchT = nullptr;  // [T, D] transpose of w_patch for vector loads
   void* w_fc1[MAX_DEPTH] = {};
   void* w_fc2[MAX_DEPTH] = {};
   // fp32 side parameters
@@ -61,6 +66,8 @@ struct nova_head {
   int T() const { return cfg.token_dim; }
   int n_ada() const { return (3 * cfg.depth + 2) * cfg.width; }
   size_t esize() const { return cfg.dtype == NOVA_BF16 ? 2 : 4; }
+  // fused-AdaLN dataflow: tcgen05 GEMMs with the modulation in the AdaLN epilogue (the fast path)
+  bool fused() const { return cfg.dtype == NOVA_BF16 && !use_simt_gemm; }
 };
 
 namespace {
@@ -77,8 +84,8 @@ struct Carver {
 };
 
 struct Workspace {
-  void *c, *a, *x, *h, *u1, *u2, *st, *zsel;
-  float *v, *xsel, *thid, *temb, *tdev;
+  void *c, *a, *x, *h, *u1, *u2, *st, *zsel, *gate;
+  float *v, *xsel, *thid, *temb, *tdev, *rstat;
   size_t bytes;
 };
 
@@ -89,7 +96,13 @@ Workspace row_view(const nova_head* h, const Workspace& w, int64_t row0) {
   auto adv = [&](void* p, size_t row_bytes) { return static_cast<void*>(static_cast<uint8_t*>(p) + r * row_bytes); };
   Workspace v = w;
   v.c = adv(w.c, D * es); v.a = adv(w.a, D * es); v.x = adv(w.x, D * es); v.h = adv(w.h, D * es);
-  v.u1 = adv(w.u1, D * es); v.u2 = adv(w.u2, D * es); v.st = adv(w.st, h->n_ada() * es);
+  v.u1 = adv(w.u1, D * es); v.u2 = adv(w.u2, D * es);
+  if (h->fused()) {
+    v.gate = adv(w.gate, D * es);
+    v.rstat = w.rstat + 2 * r;
+  } else {
+    v.st = adv(w.st, h->n_ada() * es);
+  }
   v.v = w.v + r * h->T();
   v.xsel = w.xsel + r * h->T();
   return v;
@@ -106,7 +119,15 @@ Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
   w.h = cv.take(M * D * es);
   w.u1 = cv.take(M * D * es);
   w.u2 = cv.take(M * D * es);
-  w.st = cv.take(M * h->n_ada() * es);
+  if (h->fused()) {  // one block's gate + row statistics instead of all 20 D AdaLN outputs
+    w.st = nullptr;
+    w.gate = cv.take(M * D * es);
+    w.rstat = static_cast<float*>(cv.take(M * 2 * sizeof(float)));
+  } else {
+    w.st = cv.take(M * h->n_ada() * es);
+    w.gate = nullptr;
+    w.rstat = nullptr;
+  }
   w.zsel = cv.take(M * h->Dc() * es);
   w.v = static_cast<float*>(cv.take(M * h->T() * sizeof(float)));
   w.xsel = static_cast<float*>(cv.take(M * h->T() * sizeof(float)));
@@ -177,11 +198,73 @@ struct StepIO {
   float dt;
 };
 
+// bf16 / tcgen05 dataflow with the AdaLN modulation fused into the statistics GEMM's epilogue:
+//   prep   a = silu(c + temb_s)
+//   embed  x = PatchEmbed(x_tok), rowstats(x)
+//   per block:  G_ada_i  [h | gate] = epi(a W_i^T): h = LN(x)(1+scale)+shift in the epilogue, gate plain
+//               G_fc1, G_fc2;  resid: x += LN_aff(u2) * gate, rowstats(x)
+//   G_final     y = LN(x)(1+scale_f)+shift_f in the epilogue;   headout: v = H y + h0, Euler
+// The [M, 20 D] statistics tensor of the unfused flow is never materialised.
+int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cudaStream_t s) {
+  const int D = h->D(), T = h->T(), depth = h->cfg.depth;
+  const int64_t M = io.M;
+  bf16 *a = static_cast<bf16*>(w.a), *x = static_cast<bf16*>(w.x), *hh = static_cast<bf16*>(w.h);
+  bf16 *u1 = static_cast<bf16*>(w.u1), *u2 = static_cast<bf16*>(w.u2), *gate = static_cast<bf16*>(w.gate);
+  {
+    ProfileScope ps(KC_PREP, s);
+    rw::prep_kernel<bf16, false><<<(unsigned)ceil_div(M, rw::WARPS), rw::THREADS, 0, s>>>(
+        static_cast<const bf16*>(w.c), w.temb, io.rows_per_t, io.t_offset, a, M, D);
+    NOVA_CHECK_LAUNCH();
+  }
+  {
+    ProfileScope ps(KC_ROW, s);
+    NOVA_PROPAGATE((rw::dispatch_vpl<bf16, rw::EmbedLauncher>(D, io.x_tok, io.x_rows, h->w_patchT, h->b_patch, x,
+                                                             w.rstat, M, D, T, s)));
+  }
+  tc::AdaLNArgs ada{};
+  ada.x = x; ada.ldx = D; ada.rowstats = w.rstat; ada.gate = gate; ada.ldg = D; ada.features = D;
+  if (std::getenv("NOVA_B200_DEBUG_NOX")) ada.x = nullptr;  // timing experiment only: skips the x tile loads
+  const bf16* w_il = static_cast<const bf16*>(h->w_ada_il);
+  for (int i = 0; i < depth; ++i) {
+    {
+      ProfileScope ps(KC_GEMM_ADA, s);
+      NOVA_PROPAGATE(tc::launch_adaln(a, D, w_il + (size_t)3 * i * D * D, D, h->b_ada_il + (size_t)3 * i * D, hh, D, ada,
+                                      (int)M, 3 * D, D, s));
+    }
+    {
+      ProfileScope ps(KC_GEMM_FC, s);
+      NOVA_PROPAGATE(tc::launch(hh, D, static_cast<const bf16*>(h->w_fc1[i]), D, h->b_fc1[i], u1, D, (int)M, D, D,
+                                EPI_BIAS_SILU, s));
+    }
+    {
+      ProfileScope ps(KC_GEMM_FC, s);
+      NOVA_PROPAGATE(tc::launch(u1, D, static_cast<const bf16*>(h->w_fc2[i]), D, h->b_fc2[i], u2, D, (int)M, D, D,
+                                EPI_BIAS, s));
+    }
+    ProfileScope ps(KC_ROW, s);
+    NOVA_PROPAGATE((rw::dispatch_vpl<bf16, rw::ResidLauncher>(D, (const bf16*)u2, (const bf16*)x, (const bf16*)gate,
+                                                             (const float*)h->gamma[i], (const float*)h->beta[i], x,
+                                                             w.rstat, M, D, s)));
+  }
+  {
+    ProfileScope ps(KC_GEMM_ADA, s);
+    tc::AdaLNArgs fin = ada;
+    fin.gate = nullptr;
+    NOVA_PROPAGATE(tc::launch_adaln(a, D, w_il + (size_t)3 * depth * D * D, D, h->b_ada_il + (size_t)3 * depth * D, hh,
+                                    D, fin, (int)M, 2 * D, D, s));
+  }
+  ProfileScope ps(KC_ROW, s);
+  return rw::dispatch_vpl<bf16, rw::HeadoutLauncher>(D, (const bf16*)hh, (const float*)h->w_head,
+                                                     (const float*)h->b_head, io.v_out, io.x_tok, io.xt_out, io.dt, M,
+                                                     D, T, s);
+}
+
 template <typename AT>
 int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStream_t s) {
   const int D = h->D(), T = h->T(), depth = h->cfg.depth;
   const int64_t M = io.M;
   if (M <= 0) return NOVA_OK;
+  if (h->fused()) return head_step_fused(h, w, io, s);
   {
     ProfileScope ps(KC_PREP, s);
     const unsigned grid = (unsigned)ceil_div(M, rw::WARPS);
@@ -424,6 +507,31 @@ int convert_to_act(const nova_head* h, const void* src, int src_dtype, void* dst
                                : convert<bf16, bf16>(src, static_cast<bf16*>(dst), numel, s);
 }
 
+// Pack one AdaLN projection (rows x row_len, reference order) into the interleaved operand of the fused
+// epilogue, at row offset `row0` of w_ada_il / b_ada_il.  bf16 handles only.
+int pack_adaln(const nova_head* h, const void* src, int src_dtype, size_t row0, int rows, int row_len, bool bias,
+               cudaStream_t s) {
+  if (h->cfg.dtype != NOVA_BF16) return NOVA_OK;
+  const int64_t numel = (int64_t)rows * row_len;
+  const unsigned grid = (unsigned)ceil_div(numel, 256);
+  const int D = h->D();
+  if (bias) {
+    float* dst = h->b_ada_il + row0;
+    if (src_dtype == NOVA_F32)
+      rw::pack_adaln_kernel<float, float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), dst, rows, row_len, D);
+    else
+      rw::pack_adaln_kernel<bf16, float><<<grid, 256, 0, s>>>(static_cast<const bf16*>(src), dst, rows, row_len, D);
+  } else {
+    bf16* dst = static_cast<bf16*>(h->w_ada_il) + row0 * (size_t)row_len;
+    if (src_dtype == NOVA_F32)
+      rw::pack_adaln_kernel<float, bf16><<<grid, 256, 0, s>>>(static_cast<const float*>(src), dst, rows, row_len, D);
+    else
+      rw::pack_adaln_kernel<bf16, bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(src), dst, rows, row_len, D);
+  }
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
 }  // namespace
 
 extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) {
@@ -461,6 +569,11 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
     }
     h->w_t1 = f(D * 256); h->b_t1 = f(D); h->w_t2 = f(D * D); h->b_t2 = f(D);
     h->w_patch = f(D * T); h->b_patch = f(D); h->w_head = f(T * D); h->b_head = f(T);
+    h->w_patchT = f(D * T);
+    if (cfg->dtype == NOVA_BF16) {
+      h->w_ada_il = c.take(static_cast<size_t>(h->n_ada()) * D * es);
+      h->b_ada_il = f(h->n_ada());
+    }
   };
   plan(cv);
   h->arena_bytes = cv.off;
@@ -523,6 +636,8 @@ extern "C" int nova_head_load(nova_head_t* h, int32_t n, const char* const* name
       else
         rw::permute_patch_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(src), h->w_patch, D, channels, p);
       NOVA_CHECK_LAUNCH();
+      rw::transpose_kernel<<<grid, 256, 0, s>>>(h->w_patch, h->w_patchT, D, T);
+      NOVA_CHECK_LAUNCH();
     } else if (name == "patch_embed.proj.bias") {
       if (!want(D)) return NOVA_ERR_INVALID;
       rc = convert_to_float(src, src_dtype, h->b_patch, D, s);
@@ -553,9 +668,11 @@ extern "C" int nova_head_load(nova_head_t* h, int32_t n, const char* const* name
     } else if (name == "norm.proj.weight") {
       if (!want((int64_t)2 * D * D)) return NOVA_ERR_INVALID;
       rc = convert_to_act(h, src, src_dtype, static_cast<uint8_t*>(h->w_ada) + (size_t)3 * depth * D * D * es, numel, s);
+      if (rc == NOVA_OK) rc = pack_adaln(h, src, src_dtype, (size_t)3 * depth * D, 2 * D, D, /*bias=*/false, s);
     } else if (name == "norm.proj.bias") {
       if (!want((int64_t)2 * D)) return NOVA_ERR_INVALID;
       rc = convert_to_float(src, src_dtype, h->b_ada + (size_t)3 * depth * D, numel, s);
+      if (rc == NOVA_OK) rc = pack_adaln(h, src, src_dtype, (size_t)3 * depth * D, 2 * D, 1, /*bias=*/true, s);
     } else if (name == "head.weight") {
       if (!want((int64_t)T * D)) return NOVA_ERR_INVALID;
       rc = convert_to_float(src, src_dtype, h->w_head, numel, s);
@@ -571,9 +688,11 @@ extern "C" int nova_head_load(nova_head_t* h, int32_t n, const char* const* name
       if (leaf == "norm1.proj.weight") {
         if (!want((int64_t)3 * D * D)) return NOVA_ERR_INVALID;
         rc = convert_to_act(h, src, src_dtype, static_cast<uint8_t*>(h->w_ada) + (size_t)3 * i * D * D * es, numel, s);
+        if (rc == NOVA_OK) rc = pack_adaln(h, src, src_dtype, (size_t)3 * i * D, 3 * D, D, /*bias=*/false, s);
       } else if (leaf == "norm1.proj.bias") {
         if (!want((int64_t)3 * D)) return NOVA_ERR_INVALID;
         rc = convert_to_float(src, src_dtype, h->b_ada + (size_t)3 * i * D, numel, s);
+        if (rc == NOVA_OK) rc = pack_adaln(h, src, src_dtype, (size_t)3 * i * D, 3 * D, 1, /*bias=*/true, s);
       } else if (leaf == "proj.fc1.weight") {
         if (!want((int64_t)D * D)) return NOVA_ERR_INVALID;
         rc = convert_to_act(h, src, src_dtype, h->w_fc1[i], numel, s);

@@ -288,6 +288,194 @@ int launch_row(const RowParams& p, bool has_prev, int out, cudaStream_t stream) 
   return NOVA_ERR_INVALID;
 }
 
+// ------------------------------------------------------------------ row kernels of the fused-AdaLN path
+// With the modulation fused into the AdaLN GEMM epilogue (gemm_tcgen05.cuh, EPI_ADALN) the row-wise work
+// shrinks to: start the residual stream, finish a block (LN * gate + x), and the velocity head.  Each also
+// leaves (mean, rstd) of the stored residual row for the next AdaLN epilogue.
+
+// x0 = bp + Wp x_tok  (PatchEmbed with K = T; WpT is [T, D]);  rowstats = LN statistics of the stored row
+template <typename AT, int VPL>
+__global__ void __launch_bounds__(THREADS)
+embed_kernel(const float* __restrict__ x_tok, int64_t x_rows, const float* __restrict__ WpT,
+             const float* __restrict__ bp, AT* __restrict__ x_out, float* __restrict__ rowstats, int64_t M, int D,
+             int T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= M) return;
+  const float* xt = x_tok + (row % x_rows) * T;
+  float x[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) load8(bp + (i * 32 + lane) * 8, x[i]);
+  for (int t = 0; t < T; ++t) {
+    const float xv = xt[t];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float w[8];
+      load8(WpT + (int64_t)t * D + (i * 32 + lane) * 8, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i][j] = fmaf(xv, w[j], x[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[i][j] = to_float(from_float<AT>(x[i][j]));  // statistics of what is stored
+    store8(x_out + row * D + (i * 32 + lane) * 8, x[i]);
+  }
+  float mean, rstd;
+  row_stats<VPL>(x, 1.0f / static_cast<float>(D), 1e-6f, mean, rstd);
+  if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
+}
+
+// x <- LN_affine(u; 1e-5) * gate + x   (diffusion_mlp.py:53);  rowstats = LN statistics (1e-6) of the new row
+template <typename AT, int VPL>
+__global__ void __launch_bounds__(THREADS)
+resid_kernel(const AT* __restrict__ u, const AT* __restrict__ x_in, const AT* __restrict__ gate,
+             const float* __restrict__ gamma, const float* __restrict__ beta, AT* __restrict__ x_out,
+             float* __restrict__ rowstats, int64_t M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= M) return;
+  float uu[VPL][8], x[VPL][8], g[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {  // all loads in flight before the first reduction
+    const int64_t o = row * D + (i * 32 + lane) * 8;
+    load8(u + o, uu[i]);
+    load8(x_in + o, x[i]);
+    load8(gate + o, g[i]);
+  }
+  float mean, rstd;
+  row_stats<VPL>(uu, 1.0f / static_cast<float>(D), 1e-5f, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int e = (i * 32 + lane) * 8;
+    float ga[8], be[8];
+    load8(gamma + e, ga);
+    load8(beta + e, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ln = fmaf((uu[i][j] - mean) * rstd, ga[j], be[j]);
+      x[i][j] = to_float(from_float<AT>(fmaf(ln, g[i][j], x[i][j])));
+    }
+    store8(x_out + row * D + e, x[i]);
+  }
+  row_stats<VPL>(x, 1.0f / static_cast<float>(D), 1e-6f, mean, rstd);
+  if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
+}
+
+// v = Wh y + bh  (diffusion_mlp.py:98);  optional Euler update of the fp32 latent (scheduling_cfm.py:136)
+template <typename AT, int VPL>
+__global__ void __launch_bounds__(THREADS)
+headout_kernel(const AT* __restrict__ y, const float* __restrict__ Wh, const float* __restrict__ bh,
+               float* __restrict__ v_out, const float* __restrict__ xt_in, float* __restrict__ xt_out, float dt,
+               int64_t M, int D, int T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= M) return;
+  float x[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) load8(y + row * D + (i * 32 + lane) * 8, x[i]);
+  for (int t = 0; t < T; ++t) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float w[8];
+      load8(Wh + (int64_t)t * D + (i * 32 + lane) * 8, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(x[i][j], w[j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float v = acc + bh[t];
+      if (v_out) v_out[row * T + t] = v;
+      if (xt_out) xt_out[row * T + t] = __fadd_rn(__fmul_rn(v, dt), xt_in[row * T + t]);
+    }
+  }
+}
+
+template <typename AT, template <typename, int> class Launcher, typename... Args>
+int dispatch_vpl(int D, Args... args) {
+  switch (D / 256) {
+    case 1: return Launcher<AT, 1>::run(args...);
+    case 2: return Launcher<AT, 2>::run(args...);
+    case 3: return Launcher<AT, 3>::run(args...);
+    case 4: return Launcher<AT, 4>::run(args...);
+    case 5: return Launcher<AT, 5>::run(args...);
+    case 6: return Launcher<AT, 6>::run(args...);
+    case 7: return Launcher<AT, 7>::run(args...);
+    case 8: return Launcher<AT, 8>::run(args...);
+    default: break;
+  }
+  set_error("unsupported head width %d (multiple of 256, <= 2048)", D);
+  return NOVA_ERR_INVALID;
+}
+template <typename AT, int VPL>
+struct EmbedLauncher {
+  static int run(const float* x_tok, int64_t x_rows, const float* WpT, const float* bp, AT* x_out, float* rowstats,
+                 int64_t M, int D, int T, cudaStream_t s) {
+    embed_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(x_tok, x_rows, WpT, bp, x_out, rowstats, M,
+                                                                         D, T);
+    NOVA_CHECK_LAUNCH();
+    return NOVA_OK;
+  }
+};
+template <typename AT, int VPL>
+struct ResidLauncher {
+  static int run(const AT* u, const AT* x_in, const AT* gate, const float* gamma, const float* beta, AT* x_out,
+                 float* rowstats, int64_t M, int D, cudaStream_t s) {
+    resid_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(u, x_in, gate, gamma, beta, x_out, rowstats,
+                                                                         M, D);
+    NOVA_CHECK_LAUNCH();
+    return NOVA_OK;
+  }
+};
+template <typename AT, int VPL>
+struct HeadoutLauncher {
+  static int run(const AT* y, const float* Wh, const float* bh, float* v_out, const float* xt_in, float* xt_out,
+                 float dt, int64_t M, int D, int T, cudaStream_t s) {
+    headout_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(y, Wh, bh, v_out, xt_in, xt_out, dt, M, D,
+                                                                           T);
+    NOVA_CHECK_LAUNCH();
+    return NOVA_OK;
+  }
+};
+
+// (mean, rstd) of every row of x [M, D]; generic two-pass form used by the debug hook only
+template <typename AT>
+__global__ void __launch_bounds__(THREADS)
+rowstats_kernel(const AT* __restrict__ x, float* __restrict__ rowstats, int64_t M, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= M) return;
+  const AT* xr = x + row * D;
+  float s = 0.f;
+  for (int e = lane; e < D; e += 32) s += to_float(xr[e]);
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    const float d = to_float(xr[e]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+  if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
+}
+
+// AdaLN projection rows packed for EPI_ADALN: per 128 features [128 scale rows | 128 shift rows], then the
+// gate rows unchanged.  src is the reference layout [scale (D) | shift (D) | gate (D, optional)] x row_len.
+template <typename TS, typename TD>
+__global__ void pack_adaln_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t rows, int64_t row_len,
+                                  int D) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * row_len) return;
+  const int64_t dr = i / row_len, c = i % row_len;
+  int64_t sr = dr;
+  if (dr < 2 * (int64_t)D) {
+    const int64_t grp = dr / 256, r = dr % 256;
+    sr = r < 128 ? grp * 128 + r : (int64_t)D + grp * 128 + (r - 128);
+  }
+  dst[i] = from_float<TD>(to_float(src[sr * row_len + c]));
+}
+
 // ------------------------------------------------------------------ latent bookkeeping
 // Guided Euler update over one cloud per CTA (needs per-cloud norms for renorm):
 //   v = vu + (vc - vu) * s;  v *= clamp(|vc| / |v|, renorm, 1) if renorm < 1;  x += dt * v
@@ -421,6 +609,13 @@ template <typename TS, typename TD>
 __global__ void convert_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t numel) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < numel) dst[i] = from_float<TD>(to_float(src[i]));
+}
+// [D, T] -> [T, D]
+static __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int D, int T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)D * T) return;
+  const int t = static_cast<int>(i / D), d = static_cast<int>(i % D);
+  dst[i] = src[(int64_t)d * T + t];
 }
 // Conv2d weight (D, C, p, p) -> token order (D, p, p, C)
 template <typename TS>

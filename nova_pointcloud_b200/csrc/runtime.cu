@@ -223,3 +223,37 @@ extern "C" int nova_debug_gemm(const void* A, const void* W, const float* bias, 
   return tc::launch(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, bias, static_cast<bf16*>(C), N,
                     (int)M, (int)N, (int)K, epilogue, s, impl == 3 ? 0 : impl);
 }
+
+// Test hook for the fused AdaLN GEMM: W [n_stats * D, K] and bias [n_stats * D] in the reference order
+// (scale | shift | gate); packs them, computes the row statistics of x and runs the EPI_ADALN kernel.
+extern "C" int nova_debug_adaln_gemm(const void* A, const void* W, const float* bias, const void* x, void* h_out,
+                                     void* gate_out, int64_t M, int64_t D, int64_t K, int32_t n_stats,
+                                     int32_t cta_group, void* stream) {
+  NOVA_REQUIRE(A && W && bias && x && h_out && (n_stats == 2 || (n_stats == 3 && gate_out)),
+               "nova_debug_adaln_gemm: bad arguments");
+  NOVA_REQUIRE(D > 0 && D % 256 == 0 && K % 8 == 0 && M >= 0, "nova_debug_adaln_gemm: D must be a multiple of 256");
+  NOVA_PROPAGATE(nova_device_check());
+  if (M == 0) return NOVA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t rows = (int64_t)n_stats * D;
+  bf16* w_il = nullptr;
+  float *b_il = nullptr, *rstat = nullptr;
+  NOVA_CHECK_CUDA(cudaMalloc(&w_il, rows * K * sizeof(bf16)));
+  NOVA_CHECK_CUDA(cudaMalloc(&b_il, rows * sizeof(float)));
+  NOVA_CHECK_CUDA(cudaMalloc(&rstat, M * 2 * sizeof(float)));
+  rw::pack_adaln_kernel<bf16, bf16><<<(unsigned)ceil_div(rows * K, 256), 256, 0, s>>>(static_cast<const bf16*>(W), w_il,
+                                                                                    rows, K, (int)D);
+  rw::pack_adaln_kernel<float, float><<<(unsigned)ceil_div(rows, 256), 256, 0, s>>>(bias, b_il, rows, 1, (int)D);
+  rw::rowstats_kernel<bf16><<<(unsigned)ceil_div(M, rw::WARPS), rw::THREADS, 0, s>>>(static_cast<const bf16*>(x), rstat,
+                                                                                   M, (int)D, 1e-6f);
+  tc::AdaLNArgs ada{};
+  ada.x = static_cast<const bf16*>(x); ada.ldx = D; ada.rowstats = rstat;
+  ada.gate = static_cast<bf16*>(gate_out); ada.ldg = D; ada.features = (int)D;
+  int rc = tc::launch_adaln(static_cast<const bf16*>(A), K, w_il, K, b_il, static_cast<bf16*>(h_out), D, ada, (int)M,
+                            (int)rows, (int)K, s, cta_group);
+  cudaStreamSynchronize(s);
+  cudaFree(w_il);
+  cudaFree(b_il);
+  cudaFree(rstat);
+  return rc;
+}

@@ -220,6 +220,21 @@ def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], i
     return out
 
 
+def debug_adaln_gemm(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, n_stats: int,
+                     cta_group: int = 0):
+    """Test hook over nova_debug_adaln_gemm -> (h, gate or None), all bf16."""
+    A, W, x = A.contiguous(), W.contiguous(), x.contiguous()
+    M, K = A.shape
+    D = x.shape[1]
+    h = torch.empty(M, D, dtype=torch.bfloat16, device=A.device)
+    gate = torch.empty(M, D, dtype=torch.bfloat16, device=A.device) if n_stats == 3 else None
+    b = bias.contiguous().float()
+    with torch.cuda.device(A.device):
+        check(_lib.lib().nova_debug_adaln_gemm(_ptr(A), _ptr(W), _ptr(b), _ptr(x), _ptr(h), _ptr(gate), M, D, K, n_stats,
+                                               cta_group, _stream()), "nova_debug_adaln_gemm")
+    return h, gate
+
+
 def launch_count() -> int:
     return int(_lib.lib().nova_launch_count())
 

@@ -22,7 +22,8 @@ import json
 for f in ("gpurun_out/bench.log", "gpurun_out/bench_1stream.log", "gpurun_out/bench_cfg3_2048.log"):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, "ms/step", round(d["ms_per_step"], 2), "frac", round(d["roofline"]["frac"], 3), "gemm", d["gemm"])
+        print(f, "ms/step", round(d["ms_per_step"], 2), "step_frac", round(d["step_roofline"]["frac"], 3),
+              "dominant TF/s", round(d["roofline"]["achieved"], 1), {k: round(v["ms_per_step"], 2) for k, v in d["kernel_shares"].items()})
     except Exception as e:
         print(f, "unreadable", e)
 PY

@@ -67,3 +67,24 @@ def test_tcgen05_no_bias_and_repeatability(impl):
     o2 = ops.debug_gemm(A, W, None, impl, "bias")
     assert torch.equal(o1, o2)
     assert relmax(o1.float(), A.float() @ W.float().t()) < 1e-2
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,D,n_stats", [(256, 256, 3), (1000, 768, 3), (300, 512, 2), (4096, 1024, 3)])
+def test_fused_adaln_gemm(M, D, n_stats, cta_group):
+    """EPI_ADALN: h = LN(x)(1+scale)+shift and gate straight from the statistics GEMM's epilogue."""
+    from nova_pointcloud_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    A = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(n_stats * D, D, device="cuda", generator=g) / D**0.5).bfloat16()
+    b = torch.randn(n_stats * D, device="cuda", generator=g) * 0.5
+    x = (torch.randn(M, D, device="cuda", generator=g) * 3 + 1).bfloat16()
+    h, gate = ops.debug_adaln_gemm(A, W, b, x, n_stats, cta_group)
+    st = (A.float() @ W.float().t() + b).chunk(n_stats, dim=-1)
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), eps=1e-6) * (1 + st[0]) + st[1]
+    err = (h.float() - ref).abs()
+    assert bool((err <= 2.0**-7 * ref.abs() + 3e-2).all()), float(err.max())
+    if n_stats == 3:
+        err = (gate.float() - st[2]).abs()
+        assert bool((err <= 2.0**-8 * st[2].abs() + 1e-2).all()), float(err.max())
