@@ -607,7 +607,7 @@ inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, 
                "tcgen05 adaln gemm: K and leading dimensions must be multiples of 8");
   NOVA_REQUIRE(ada.features % 128 == 0 && (2 * ada.features) % BN == 0 && N >= 2 * ada.features && N % BN == 0,
                "tcgen05 adaln gemm: features must be a multiple of 128 and N a multiple of %d", BN);
-  NOVA_REQUIRE(ada.rowstats && (N == 2 * ada.features || ada.gate), "tcgen05 adaln gemm: null operand");
+  NOVA_REQUIRE(ada.x && ada.rowstats && (N == 2 * ada.features || ada.gate), "tcgen05 adaln gemm: null operand");
   if (cta_group == 0) cta_group = default_cta_group(M);
   if (cta_group == 2)
     return launch_epi<EPI_ADALN, 2>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada);

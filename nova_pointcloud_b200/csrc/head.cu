@@ -223,7 +223,6 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
   }
   tc::AdaLNArgs ada{};
   ada.x = x; ada.ldx = D; ada.rowstats = w.rstat; ada.gate = gate; ada.ldg = D; ada.features = D;
-  if (std::getenv("NOVA_B200_DEBUG_NOX")) ada.x = nullptr;  // timing experiment only: skips the x tile loads
   const bf16* w_il = static_cast<const bf16*>(h->w_ada_il);
   for (int i = 0; i < depth; ++i) {
     {

@@ -1,6 +1,7 @@
 """Short driver for ncu: two calls of the fused sampling loop (S = 2 diffusion steps) at bench shape.
-Per call the kernels matching gemm_kernel|row_kernel|prep_kernel are: 2 condition GEMMs, then per
-diffusion step prep, AdaLN GEMM, row, 6 x (fc1 GEMM, fc2 GEMM, row) = 21."""
+Per call the kernels matching gemm_kernel|resid_kernel|embed_kernel|headout_kernel|prep_kernel are:
+2 condition GEMMs, then per diffusion step prep, embed, 6 x (AdaLN GEMM, fc1 GEMM, fc2 GEMM, resid),
+final AdaLN GEMM, headout = 28."""
 import sys
 
 import torch
