@@ -44,9 +44,12 @@ struct Plan {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB / 32 KB
   static constexpr int STAGES = CG == 1 ? 4 : 6;                 // 192 KB of operand ring either way
   static constexpr int OFF_CSTAGE = STAGES * STAGE_BYTES;        // 4 warps x 2 buffers x 4 KB
-  static constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;  // 2 x BN fp32 bias tiles
-  static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256;               // 231 680 B <= 227 KB
+  static constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;  // one BN fp32 bias tile
+  static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+  // 230 656 B: with the 1 KB the hardware reserves per CTA this leaves >= 1 KB of the SM's 228 KB, so a
+  // CTA of a shared-memory-free kernel (the HBM-bound row kernels, launched on a second stream) can be
+  // co-resident with a persistent GEMM CTA and its memory traffic overlaps the MMAs.
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static constexpr int UMMA_M = BM * CG;
 };
 
@@ -386,14 +389,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int tid_e = threadIdx.x - EPI_WARP0 * 32;
     const uint32_t cbuf = base + P::OFF_CSTAGE + static_cast<uint32_t>(q) * 2u * C_BUF_BYTES;
     float* bias_all = reinterpret_cast<float*>(smem + P::OFF_BIAS);
-    int buf = 0, cpar = 0, it = 0;
+    int buf = 0, cpar = 0;
     uint32_t buf_phase = 0;
-    for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
+    for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_idx = (tile / num_n) * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
-      float* bias_s = bias_all + (it & 1) * BN;
+      float* bias_s = bias_all;
+      epi_bar_sync();  // every epilogue warp has finished reading the previous tile's bias
       for (int j = tid_e; j < BN; j += 128)
         bias_s[j] = (p.bias != nullptr && n_idx + j < p.N) ? __ldg(p.bias + n_idx + j) : 0.f;
-      epi_bar_sync();  // bias tile visible to the 4 epilogue warps (double buffered across tiles)
+      epi_bar_sync();  // bias tile visible to the 4 epilogue warps
       const int tile_n = tile % num_n;
       const int m0 = m_idx + q * 32;
       const bool mod_tile = EPI == EPI_ADALN && tile_n < p.n_mod_tiles;

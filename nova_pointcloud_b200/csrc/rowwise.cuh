@@ -328,38 +328,90 @@ embed_kernel(const float* __restrict__ x_tok, int64_t x_rows, const float* __res
 }
 
 // x <- LN_affine(u; 1e-5) * gate + x   (diffusion_mlp.py:53);  rowstats = LN statistics (1e-6) of the new row
+//
+// bf16 only (the fused-AdaLN dataflow).  The row stays PACKED in registers (VPL x uint4 each for u and x),
+// unpacked on the fly for every pass, so the kernel needs <= 64 registers per thread and 128-thread CTAs:
+// several of them fit next to a persistent tcgen05 GEMM CTA (which owns ~230 KB of shared memory but only
+// 28-49 K registers), so on a second stream this HBM-bound work overlaps the other half's MMAs.
+constexpr int RESID_WARPS = 4;
+constexpr int RESID_THREADS = RESID_WARPS * 32;
+
+__device__ __forceinline__ float bf16x2_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16x2_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  v[0] = bf16x2_lo(q.x); v[1] = bf16x2_hi(q.x); v[2] = bf16x2_lo(q.y); v[3] = bf16x2_hi(q.y);
+  v[4] = bf16x2_lo(q.z); v[5] = bf16x2_hi(q.z); v[6] = bf16x2_lo(q.w); v[7] = bf16x2_hi(q.w);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int VPL>
+__device__ __forceinline__ void packed_stats(const uint4 (&q)[VPL], float inv_d, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float v[8];
+    unpack8(q[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  mean = warp_sum(s) * inv_d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float v[8];
+    unpack8(q[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[j] - mean;
+      ss = fmaf(d, d, ss);
+    }
+  }
+  rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+}
+
 template <typename AT, int VPL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(RESID_THREADS, (VPL <= 4 ? 8 : 4))  // 64 registers up to D = 1024, 128 above
 resid_kernel(const AT* __restrict__ u, const AT* __restrict__ x_in, const AT* __restrict__ gate,
              const float* __restrict__ gamma, const float* __restrict__ beta, AT* __restrict__ x_out,
              float* __restrict__ rowstats, int64_t M, int D) {
+  static_assert(sizeof(AT) == 2, "resid_kernel is the bf16 fused-path kernel");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t row = (int64_t)blockIdx.x * RESID_WARPS + warp;
   if (row >= M) return;
-  float uu[VPL][8], x[VPL][8], g[VPL][8];
+  const float inv_d = 1.0f / static_cast<float>(D);
+  const uint4* up = reinterpret_cast<const uint4*>(u + row * D) + lane;
+  const uint4* xp = reinterpret_cast<const uint4*>(x_in + row * D) + lane;
+  const uint4* gp = reinterpret_cast<const uint4*>(gate + row * D) + lane;
+  uint4 uq[VPL], xq[VPL], gq[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {  // all loads in flight before the first reduction
-    const int64_t o = row * D + (i * 32 + lane) * 8;
-    load8(u + o, uu[i]);
-    load8(x_in + o, x[i]);
-    load8(gate + o, g[i]);
-  }
+  for (int i = 0; i < VPL; ++i) uq[i] = up[i * 32];  // every load of the row in flight before the first use
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) xq[i] = xp[i * 32];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) gq[i] = gp[i * 32];
   float mean, rstd;
-  row_stats<VPL>(uu, 1.0f / static_cast<float>(D), 1e-5f, mean, rstd);
+  packed_stats<VPL>(uq, inv_d, 1e-5f, mean, rstd);
+  uint4* op = reinterpret_cast<uint4*>(x_out + row * D) + lane;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int e = (i * 32 + lane) * 8;
-    float ga[8], be[8];
+    float uu[8], xx[8], gg[8], ga[8], be[8];
+    unpack8(uq[i], uu);
+    unpack8(xq[i], xx);
+    unpack8(gq[i], gg);
     load8(gamma + e, ga);
     load8(beta + e, be);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float ln = fmaf((uu[i][j] - mean) * rstd, ga[j], be[j]);
-      x[i][j] = to_float(from_float<AT>(fmaf(ln, g[i][j], x[i][j])));
+      const float ln = fmaf((uu[j] - mean) * rstd, ga[j], be[j]);
+      xx[j] = fmaf(ln, gg[j], xx[j]);
     }
-    store8(x_out + row * D + e, x[i]);
+    xq[i] = make_uint4(pack2(xx[0], xx[1]), pack2(xx[2], xx[3]), pack2(xx[4], xx[5]), pack2(xx[6], xx[7]));
+    op[i * 32] = xq[i];
   }
-  row_stats<VPL>(x, 1.0f / static_cast<float>(D), 1e-6f, mean, rstd);
+  packed_stats<VPL>(xq, inv_d, 1e-6f, mean, rstd);  // statistics of what was stored (rounded)
   if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
 }
 
@@ -393,6 +445,137 @@ headout_kernel(const AT* __restrict__ y, const float* __restrict__ Wh, const flo
   }
 }
 
+// ------------------------------------------------------------------ xyz-token (T = 3) fast paths, bf16
+// Point tokens have T = 3, so the patch-embed / velocity-head weights of one lane's features fit in
+// registers (D <= 1024) or L1 (above).  Each warp walks rows grid-stride with the next row's inputs already
+// in flight, so these kernels run at HBM speed instead of one latency-bound row per warp.
+// Arithmetic order is identical to embed_kernel / headout_kernel (same fmaf chains) => bit-identical output.
+constexpr int ROWLOOP_CTAS_PER_SM = 2;
+
+template <int VPL, bool WREG>
+__global__ void __launch_bounds__(THREADS, 1)  // store-bound: occupancy is irrelevant, registers hold the weights
+embed3_kernel(const float* __restrict__ x_tok, int64_t x_rows, const float* __restrict__ WpT,
+              const float* __restrict__ bp, bf16* __restrict__ x_out, float* __restrict__ rowstats, int64_t M,
+              int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= M) return;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  float w[WREG ? 3 : 1][VPL][8], b[WREG ? VPL : 1][8];
+  if (WREG) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      load8(bp + (i * 32 + lane) * 8, b[i]);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) load8(WpT + (int64_t)t * D + (i * 32 + lane) * 8, w[t][i]);
+    }
+  }
+  auto latent = [&](int64_t r, float (&xv)[3]) {
+    const float* xt = x_tok + (r >= x_rows ? r % x_rows : r) * 3;
+    xv[0] = xt[0]; xv[1] = xt[1]; xv[2] = xt[2];
+  };
+  float cur[3], nxt[3] = {0.f, 0.f, 0.f};
+  latent(row, cur);
+  for (; row < M; row += stride) {
+    if (row + stride < M) latent(row + stride, nxt);
+    uint4 q[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float acc[8];
+      if (WREG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cur[2], w[2][i][j], fmaf(cur[1], w[1][i][j], fmaf(cur[0], w[0][i][j], b[i][j])));
+      } else {
+        float w0[8], w1[8], w2[8];
+        load8(bp + (i * 32 + lane) * 8, acc);
+        load8(WpT + (i * 32 + lane) * 8, w0);
+        load8(WpT + (int64_t)D + (i * 32 + lane) * 8, w1);
+        load8(WpT + (int64_t)2 * D + (i * 32 + lane) * 8, w2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cur[2], w2[j], fmaf(cur[1], w1[j], fmaf(cur[0], w0[j], acc[j])));
+      }
+      q[i] = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
+      reinterpret_cast<uint4*>(x_out + row * D)[i * 32 + lane] = q[i];
+    }
+    float mean, rstd;
+    packed_stats<VPL>(q, inv_d, 1e-6f, mean, rstd);  // statistics of what is stored
+    if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
+    cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
+  }
+}
+
+template <int VPL, bool WREG>
+__global__ void __launch_bounds__(THREADS, ROWLOOP_CTAS_PER_SM)
+headout3_kernel(const bf16* __restrict__ y, const float* __restrict__ Wh, const float* __restrict__ bh,
+                float* __restrict__ v_out, const float* __restrict__ xt_in, float* __restrict__ xt_out, float dt,
+                int64_t M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  extern __shared__ float wh_s[];  // !WREG: [3, D] head weights staged once per CTA
+  float w[WREG ? 3 : 1][VPL][8];
+  if (WREG) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) load8(Wh + (int64_t)t * D + (i * 32 + lane) * 8, w[t][i]);
+  } else {
+    for (int e = threadIdx.x * 4; e < 3 * D; e += THREADS * 4)
+      *reinterpret_cast<float4*>(wh_s + e) = *reinterpret_cast<const float4*>(Wh + e);
+    __syncthreads();
+  }
+  if (row >= M) return;
+  const float bias = lane < 3 ? bh[lane] : 0.f;
+  uint4 cur[VPL], nxt[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) cur[i] = reinterpret_cast<const uint4*>(y + row * D)[i * 32 + lane];
+  for (; row < M; row += stride) {
+    const bool more = row + stride < M;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      nxt[i] = more ? reinterpret_cast<const uint4*>(y + (row + stride) * D)[i * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+    const float xin = (xt_out != nullptr && lane < 3) ? xt_in[row * 3 + lane] : 0.f;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float x[8];
+      unpack8(cur[i], x);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        if (WREG) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t] = fmaf(x[j], w[t][i][j], acc[t]);
+        } else {
+          float wv[8];
+          load8(wh_s + t * D + (i * 32 + lane) * 8, wv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t] = fmaf(x[j], wv[j], acc[t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
+      acc[2] += __shfl_xor_sync(0xffffffffu, acc[2], o);
+    }
+    if (lane < 3) {  // lane t finishes output t
+      const float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + bias;
+      if (v_out) v_out[row * 3 + lane] = v;
+      if (xt_out) xt_out[row * 3 + lane] = __fadd_rn(__fmul_rn(v, dt), xin);
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) cur[i] = nxt[i];
+  }
+}
+
+int num_sms_rw();  // SM count of the current device (runtime.cu)
+inline unsigned rowloop_grid(int64_t M, int ctas_per_sm) {
+  const int64_t want = ceil_div(M, WARPS), cap = (int64_t)num_sms_rw() * ctas_per_sm;
+  return (unsigned)(want < cap ? want : cap);
+}
+
 template <typename AT, template <typename, int> class Launcher, typename... Args>
 int dispatch_vpl(int D, Args... args) {
   switch (D / 256) {
@@ -413,8 +596,12 @@ template <typename AT, int VPL>
 struct EmbedLauncher {
   static int run(const float* x_tok, int64_t x_rows, const float* WpT, const float* bp, AT* x_out, float* rowstats,
                  int64_t M, int D, int T, cudaStream_t s) {
-    embed_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(x_tok, x_rows, WpT, bp, x_out, rowstats, M,
-                                                                         D, T);
+    if (T == 3 && sizeof(AT) == 2)
+      embed3_kernel<VPL, (VPL <= 4)><<<rowloop_grid(M, 1), THREADS, 0, s>>>(x_tok, x_rows, WpT, bp,
+                                                                         reinterpret_cast<bf16*>(x_out), rowstats, M, D);
+    else
+      embed_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(x_tok, x_rows, WpT, bp, x_out, rowstats,
+                                                                           M, D, T);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }
@@ -423,8 +610,8 @@ template <typename AT, int VPL>
 struct ResidLauncher {
   static int run(const AT* u, const AT* x_in, const AT* gate, const float* gamma, const float* beta, AT* x_out,
                  float* rowstats, int64_t M, int D, cudaStream_t s) {
-    resid_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(u, x_in, gate, gamma, beta, x_out, rowstats,
-                                                                         M, D);
+    resid_kernel<AT, VPL><<<(unsigned)ceil_div(M, RESID_WARPS), RESID_THREADS, 0, s>>>(u, x_in, gate, gamma, beta,
+                                                                                     x_out, rowstats, M, D);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }
@@ -433,8 +620,13 @@ template <typename AT, int VPL>
 struct HeadoutLauncher {
   static int run(const AT* y, const float* Wh, const float* bh, float* v_out, const float* xt_in, float* xt_out,
                  float dt, int64_t M, int D, int T, cudaStream_t s) {
-    headout_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(y, Wh, bh, v_out, xt_in, xt_out, dt, M, D,
-                                                                           T);
+    if (T == 3 && sizeof(AT) == 2)
+      headout3_kernel<VPL, (VPL <= 3)><<<rowloop_grid(M, ROWLOOP_CTAS_PER_SM), THREADS,
+                                         (VPL <= 3) ? 0 : 3 * D * sizeof(float), s>>>(
+          reinterpret_cast<const bf16*>(y), Wh, bh, v_out, xt_in, xt_out, dt, M, D);
+    else
+      headout_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(y, Wh, bh, v_out, xt_in, xt_out, dt, M,
+                                                                             D, T);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }

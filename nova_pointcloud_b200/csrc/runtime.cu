@@ -123,6 +123,9 @@ int default_cta_group(int M) {
 }
 
 }  // namespace tc
+namespace rw {
+int num_sms_rw() { return tc::num_sms(); }
+}  // namespace rw
 }  // namespace nova
 
 using namespace nova;
