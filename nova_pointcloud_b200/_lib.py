@@ -10,7 +10,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libnova_b200.so")
+LIB_PATH = os.environ.get("NOVA_B200_LIB") or os.path.join(_PKG, "lib", "libnova_b200.so")  # override: A/B builds
 
 NOVA_F32, NOVA_BF16 = 0, 1
 EPI_BIAS, EPI_BIAS_SILU = 0, 1

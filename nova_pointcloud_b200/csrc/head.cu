@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,18 @@ namespace {
 constexpr int MAX_DEPTH = 16;
 constexpr int MAX_STEPS = 256;
 }  // namespace
+
+// One captured S-step loop of nova_head_sample: everything in it touches only the caller's workspace, so a
+// replay is valid whenever the same workspace address, shapes, schedule and guidance come back.
+struct LoopGraph {
+  uint64_t key_hash = 0;
+  const void* ws = nullptr;
+  int64_t M = 0, Mx = 0, n = 0;
+  int S = 0;
+  cudaGraphExec_t exec = nullptr;  // nullptr: seen once, not captured yet
+  int64_t launches = 0;            // kernel launches inside the graph (for nova_launch_count)
+  uint64_t last_use = 0;
+};
 
 struct nova_head {
   nova_head_config cfg{};
@@ -54,12 +67,19 @@ struct nova_head {
   float *w_t1 = nullptr, *b_t1 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr;
   float *w_patch = nullptr, *b_patch = nullptr, *w_head = nullptr, *b_head = nullptr;
   bool use_simt_gemm = false;  // NOVA_B200_GEMM=simt: isolate tcgen05 problems (bf16 handle only)
-  // Optional second stream (NOVA_B200_STREAMS=2): nova_head_sample splits the rows into two halves whose
-  // chains run on two streams so row-wise (HBM-bound) kernels could overlap the other half's GEMMs.
-  // Measured on B200 (round 1): no gain -- a resident persistent GEMM CTA (231 KB smem, max-shared
-  // carveout) does not share its SM with other kernels' CTAs -- so the default is one stream.
-  cudaStream_t side = nullptr;
-  bool two_streams = false;
+  // Overlapping the HBM-bound row kernels with the tensor-bound GEMMs was tried twice in round 1 and is
+  // NOT in the code: (a) two streams over row halves -- CTAs of another kernel are not
+  // scheduled next to a persistent GEMM CTA even when registers and shared memory would allow it;
+  // (b) 8 row-worker warps inside the next AdaLN GEMM (setmaxnreg register split, per-32-row release
+  // counters) -- latency/issue-bound, the GEMM grew by as much as the separate kernel took.
+
+  // CUDA graphs of the denoise loop (NOVA_B200_GRAPH=0 disables): a loop seen twice with the same key is
+  // captured once and replayed afterwards -- ~710 launches become one; 4-5 % at M = 65 536, 1.3x at small M.
+  bool use_graphs = true;
+  cudaStream_t capture_stream = nullptr;
+  mutable std::mutex graph_mutex;
+  mutable std::vector<LoopGraph> graphs;
+  mutable uint64_t graph_clock = 0;
 
   int D() const { return cfg.width; }
   int Dc() const { return cfg.cond_width; }
@@ -88,25 +108,6 @@ struct Workspace {
   float *v, *xsel, *thid, *temb, *tdev, *rstat;
   size_t bytes;
 };
-
-// The same buffers seen from row `row0` on: rows are independent, so a contiguous slice of the rows
-// can run the whole step chain on its own stream.
-Workspace row_view(const nova_head* h, const Workspace& w, int64_t row0) {
-  const size_t D = h->D(), es = h->esize(), r = static_cast<size_t>(row0);
-  auto adv = [&](void* p, size_t row_bytes) { return static_cast<void*>(static_cast<uint8_t*>(p) + r * row_bytes); };
-  Workspace v = w;
-  v.c = adv(w.c, D * es); v.a = adv(w.a, D * es); v.x = adv(w.x, D * es); v.h = adv(w.h, D * es);
-  v.u1 = adv(w.u1, D * es); v.u2 = adv(w.u2, D * es);
-  if (h->fused()) {
-    v.gate = adv(w.gate, D * es);
-    v.rstat = w.rstat + 2 * r;
-  } else {
-    v.st = adv(w.st, h->n_ada() * es);
-  }
-  v.v = w.v + r * h->T();
-  v.xsel = w.xsel + r * h->T();
-  return v;
-}
 
 Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
   const size_t M = static_cast<size_t>(rows > 0 ? rows : 1), D = h->D(), es = h->esize();
@@ -418,49 +419,10 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
     rw::fill_kernel<<<(unsigned)ceil_div(Bx * S, 256), 256, 0, s>>>(ratios, Bx * S, 1.0f);
     NOVA_CHECK_LAUNCH();
   }
-  if (!guided) {
-    // Unguided: every row is independent for the whole loop.  Split the rows into two halves and run
-    // each half's chain (hoisted condition projection + S steps) on its own stream, so that the HBM-bound
-    // row kernels of one half overlap the tensor-bound GEMMs of the other.
-    auto run_rows = [&](int64_t row0, int64_t rows, cudaStream_t st) -> int {
-      const Workspace wv = row_view(h, w, row0);
-      NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows + row0 * Dc, rows, wv, st));  // hoisted: step-invariant
-      for (int i = 0; i < S; ++i) {
-        StepIO io{};
-        io.M = rows;
-        io.rows_per_t = rows + 1;  // every row uses temb row t_offset
-        io.t_offset = i;
-        io.x_tok = wv.xsel;
-        io.x_rows = rows;
-        io.xt_out = wv.xsel;  // Euler update fused into the last row kernel, latent stays fp32
-        io.dt = dts.v[i];
-        NOVA_PROPAGATE(head_step<AT>(h, wv, io, st));
-      }
-      return NOVA_OK;
-    };
-    const bool split = h->two_streams && h->side != nullptr && M >= 4096;
-    if (!split) {
-      NOVA_PROPAGATE(run_rows(0, M, s));
-    } else {
-      const int64_t M0 = ceil_div(M / 2, 256) * 256;
-      cudaEvent_t fork = nullptr, join = nullptr;
-      NOVA_CHECK_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-      NOVA_CHECK_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-      int rc = NOVA_OK;
-      if (cudaEventRecord(fork, s) != cudaSuccess || cudaStreamWaitEvent(h->side, fork, 0) != cudaSuccess) rc = NOVA_ERR_CUDA;
-      if (rc == NOVA_OK) rc = run_rows(M0, M - M0, h->side);
-      if (rc == NOVA_OK) rc = run_rows(0, M0, s);
-      // always re-join, even on error, so the caller's stream never races the side stream
-      if (cudaEventRecord(join, h->side) != cudaSuccess || cudaStreamWaitEvent(s, join, 0) != cudaSuccess) {
-        if (rc == NOVA_OK) { set_error("nova_head_sample: stream join failed"); rc = NOVA_ERR_CUDA; }
-      }
-      cudaEventDestroy(fork);
-      cudaEventDestroy(join);
-      NOVA_PROPAGATE(rc);
-    }
-  } else {
-    NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));  // hoisted: step-invariant
-    bool active = true;
+  NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));  // hoisted: step-invariant
+  // ---- the S-step loop: from here to the end of `run_loop` only workspace memory is touched
+  auto run_loop = [&](cudaStream_t st) -> int {
+    bool active = guided;
     for (int i = 0; i < S; ++i) {
       if (active && g->trunc > 0.f && timesteps[i] < g->trunc) active = false;  // maybe_disable
       StepIO io{};
@@ -472,16 +434,87 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
       if (active) {
         io.M = M;
         io.v_out = w.v;
-        NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
-        rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, s>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt,
+        NOVA_PROPAGATE(head_step<AT>(h, w, io, st));
+        rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, st>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt,
                                                           renorm_extra ? extra_sumsq : nullptr,
                                                           renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
         NOVA_CHECK_LAUNCH();
       } else {
-        io.M = Mx;  // guidance truncated: only the conditional rows run from here on
+        io.M = Mx;  // no guidance (or truncated): only the conditional rows run; Euler fused into the last row kernel
         io.xt_out = w.xsel;
-        NOVA_PROPAGATE(head_step<AT>(h, w, io, s));
+        NOVA_PROPAGATE(head_step<AT>(h, w, io, st));
       }
+    }
+    return NOVA_OK;
+  };
+  // Replay a captured graph when this exact loop (workspace, shapes, schedule, guidance) has been seen before.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool graphable = h->use_graphs && h->capture_stream != nullptr && S > 0 && !profile_enabled() &&
+                         cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+  if (!graphable) {
+    NOVA_PROPAGATE(run_loop(s));
+  } else {
+    uint64_t hash = 1469598103934665603ull;  // FNV-1a over everything the captured launches depend on
+    auto mix = [&](const void* p, size_t nbytes) {
+      const uint8_t* b = static_cast<const uint8_t*>(p);
+      for (size_t k = 0; k < nbytes; ++k) hash = (hash ^ b[k]) * 1099511628211ull;
+    };
+    mix(timesteps, sizeof(float) * S);
+    mix(dts.v, sizeof(float) * S);
+    const float gparams[3] = {guided ? g->scale : 0.f, guided ? g->trunc : 0.f, guided ? g->renorm : 1.f};
+    mix(gparams, sizeof(gparams));
+    const int64_t shape[6] = {B, Bx, N, n, (int64_t)renorm_extra, (int64_t)T};
+    mix(shape, sizeof(shape));
+    std::lock_guard<std::mutex> lock(h->graph_mutex);
+    LoopGraph* e = nullptr;
+    for (LoopGraph& c : h->graphs)
+      if (c.key_hash == hash && c.ws == ws && c.M == M && c.Mx == Mx && c.n == n && c.S == S) e = &c;
+    if (e != nullptr && e->exec != nullptr) {
+      NOVA_CHECK_CUDA(cudaGraphLaunch(e->exec, s));
+      count_launch((int)e->launches);
+      e->last_use = ++h->graph_clock;
+    } else if (e == nullptr) {  // first sight: run eagerly, remember the key
+      if (h->graphs.size() >= 64) {  // evict the least recently used entry
+        size_t victim = 0;
+        for (size_t k = 1; k < h->graphs.size(); ++k)
+          if (h->graphs[k].last_use < h->graphs[victim].last_use) victim = k;
+        if (h->graphs[victim].exec) cudaGraphExecDestroy(h->graphs[victim].exec);
+        h->graphs.erase(h->graphs.begin() + victim);
+      }
+      LoopGraph c{};
+      c.key_hash = hash; c.ws = ws; c.M = M; c.Mx = Mx; c.n = n; c.S = S; c.last_use = ++h->graph_clock;
+      h->graphs.push_back(c);
+      NOVA_PROPAGATE(run_loop(s));
+    } else {  // second sight: capture, instantiate, launch
+      const int64_t before = nova_launch_count();
+      // captured on the handle's own stream (the caller's may be the legacy default stream, which cannot be
+      // captured); nothing executes here, the instantiated graph is then launched on the caller's stream
+      NOVA_CHECK_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = run_loop(h->capture_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
+      const int64_t captured = nova_launch_count() - before;
+      count_launch(-(int)captured);  // nothing ran yet
+      if (rc != NOVA_OK || ce != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == NOVA_OK) set_error("nova_head_sample: stream capture failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        h->graphs.erase(h->graphs.begin() + (e - h->graphs.data()));
+        return rc != NOVA_OK ? rc : NOVA_ERR_CUDA;
+      }
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        set_error("nova_head_sample: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        h->graphs.erase(h->graphs.begin() + (e - h->graphs.data()));
+        return NOVA_ERR_CUDA;
+      }
+      e->exec = exec;
+      e->launches = captured;
+      e->last_use = ++h->graph_clock;
+      NOVA_CHECK_CUDA(cudaGraphLaunch(exec, s));
+      count_launch((int)captured);
     }
   }
   if (has_unpred) NOVA_PROPAGATE(unpredicted(w, renorm_extra ? ratios : nullptr));
@@ -548,8 +581,12 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   h->cfg = *cfg;
   const char* env = std::getenv("NOVA_B200_GEMM");
   h->use_simt_gemm = env != nullptr && std::strcmp(env, "simt") == 0;
-  const char* env_streams = std::getenv("NOVA_B200_STREAMS");
-  h->two_streams = env_streams != nullptr && std::atoi(env_streams) == 2;
+  const char* env_graph = std::getenv("NOVA_B200_GRAPH");
+  h->use_graphs = env_graph == nullptr || std::atoi(env_graph) != 0;
+  if (h->use_graphs && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->capture_stream = nullptr;
+    cudaGetLastError();
+  }
 
   const size_t D = cfg->width, Dc = cfg->cond_width, T = cfg->token_dim, es = h->esize();
   Carver cv(nullptr);
@@ -584,14 +621,15 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   }
   Carver real(h->arena);
   plan(real);
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) h->side = nullptr;
   *out = h;
   return NOVA_OK;
 }
 
 extern "C" int nova_head_destroy(nova_head_t* h) {
   if (!h) return NOVA_OK;
-  if (h->side) cudaStreamDestroy(h->side);
+  for (LoopGraph& c : h->graphs)
+    if (c.exec) cudaGraphExecDestroy(c.exec);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->arena) cudaFree(h->arena);
   delete h;
   return NOVA_OK;

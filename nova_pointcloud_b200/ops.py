@@ -41,6 +41,7 @@ class HeadHandle:
         self.dtype = dtype
         self.cfg = HeadConfig(depth, width, cond_width, token_dim, _DTYPES[dtype])
         self._h = C.c_void_p()
+        self._ws: Dict[int, torch.Tensor] = {}
         with torch.cuda.device(self.device):
             check(_lib.lib().nova_head_create(C.byref(self.cfg), C.byref(self._h)), "nova_head_create")
         self.id = HeadHandle._next_id
@@ -71,13 +72,22 @@ class HeadHandle:
             torch.cuda.current_stream().synchronize()  # `keep` may be freed after this returns
 
     def workspace(self, rows: int, steps: int) -> torch.Tensor:
-        nbytes = _lib.lib().nova_head_workspace_bytes(self._h, rows, steps)
-        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        """Scratch for one call, cached per CUDA stream (grow-only) so that its address is stable: the library
+        replays a captured CUDA graph of the denoise loop when the same workspace, shapes and schedule come back.
+        Calls on different streams get different workspaces (the C ABI's concurrency rule)."""
+        nbytes = max(int(_lib.lib().nova_head_workspace_bytes(self._h, rows, steps)), 256)
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
 
     def close(self):
         if self._h:
             _lib.lib().nova_head_destroy(self._h)
             self._h = C.c_void_p()
+            self._ws = {}
         HeadHandle._registry.pop(self.id, None)
 
     def __del__(self):
