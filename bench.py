@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default: workload's)")
     ap.add_argument("--impl", default="nova", choices=["nova", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the set-by-set and Chamfer legs")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -280,6 +281,71 @@ def main():
     except Exception as e:  # report, never hide
         gemm = {"error": str(e)[:300]}
 
+    # ---- secondary legs (rank 0, reported beside the headline; bounded to ~2 s)
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        try:  # set-by-set autoregressive generation (the reference's generate_frame pattern): 64 cosine-schedule sets
+            sizes = nb.partition.cosine_num_preds(N, 64)
+            gen = torch.Generator(device=dev).manual_seed(7)
+            shape = (B, 3, N, 1)
+
+            def ar_pass():
+                return nb.generate_sets(head, sched, z_d, shape, sizes, None, gen)
+
+            for _ in range(3):  # eager, graph capture, first replay: every set size has its own loop graph
+                ar_pass()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                ar_pass()
+            e1.record()
+            torch.cuda.synchronize()
+            ar_ms = e0.elapsed_time(e1) / 2
+            extras["set_by_set"] = {
+                "value": B / (ar_ms * 1e-3), "unit": "clouds/s", "ms_per_pass": ar_ms, "sets": len([k for k in sizes if k]),
+                "rows_per_head_call": [int(B * min(k for k in sizes if k)), int(B * max(sizes))],
+                "what": "64-set cosine schedule, every set = one fused 25-step call over B*n rows (CUDA-graph replay)"}
+        except Exception as e:  # report, never hide
+            extras["set_by_set"] = {"error": str(e)[:300]}
+        try:  # Chamfer scorer, BASELINE configs[4]: 256 pairs of 2048 x 2048 points
+            Bc, Nc = 256, 2048
+            gc = torch.Generator(device=dev).manual_seed(11)
+            pa = torch.rand(Bc, Nc, 3, device=dev, generator=gc) * 2 - 1
+            pb = torch.rand(Bc, Nc, 3, device=dev, generator=gc) * 2 - 1
+            for _ in range(3):
+                nb.chamfer_nn(pa, pb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                nb.chamfer_nn(pa, pb)
+            e1.record()
+            torch.cuda.synchronize()
+            cms = e0.elapsed_time(e1) / reps
+            alg_bytes = 2 * Bc * Nc * 3 * 4 + 2 * Bc * Nc * (4 + 4)  # points in, distances + indices out
+            extras["chamfer"] = {
+                "value": Bc / (cms * 1e-3), "unit": "cloud pairs/s", "ms": cms, "pairs": Bc, "points": Nc,
+                "pair_evals_per_s": 2.0 * Bc * Nc * Nc / (cms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": alg_bytes / (cms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": alg_bytes / (cms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                             "note": "algorithmically HBM-trivial (%.1f MB for 2.1 G pair evaluations): the limiter is "
+                                     "fp32 issue rate, see pair_evals_per_s" % (alg_bytes / 1e6)}}
+            if not args.no_cpu_baseline:
+                import numpy as np
+                from oracle import chamfer as OC
+
+                a_np, b_np = pa[:4].cpu().numpy(), pb[:4].cpu().numpy()
+                t0 = time.perf_counter()
+                for i in range(4):
+                    OC.chamfer_a(a_np[i], b_np[i])
+                cpu_s = (time.perf_counter() - t0) / 4
+                extras["chamfer"]["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "cloud pairs/s", "cores": 1, "kind": "port",
+                                                     "sample": "4 pairs, scipy cdist float64 + min (oracle/chamfer.py, demo.py:38-55)"}
+        except Exception as e:
+            extras["chamfer"] = {"error": str(e)[:300]}
+
     if rank == 0:
         flops = algorithmic_flops(D, B * N)  # per GPU per step
         achieved = flops / (ms * 1e-3) / 1e12
@@ -331,6 +397,7 @@ def main():
             "kernel_shares": shares,
             "gemm_alone": gemm,
         }
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             sample_clouds = 1

@@ -474,7 +474,7 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
       count_launch((int)e->launches);
       e->last_use = ++h->graph_clock;
     } else if (e == nullptr) {  // first sight: run eagerly, remember the key
-      if (h->graphs.size() >= 64) {  // evict the least recently used entry
+      if (h->graphs.size() >= 256) {  // evict the least recently used entry
         size_t victim = 0;
         for (size_t k = 1; k < h->graphs.size(); ++k)
           if (h->graphs[k].last_use < h->graphs[victim].last_use) victim = k;
