@@ -118,6 +118,34 @@ __device__ __forceinline__ float silu(float x) {
 // fp32 parity mode uses the accurate exponential.
 __device__ __forceinline__ float silu_accurate(float x) { return x / (1.0f + expf(-x)); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------
+// Every kernel of the sampling step starts with pdl_trigger() (lets the NEXT kernel's CTAs be scheduled and
+// run their prologue as soon as resources free up) and calls pdl_wait() before its first access to global
+// memory (blocks until every preceding kernel has completed and flushed).  Both are no-ops for a kernel
+// launched without the attribute.  Saves the launch latency + prologue at each of the ~700 kernel
+// boundaries of a sampling pass; captured into the loop's CUDA graph as programmatic edges.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();                   // decided per call from the row count (runtime.cu); NOVA_B200_PDL forces it
+void pdl_set_for_rows(int64_t rows);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -300,6 +300,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P::OFF_BAR + 8 * (2 * STAGES + 4));
 
+  pdl_trigger();  // the next kernel may be scheduled as soon as resources free up; it waits for our completion itself
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the CTA pair
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
@@ -329,6 +330,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // peer barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, TMEM, tensor-map prefetch) is independent of the preceding kernel and overlaps
+  // its tail; from here on global memory written by it is read (A via TMA, x / rowstats) or overwritten (C).
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------------------------------------- TMA producer (both CTAs of a pair)
@@ -572,13 +576,15 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = P::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG>, ta, tb, tc_, tc2, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;

@@ -213,8 +213,8 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
   bf16 *u1 = static_cast<bf16*>(w.u1), *u2 = static_cast<bf16*>(w.u2), *gate = static_cast<bf16*>(w.gate);
   {
     ProfileScope ps(KC_PREP, s);
-    rw::prep_kernel<bf16, false><<<(unsigned)ceil_div(M, rw::WARPS), rw::THREADS, 0, s>>>(
-        static_cast<const bf16*>(w.c), w.temb, io.rows_per_t, io.t_offset, a, M, D);
+    launch_pdl(rw::prep_kernel<bf16, false>, dim3((unsigned)ceil_div(M, rw::WARPS)), dim3(rw::THREADS), 0, s,
+               static_cast<const bf16*>(w.c), w.temb, io.rows_per_t, io.t_offset, a, M, D);
     NOVA_CHECK_LAUNCH();
   }
   {
@@ -344,6 +344,7 @@ int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_p
                  cudaStream_t s) {
   const int64_t M = B * n;
   if (M == 0) return NOVA_OK;
+  pdl_set_for_rows(M);
   const int T = h->T(), Dc = h->Dc();
   const int64_t R = t_per_token ? M : B;
   Workspace w = carve(h, ws, M, 0);
@@ -392,6 +393,7 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
     return NOVA_OK;
   }
   Workspace w = carve(h, ws, M, S);
+  pdl_set_for_rows(M);
   const AT* z_rows = z;
   if (pred_ids) {
     const int64_t nvec = M * (Dc / 8);
@@ -435,9 +437,9 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
         io.M = M;
         io.v_out = w.v;
         NOVA_PROPAGATE(head_step<AT>(h, w, io, st));
-        rw::cfg_euler_kernel<<<(unsigned)Bx, 256, 0, st>>>(w.v, w.xsel, Bx, n * T, g->scale, g->renorm, io.dt,
-                                                          renorm_extra ? extra_sumsq : nullptr,
-                                                          renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
+        launch_pdl(rw::cfg_euler_kernel, dim3((unsigned)Bx), dim3(256), 0, st, w.v, w.xsel, Bx, n * T, g->scale,
+                   g->renorm, io.dt, renorm_extra ? extra_sumsq : nullptr,
+                   renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
         NOVA_CHECK_LAUNCH();
       } else {
         io.M = Mx;  // no guidance (or truncated): only the conditional rows run; Euler fused into the last row kernel

@@ -98,7 +98,9 @@ prep_kernel(const AT* __restrict__ c, const float* __restrict__ temb, int64_t ro
             AT* __restrict__ a, int64_t M, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
+  pdl_trigger();
   if (m >= M) return;
+  pdl_wait();
   const float* te = temb + ((m / rows_per_t) + t_offset) * D;
   const AT* cr = c + m * D;
   AT* ar = a + m * D;
@@ -301,7 +303,9 @@ embed_kernel(const float* __restrict__ x_tok, int64_t x_rows, const float* __res
              int T) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  pdl_trigger();
   if (row >= M) return;
+  pdl_wait();
   const float* xt = x_tok + (row % x_rows) * T;
   float x[VPL][8];
 #pragma unroll
@@ -379,7 +383,9 @@ resid_kernel(const AT* __restrict__ u, const AT* __restrict__ x_in, const AT* __
   static_assert(sizeof(AT) == 2, "resid_kernel is the bf16 fused-path kernel");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * RESID_WARPS + warp;
+  pdl_trigger();
   if (row >= M) return;
+  pdl_wait();
   const float inv_d = 1.0f / static_cast<float>(D);
   const uint4* up = reinterpret_cast<const uint4*>(u + row * D) + lane;
   const uint4* xp = reinterpret_cast<const uint4*>(x_in + row * D) + lane;
@@ -423,7 +429,9 @@ headout_kernel(const AT* __restrict__ y, const float* __restrict__ Wh, const flo
                int64_t M, int D, int T) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  pdl_trigger();
   if (row >= M) return;
+  pdl_wait();
   float x[VPL][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) load8(y + row * D + (i * 32 + lane) * 8, x[i]);
@@ -460,7 +468,9 @@ embed3_kernel(const float* __restrict__ x_tok, int64_t x_rows, const float* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * WARPS;
   int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  pdl_trigger();
   if (row >= M) return;
+  pdl_wait();
   const float inv_d = 1.0f / static_cast<float>(D);
   float w[WREG ? 3 : 1][VPL][8], b[WREG ? VPL : 1][8];
   if (WREG) {
@@ -513,6 +523,8 @@ headout3_kernel(const bf16* __restrict__ y, const float* __restrict__ Wh, const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * WARPS;
   int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float wh_s[];  // !WREG: [3, D] head weights staged once per CTA
   float w[WREG ? 3 : 1][VPL][8];
   if (WREG) {
@@ -597,11 +609,11 @@ struct EmbedLauncher {
   static int run(const float* x_tok, int64_t x_rows, const float* WpT, const float* bp, AT* x_out, float* rowstats,
                  int64_t M, int D, int T, cudaStream_t s) {
     if (T == 3 && sizeof(AT) == 2)
-      embed3_kernel<VPL, (VPL <= 4)><<<rowloop_grid(M, 1), THREADS, 0, s>>>(x_tok, x_rows, WpT, bp,
-                                                                         reinterpret_cast<bf16*>(x_out), rowstats, M, D);
+      launch_pdl(embed3_kernel<VPL, (VPL <= 4)>, dim3(rowloop_grid(M, 1)), dim3(THREADS), 0, s, x_tok, x_rows, WpT, bp,
+                 reinterpret_cast<bf16*>(x_out), rowstats, M, D);
     else
-      embed_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(x_tok, x_rows, WpT, bp, x_out, rowstats,
-                                                                           M, D, T);
+      launch_pdl(embed_kernel<AT, VPL>, dim3((unsigned)ceil_div(M, WARPS)), dim3(THREADS), 0, s, x_tok, x_rows, WpT, bp,
+                 x_out, rowstats, M, D, T);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }
@@ -610,8 +622,8 @@ template <typename AT, int VPL>
 struct ResidLauncher {
   static int run(const AT* u, const AT* x_in, const AT* gate, const float* gamma, const float* beta, AT* x_out,
                  float* rowstats, int64_t M, int D, cudaStream_t s) {
-    resid_kernel<AT, VPL><<<(unsigned)ceil_div(M, RESID_WARPS), RESID_THREADS, 0, s>>>(u, x_in, gate, gamma, beta,
-                                                                                     x_out, rowstats, M, D);
+    launch_pdl(resid_kernel<AT, VPL>, dim3((unsigned)ceil_div(M, RESID_WARPS)), dim3(RESID_THREADS), 0, s, u, x_in, gate,
+               gamma, beta, x_out, rowstats, M, D);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }
@@ -621,12 +633,12 @@ struct HeadoutLauncher {
   static int run(const AT* y, const float* Wh, const float* bh, float* v_out, const float* xt_in, float* xt_out,
                  float dt, int64_t M, int D, int T, cudaStream_t s) {
     if (T == 3 && sizeof(AT) == 2)
-      headout3_kernel<VPL, (VPL <= 3)><<<rowloop_grid(M, ROWLOOP_CTAS_PER_SM), THREADS,
-                                         (VPL <= 3) ? 0 : 3 * D * sizeof(float), s>>>(
-          reinterpret_cast<const bf16*>(y), Wh, bh, v_out, xt_in, xt_out, dt, M, D);
+      launch_pdl(headout3_kernel<VPL, (VPL <= 3)>, dim3(rowloop_grid(M, ROWLOOP_CTAS_PER_SM)), dim3(THREADS),
+                 (VPL <= 3) ? 0 : 3 * D * sizeof(float), s, reinterpret_cast<const bf16*>(y), Wh, bh, v_out, xt_in,
+                 xt_out, dt, M, D);
     else
-      headout_kernel<AT, VPL><<<(unsigned)ceil_div(M, WARPS), THREADS, 0, s>>>(y, Wh, bh, v_out, xt_in, xt_out, dt, M,
-                                                                             D, T);
+      launch_pdl(headout_kernel<AT, VPL>, dim3((unsigned)ceil_div(M, WARPS)), dim3(THREADS), 0, s, y, Wh, bh, v_out,
+                 xt_in, xt_out, dt, M, D, T);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }
@@ -679,6 +691,8 @@ static __global__ void __launch_bounds__(256)
 cfg_euler_kernel(const float* __restrict__ v2, float* __restrict__ x_sel, int64_t B, int64_t len, float scale,
                  float renorm, float dt, float* __restrict__ extra_sumsq, float* __restrict__ ratio_out) {
   __shared__ float red[2][8];
+  pdl_trigger();
+  pdl_wait();
   const int64_t b = blockIdx.x;
   const float* vc = v2 + b * len;
   const float* vu = v2 + (B + b) * len;

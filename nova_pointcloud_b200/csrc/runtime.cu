@@ -24,6 +24,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+// PDL is a per-call decision (head.cu): it pays at small M, where the ~28 kernels of a diffusion step are
+// latency-bound (4-5 % measured), and costs 2-3 % at M = 65 536, where early-scheduled dependents sit next
+// to the persistent GEMM CTAs.  NOVA_B200_PDL=0 / 1 forces it off / on.
+static thread_local bool g_pdl_active = false;
+int pdl_forced() {
+  static const int forced = [] {
+    const char* e = std::getenv("NOVA_B200_PDL");
+    return e == nullptr ? -1 : (std::atoi(e) != 0 ? 1 : 0);
+  }();
+  return forced;
+}
+void pdl_set_for_rows(int64_t rows) { g_pdl_active = pdl_forced() >= 0 ? pdl_forced() == 1 : rows <= 16384; }
+bool pdl_enabled() { return g_pdl_active; }
 
 namespace {
 struct ProfileSpan {
