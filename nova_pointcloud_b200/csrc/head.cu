@@ -86,8 +86,12 @@ struct nova_head {
   int T() const { return cfg.token_dim; }
   int n_ada() const { return (3 * cfg.depth + 2) * cfg.width; }
   size_t esize() const { return cfg.dtype == NOVA_BF16 ? 2 : 4; }
-  // fused-AdaLN dataflow: tcgen05 GEMMs with the modulation in the AdaLN epilogue (the fast path)
-  bool fused() const { return cfg.dtype == NOVA_BF16 && !use_simt_gemm; }
+  // fused-AdaLN dataflow: tcgen05 GEMMs with the modulation in the AdaLN epilogue (the fast path at large M).
+  // Below `wide_ada_rows` rows a step is latency-bound (28 tiny launches), so the bf16 handle switches to the
+  // wide dataflow: ONE statistics GEMM with N = 20 D (fills the SMs even at M = 64) + the fused row kernel,
+  // 21 launches per step; its [M, 20 D] statistics tensor is small there.  NOVA_B200_WIDE_ADA_ROWS overrides.
+  int64_t wide_ada_rows = 1024;
+  bool fused(int64_t rows) const { return cfg.dtype == NOVA_BF16 && !use_simt_gemm && rows > wide_ada_rows; }
 };
 
 namespace {
@@ -120,7 +124,7 @@ Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
   w.h = cv.take(M * D * es);
   w.u1 = cv.take(M * D * es);
   w.u2 = cv.take(M * D * es);
-  if (h->fused()) {  // one block's gate + row statistics instead of all 20 D AdaLN outputs
+  if (h->fused(rows)) {  // one block's gate + row statistics instead of all 20 D AdaLN outputs
     w.st = nullptr;
     w.gate = cv.take(M * D * es);
     w.rstat = static_cast<float*>(cv.take(M * 2 * sizeof(float)));
@@ -264,7 +268,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   const int D = h->D(), T = h->T(), depth = h->cfg.depth;
   const int64_t M = io.M;
   if (M <= 0) return NOVA_OK;
-  if (h->fused()) return head_step_fused(h, w, io, s);
+  if (w.st == nullptr) return head_step_fused(h, w, io, s);  // the workspace was carved for the fused dataflow
   {
     ProfileScope ps(KC_PREP, s);
     const unsigned grid = (unsigned)ceil_div(M, rw::WARPS);
@@ -583,6 +587,7 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   h->cfg = *cfg;
   const char* env = std::getenv("NOVA_B200_GEMM");
   h->use_simt_gemm = env != nullptr && std::strcmp(env, "simt") == 0;
+  if (const char* env_wide = std::getenv("NOVA_B200_WIDE_ADA_ROWS")) h->wide_ada_rows = std::atoll(env_wide);
   const char* env_graph = std::getenv("NOVA_B200_GRAPH");
   h->use_graphs = env_graph == nullptr || std::atoi(env_graph) != 0;
   if (h->use_graphs && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -127,6 +127,8 @@ def head_forward(x_tok: torch.Tensor, t: torch.Tensor, z: torch.Tensor, pred_ids
     if not per_token and t.numel() != B:
         raise NovaError(f"timestep must have B={B} entries; got {tuple(t.shape)}")
     ids = None if pred_ids is None else pred_ids.contiguous()
+    if ids is not None and ids.numel() == 0:  # an empty set still means "pred_ids given": keep the pointer non-null
+        ids = torch.zeros(1, dtype=torch.int64, device=z.device)
     out = torch.empty(B, n, h.cfg.token_dim, dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device):
         ws = h.workspace(B * n, 0)
@@ -157,6 +159,8 @@ def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[tor
     Bx = noise_tok.shape[0]
     n = N if pred_ids is None else pred_ids.shape[1]
     ids = None if pred_ids is None else pred_ids.contiguous()
+    if ids is not None and ids.numel() == 0:  # an empty set still means "pred_ids given": keep the pointer non-null
+        ids = torch.zeros(1, dtype=torch.int64, device=z.device)
     c_t = (C.c_float * max(S, 1))(*[float(v) for v in timesteps])
     c_s = (C.c_double * (S + 1))(*[float(v) for v in sigmas])
     g = Guidance(float(guidance_scale), float(guidance_trunc), float(guidance_renorm))

@@ -130,8 +130,10 @@ def test_sample_fp32_other_schedules(shift, steps):
     assert relmax(nb.denoise(head.cuda(), sched, z.cuda(), x.cuda()), ref) < 3e-5
 
 
+@pytest.mark.parametrize("wide_rows", ["0", "1000000"])  # fused-AdaLN dataflow / wide (N = 20 D) small-M dataflow
 @pytest.mark.parametrize("D,N", [(768, 300), (1024, 256)])
-def test_forward_bf16_matches_fp32_oracle_on_rounded_weights(D, N):
+def test_forward_bf16_matches_fp32_oracle_on_rounded_weights(monkeypatch, D, N, wide_rows):
+    monkeypatch.setenv("NOVA_B200_WIDE_ADA_ROWS", wide_rows)
     head, x, z, t, _ = make_case(6, D, D, 2, N, 1)
     head = head.to(torch.bfloat16)
     sd = cpu_sd(head, torch.float32)  # bf16-rounded weights, fp32 arithmetic
@@ -142,8 +144,11 @@ def test_forward_bf16_matches_fp32_oracle_on_rounded_weights(D, N):
     assert relmax(out.float(), ref) < BF16_TOL
 
 
-def test_sample_bf16_teacher_forced_and_chamfer():
+@pytest.mark.parametrize("wide_rows", ["0", "1000000"])
+def test_sample_bf16_teacher_forced_and_chamfer(monkeypatch, wide_rows):
     import nova_pointcloud_b200 as nb
+
+    monkeypatch.setenv("NOVA_B200_WIDE_ADA_ROWS", wide_rows)
 
     B, N, D = 2, 256, 768
     head, x, z, _, _ = make_case(6, D, D, B, N, 1)
