@@ -314,17 +314,17 @@ def main():
             pa = torch.rand(Bc, Nc, 3, device=dev, generator=gc) * 2 - 1
             pb = torch.rand(Bc, Nc, 3, device=dev, generator=gc) * 2 - 1
             for _ in range(3):
-                nb.chamfer_nn(pa, pb)
+                nb.chamfer_nn(pa, pb, with_indices=False)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 10
             e0.record()
             for _ in range(reps):
-                nb.chamfer_nn(pa, pb)
+                nb.chamfer_nn(pa, pb, with_indices=False)  # the distance-only kernel the three Chamfer variants use
             e1.record()
             torch.cuda.synchronize()
             cms = e0.elapsed_time(e1) / reps
-            alg_bytes = 2 * Bc * Nc * 3 * 4 + 2 * Bc * Nc * (4 + 4)  # points in, distances + indices out
+            alg_bytes = 2 * Bc * Nc * 3 * 4 + 2 * Bc * Nc * 4  # points in, distances out (16.78 MB)
             extras["chamfer"] = {
                 "value": Bc / (cms * 1e-3), "unit": "cloud pairs/s", "ms": cms, "pairs": Bc, "points": Nc,
                 "pair_evals_per_s": 2.0 * Bc * Nc * Nc / (cms * 1e-3),

@@ -29,18 +29,20 @@ def _as_cuda_batch(x, device=None) -> Tuple[torch.Tensor, bool]:
     return t.float().contiguous(), single
 
 
-def chamfer_nn(a, b):
-    """(d1, d2, idx1, idx2): per-point nearest-neighbour Euclidean distances both ways."""
+def chamfer_nn(a, b, with_indices: bool = True):
+    """(d1, d2, idx1, idx2): per-point nearest-neighbour Euclidean distances both ways.
+
+    ``with_indices=False`` selects the distance-only kernel (idx1, idx2 come back empty)."""
     a, _ = _as_cuda_batch(a)
     b, _ = _as_cuda_batch(b, a.device)
-    return torch.ops.nova_b200.chamfer_nn(a, b)
+    return torch.ops.nova_b200.chamfer_nn(a, b, with_indices)
 
 
 def chamfer_distance(points1, points2):
     """Variant A: mean_i min_j |p_i-q_j| + mean_j min_i |p_i-q_j|.  (N,3),(M,3) -> float; batched -> (B,) tensor."""
     a, single = _as_cuda_batch(points1)
     b, _ = _as_cuda_batch(points2, a.device)
-    d1, d2, _, _ = torch.ops.nova_b200.chamfer_nn(a, b)
+    d1, d2, _, _ = torch.ops.nova_b200.chamfer_nn(a, b, False)
     cd = d1.double().mean(dim=1) + d2.double().mean(dim=1)
     return float(cd[0]) if single else cd
 
@@ -54,7 +56,7 @@ def dist_chamfer(a, b):
     """Variant B: clamp to [-1,1], project onto the unit sphere, exp(clamp(log(min d))) means -> (dl, dr)."""
     a, _ = _as_cuda_batch(a)
     b, _ = _as_cuda_batch(b, a.device)
-    d1, d2, _, _ = torch.ops.nova_b200.chamfer_nn(_unit_sphere(a), _unit_sphere(b))
+    d1, d2, _, _ = torch.ops.nova_b200.chamfer_nn(_unit_sphere(a), _unit_sphere(b), False)
     f = lambda m: (m.clamp(min=1e-8) + 1e-8).log().clamp(-10, 10).exp().mean()
     return f(d1), f(d2)
 
@@ -70,7 +72,7 @@ def compute_chamfer_distance(pred, target):
     t, _ = _as_cuda_batch(target, p.device)
     p, t = p.clamp(-5.0, 5.0), t.clamp(-5.0, 5.0)
     n = min(p.shape[1], t.shape[1])
-    m1, m2, _, _ = torch.ops.nova_b200.chamfer_nn(p[:, :n].contiguous(), t[:, :n].contiguous())
+    m1, m2, _, _ = torch.ops.nova_b200.chamfer_nn(p[:, :n].contiguous(), t[:, :n].contiguous(), False)
     d1 = (m1 * (1.0 / (m1 + 1e-6))).mean(dim=1)
     d2 = (m2 * (1.0 / (m2 + 1e-6))).mean(dim=1)
     return (d1 + d2).mean().clamp(0.0, 10.0)

@@ -460,58 +460,58 @@ headout_kernel(const AT* __restrict__ y, const float* __restrict__ Wh, const flo
 // Arithmetic order is identical to embed_kernel / headout_kernel (same fmaf chains) => bit-identical output.
 constexpr int ROWLOOP_CTAS_PER_SM = 2;
 
-template <int VPL, bool WREG>
-__global__ void __launch_bounds__(THREADS, 1)  // store-bound: occupancy is irrelevant, registers hold the weights
+// x0 = bp + Wp x_tok for T = 3; weights [3, D] and bias [D] staged once per CTA in shared memory, two rows per
+// iteration share every weight load, so the kernel keeps 16+ warps per SM and runs close to its HBM write time
+// (the round-1 register-resident version had 8 warps per SM and was issue-bound at 55 us for M = 65 536).
+constexpr int EMBED3_CTAS_PER_SM = 2;
+template <int VPL>
+__global__ void __launch_bounds__(THREADS, EMBED3_CTAS_PER_SM)
 embed3_kernel(const float* __restrict__ x_tok, int64_t x_rows, const float* __restrict__ WpT,
               const float* __restrict__ bp, bf16* __restrict__ x_out, float* __restrict__ rowstats, int64_t M,
               int D) {
+  extern __shared__ float emb_s[];  // [w0 | w1 | w2 | b], D floats each
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * WARPS;
-  int64_t row = (int64_t)blockIdx.x * WARPS + warp;
   pdl_trigger();
-  if (row >= M) return;
   pdl_wait();
+  for (int e = threadIdx.x * 4; e < 3 * D; e += THREADS * 4)
+    *reinterpret_cast<float4*>(emb_s + e) = *reinterpret_cast<const float4*>(WpT + e);
+  for (int e = threadIdx.x * 4; e < D; e += THREADS * 4)
+    *reinterpret_cast<float4*>(emb_s + 3 * D + e) = *reinterpret_cast<const float4*>(bp + e);
+  __syncthreads();
   const float inv_d = 1.0f / static_cast<float>(D);
-  float w[WREG ? 3 : 1][VPL][8], b[WREG ? VPL : 1][8];
-  if (WREG) {
+  const int64_t stride = (int64_t)gridDim.x * WARPS * 2;
+  for (int64_t row = ((int64_t)blockIdx.x * WARPS + warp) * 2; row < M; row += stride) {
+    const bool two = row + 1 < M;
+    const int64_t ra = row >= x_rows ? row % x_rows : row;
+    const int64_t rb = two ? ((row + 1) >= x_rows ? (row + 1) % x_rows : row + 1) : ra;
+    const float a0 = x_tok[ra * 3], a1 = x_tok[ra * 3 + 1], a2 = x_tok[ra * 3 + 2];
+    const float b0 = x_tok[rb * 3], b1 = x_tok[rb * 3 + 1], b2 = x_tok[rb * 3 + 2];
+    uint4 qa[VPL], qb[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      load8(bp + (i * 32 + lane) * 8, b[i]);
+      const int e = (i * 32 + lane) * 8;
+      float w0[8], w1[8], w2[8], bb[8], xa[8], xb[8];
+      load8(emb_s + e, w0);
+      load8(emb_s + D + e, w1);
+      load8(emb_s + 2 * D + e, w2);
+      load8(emb_s + 3 * D + e, bb);
 #pragma unroll
-      for (int t = 0; t < 3; ++t) load8(WpT + (int64_t)t * D + (i * 32 + lane) * 8, w[t][i]);
-    }
-  }
-  auto latent = [&](int64_t r, float (&xv)[3]) {
-    const float* xt = x_tok + (r >= x_rows ? r % x_rows : r) * 3;
-    xv[0] = xt[0]; xv[1] = xt[1]; xv[2] = xt[2];
-  };
-  float cur[3], nxt[3] = {0.f, 0.f, 0.f};
-  latent(row, cur);
-  for (; row < M; row += stride) {
-    if (row + stride < M) latent(row + stride, nxt);
-    uint4 q[VPL];
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float acc[8];
-      if (WREG) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cur[2], w[2][i][j], fmaf(cur[1], w[1][i][j], fmaf(cur[0], w[0][i][j], b[i][j])));
-      } else {
-        float w0[8], w1[8], w2[8];
-        load8(bp + (i * 32 + lane) * 8, acc);
-        load8(WpT + (i * 32 + lane) * 8, w0);
-        load8(WpT + (int64_t)D + (i * 32 + lane) * 8, w1);
-        load8(WpT + (int64_t)2 * D + (i * 32 + lane) * 8, w2);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cur[2], w2[j], fmaf(cur[1], w1[j], fmaf(cur[0], w0[j], acc[j])));
+      for (int j = 0; j < 8; ++j) {  // same fmaf chain as embed_kernel: bias, then t = 0, 1, 2
+        xa[j] = fmaf(a2, w2[j], fmaf(a1, w1[j], fmaf(a0, w0[j], bb[j])));
+        xb[j] = fmaf(b2, w2[j], fmaf(b1, w1[j], fmaf(b0, w0[j], bb[j])));
       }
-      q[i] = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
-      reinterpret_cast<uint4*>(x_out + row * D)[i * 32 + lane] = q[i];
+      qa[i] = make_uint4(pack2(xa[0], xa[1]), pack2(xa[2], xa[3]), pack2(xa[4], xa[5]), pack2(xa[6], xa[7]));
+      qb[i] = make_uint4(pack2(xb[0], xb[1]), pack2(xb[2], xb[3]), pack2(xb[4], xb[5]), pack2(xb[6], xb[7]));
+      reinterpret_cast<uint4*>(x_out + row * D)[i * 32 + lane] = qa[i];
+      if (two) reinterpret_cast<uint4*>(x_out + (row + 1) * D)[i * 32 + lane] = qb[i];
     }
     float mean, rstd;
-    packed_stats<VPL>(q, inv_d, 1e-6f, mean, rstd);  // statistics of what is stored
+    packed_stats<VPL>(qa, inv_d, 1e-6f, mean, rstd);  // statistics of what is stored
     if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
-    cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
+    if (two) {
+      packed_stats<VPL>(qb, inv_d, 1e-6f, mean, rstd);
+      if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * (row + 1)) = make_float2(mean, rstd);
+    }
   }
 }
 
@@ -609,8 +609,8 @@ struct EmbedLauncher {
   static int run(const float* x_tok, int64_t x_rows, const float* WpT, const float* bp, AT* x_out, float* rowstats,
                  int64_t M, int D, int T, cudaStream_t s) {
     if (T == 3 && sizeof(AT) == 2)
-      launch_pdl(embed3_kernel<VPL, (VPL <= 4)>, dim3(rowloop_grid(M, 1)), dim3(THREADS), 0, s, x_tok, x_rows, WpT, bp,
-                 reinterpret_cast<bf16*>(x_out), rowstats, M, D);
+      launch_pdl(embed3_kernel<VPL>, dim3(rowloop_grid(ceil_div(M, 2), EMBED3_CTAS_PER_SM)), dim3(THREADS),
+                 4 * D * sizeof(float), s, x_tok, x_rows, WpT, bp, reinterpret_cast<bf16*>(x_out), rowstats, M, D);
     else
       launch_pdl(embed_kernel<AT, VPL>, dim3((unsigned)ceil_div(M, WARPS)), dim3(THREADS), 0, s, x_tok, x_rows, WpT, bp,
                  x_out, rowstats, M, D, T);

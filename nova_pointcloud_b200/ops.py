@@ -196,27 +196,31 @@ def _(model_output, sample, dt):
 
 
 @torch.library.custom_op("nova_b200::chamfer_nn", mutates_args=(), device_types="cuda")
-def chamfer_nn(a: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Nearest-neighbour distances both ways: (d1 (B,N), d2 (B,M), idx1 int32, idx2 int32)."""
+def chamfer_nn(a: torch.Tensor, b: torch.Tensor, with_indices: bool = True
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Nearest-neighbour distances both ways: (d1 (B,N), d2 (B,M), idx1 int32, idx2 int32).
+
+    ``with_indices=False`` runs the distance-only kernel (~30 % fewer instructions); idx1/idx2 are then empty."""
     if a.dim() != 3 or b.dim() != 3 or a.shape[-1] != 3 or b.shape[-1] != 3 or a.shape[0] != b.shape[0]:
         raise NovaError(f"chamfer_nn expects (B,N,3) and (B,M,3); got {tuple(a.shape)} and {tuple(b.shape)}")
     a, b = a.contiguous().float(), b.contiguous().float()
     B, N, M = a.shape[0], a.shape[1], b.shape[1]
     d1 = torch.empty(B, N, dtype=torch.float32, device=a.device)
     d2 = torch.empty(B, M, dtype=torch.float32, device=a.device)
-    i1 = torch.empty(B, N, dtype=torch.int32, device=a.device)
-    i2 = torch.empty(B, M, dtype=torch.int32, device=a.device)
+    i1 = torch.empty((B, N) if with_indices else (0,), dtype=torch.int32, device=a.device)
+    i2 = torch.empty((B, M) if with_indices else (0,), dtype=torch.int32, device=a.device)
     with torch.cuda.device(a.device):
-        check(_lib.lib().nova_chamfer_nn(_ptr(a), _ptr(b), B, N, M, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2), _stream()),
-              "nova_chamfer_nn")
+        check(_lib.lib().nova_chamfer_nn(_ptr(a), _ptr(b), B, N, M, _ptr(d1), _ptr(d2), _ptr(i1) if with_indices else None,
+                                         _ptr(i2) if with_indices else None, _stream()), "nova_chamfer_nn")
     return d1, d2, i1, i2
 
 
 @chamfer_nn.register_fake
-def _(a, b):
+def _(a, b, with_indices=True):
     B, N, M = a.shape[0], a.shape[1], b.shape[1]
     return (a.new_empty((B, N), dtype=torch.float32), a.new_empty((B, M), dtype=torch.float32),
-            a.new_empty((B, N), dtype=torch.int32), a.new_empty((B, M), dtype=torch.int32))
+            a.new_empty((B, N) if with_indices else (0,), dtype=torch.int32),
+            a.new_empty((B, M) if with_indices else (0,), dtype=torch.int32))
 
 
 def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: str, epilogue: str) -> torch.Tensor:

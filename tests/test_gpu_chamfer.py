@@ -20,6 +20,8 @@ def test_nn_matches_scipy(B, N, M):
     a = rng.uniform(-1, 1, (B, N, 3)).astype(np.float32)
     b = rng.uniform(-1, 1, (B, M, 3)).astype(np.float32)
     d1, d2, i1, i2 = nb.chamfer_nn(torch.from_numpy(a), torch.from_numpy(b))
+    e1, e2, n1, n2 = nb.chamfer_nn(torch.from_numpy(a), torch.from_numpy(b), with_indices=False)
+    assert torch.equal(e1, d1) and torch.equal(e2, d2) and n1.numel() == 0 and n2.numel() == 0  # distance-only kernel
     for k in range(B):
         m1, m2, j1, j2 = OC.nn_dist(a[k], b[k])
         assert np.abs(d1[k].cpu().numpy() - m1).max() < 1e-6
