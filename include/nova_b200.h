@@ -126,6 +126,10 @@ NOVA_API int nova_head_forward(const nova_head_t* h, const float* x_tok, const f
  *   timesteps [S] host fp32, sigmas [S+1] host fp64  (the scheduler's own values)
  *   x_out     [Bx, N, T] fp32   patchify(x_S).  Tokens outside pred_ids follow the
  *                               reference's x <- x + dt*x recurrence (two roundings per step).
+ * The S-step loop touches only `workspace`; when the same (workspace address, shapes, schedule, guidance)
+ * comes back the library replays a CUDA graph it captured on the second call (bit-identical results,
+ * NOVA_B200_GRAPH=0 disables).  Keep the workspace address stable across calls to benefit.  If `stream` is
+ * itself being captured the launches go into the caller's graph instead.
  */
 NOVA_API int nova_head_sample(const nova_head_t* h, const float* noise_tok, const void* z, const int64_t* pred_ids,
                      int64_t B, int64_t Bx, int64_t N, int64_t n, const float* timesteps_host,
