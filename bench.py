@@ -372,8 +372,9 @@ def main():
             "config": {"workload": args.workload + ": " + wl["desc"], "points": N, "width": D, "depth": DEPTH,
                        "diffusion_steps": S_STEPS, "clouds_per_gpu": B, "rows_per_head_call": B * N,
                        "parallelism": f"dp{world} (clouds sharded, one all-gather of outputs)",
-                       "l2": "inputs larger than L2: per-step activations 6 x M x D x 2 B = "
-                             f"{6 * B * N * D * 2 / 1e6:.0f} MB + AdaLN stats {B * N * 20 * D * 2 / 1e6:.0f} MB stream through HBM"},
+                       "l2": "inputs larger than L2 (126 MB): every [M, D] bf16 activation is "
+                             f"{B * N * D * 2 / 1e6:.0f} MB and a diffusion step streams ~85 of them "
+                             f"({85 * B * N * D * 2 / 1e9:.1f} GB) through HBM; weights {32 * D * D * 2 / 1e6:.0f} MB stay L2-resident"},
             "head_tokens_per_s": value * N,
             "token_steps_per_s": value * N * S_STEPS,
             "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e,
