@@ -268,6 +268,9 @@ struct EpiParams {
   int64_t ldx;
   const float* rowstats;  // [M, 2] = (mean, rstd) of x, eps 1e-6
   int n_mod_tiles;
+  // Row-block order: consecutive kernels of a step alternate between ascending and descending row blocks, so a
+  // kernel starts on the rows its producer wrote LAST -- the part of a 100 MB activation still in the 126 MB L2.
+  int reverse_m;
 };
 
 __device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
@@ -339,7 +342,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int m_idx = (tile / num_n) * (BM * CG) + static_cast<int>(rank) * BM;
+        const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
+        const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM;
         const int n_idx = (tile % num_n) * BN + static_cast<int>(rank) * P::B_ROWS;  // CG == 2: my half of W
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, dbg, 0x100u | stage);
@@ -396,7 +400,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int buf = 0, cpar = 0;
     uint32_t buf_phase = 0;
     for (int tile = group; tile < num_tiles; tile += num_groups) {
-      const int m_idx = (tile / num_n) * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
+      const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
+      const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
       float* bias_s = bias_all;
       epi_bar_sync();  // every epilogue warp has finished reading the previous tile's bias
       for (int j = tid_e; j < BN; j += 128)
@@ -545,7 +550,7 @@ struct AdaLNArgs {
 
 template <int EPI, int CG>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
-               int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr) {
+               int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false) {
   using P = Plan<CG>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -557,7 +562,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
   NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, P::B_ROWS));
   EpiParams p{};
-  p.bias = bias; p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.M = M; p.N = N; p.K = K; p.reverse_m = reverse_m ? 1 : 0;
   if (EPI == EPI_ADALN) {
     // C = h [M, features] fed by the mod tiles; gate [M, N - 2 features] fed by the remaining tiles
     NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, ada->features, ldc, 32));
@@ -592,7 +597,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
 
 // cta_group selection: 0 = automatic (CTA pairs once there are at least 2 x 128 rows), 1, 2
 inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
-                  int M, int N, int K, int epi, cudaStream_t stream, int cta_group = 0) {
+                  int M, int N, int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false) {
   if (M <= 0 || N <= 0) return NOVA_OK;
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tcgen05 gemm: K, lda, ldw must be multiples of 8");
   NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
@@ -600,10 +605,10 @@ inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const 
                "tcgen05 gemm: operands must be 16-byte aligned");
   if (cta_group == 0) cta_group = default_cta_group(M);
   if (cta_group == 2)
-    return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
-                           : launch_epi<EPI_BIAS_SILU, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-  return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream)
-                         : launch_epi<EPI_BIAS_SILU, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+    return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m)
+                           : launch_epi<EPI_BIAS_SILU, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
+  return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m)
+                         : launch_epi<EPI_BIAS_SILU, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
 }
 
 // AdaLN statistics GEMM with the modulation fused into the epilogue:
@@ -611,7 +616,7 @@ inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const 
 //   h [M, features] = LN(x)(1 + scale) + shift,  gate [M, gate_cols] = a W_gate^T + b_gate.
 inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* h_out,
                         int64_t ldh, const AdaLNArgs& ada, int M, int N, int K, cudaStream_t stream,
-                        int cta_group = 0) {
+                        int cta_group = 0, bool reverse_m = false) {
   if (M <= 0 || N <= 0) return NOVA_OK;
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldh % 8 == 0 && ada.ldx % 8 == 0,
                "tcgen05 adaln gemm: K and leading dimensions must be multiples of 8");
@@ -620,8 +625,8 @@ inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, 
   NOVA_REQUIRE(ada.x && ada.rowstats && (N == 2 * ada.features || ada.gate), "tcgen05 adaln gemm: null operand");
   if (cta_group == 0) cta_group = default_cta_group(M);
   if (cta_group == 2)
-    return launch_epi<EPI_ADALN, 2>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada);
-  return launch_epi<EPI_ADALN, 1>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada);
+    return launch_epi<EPI_ADALN, 2>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada, reverse_m);
+  return launch_epi<EPI_ADALN, 1>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada, reverse_m);
 }
 
 }  // namespace tc

@@ -67,6 +67,7 @@ struct nova_head {
   float *w_t1 = nullptr, *b_t1 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr;
   float *w_patch = nullptr, *b_patch = nullptr, *w_head = nullptr, *b_head = nullptr;
   bool use_simt_gemm = false;  // NOVA_B200_GEMM=simt: isolate tcgen05 problems (bf16 handle only)
+  bool alternate_rows = true;  // NOVA_B200_ALTERNATE=0: every kernel walks the row blocks in ascending order
   // Overlapping the HBM-bound row kernels with the tensor-bound GEMMs was tried twice in round 1 and is
   // NOT in the code: (a) two streams over row halves -- CTAs of another kernel are not
   // scheduled next to a persistent GEMM CTA even when registers and shared memory would allow it;
@@ -229,33 +230,36 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
   tc::AdaLNArgs ada{};
   ada.x = x; ada.ldx = D; ada.rowstats = w.rstat; ada.gate = gate; ada.ldg = D; ada.features = D;
   const bf16* w_il = static_cast<const bf16*>(h->w_ada_il);
+  // Row-block direction alternates from launch to launch: each kernel starts on the rows its producer wrote last.
+  bool rev = h->alternate_rows;  // embed wrote x ascending
+  auto flip = [&]() { const bool r = rev; if (h->alternate_rows) rev = !rev; return r; };
   for (int i = 0; i < depth; ++i) {
     {
       ProfileScope ps(KC_GEMM_ADA, s);
       NOVA_PROPAGATE(tc::launch_adaln(a, D, w_il + (size_t)3 * i * D * D, D, h->b_ada_il + (size_t)3 * i * D, hh, D, ada,
-                                      (int)M, 3 * D, D, s));
+                                      (int)M, 3 * D, D, s, 0, flip()));
     }
     {
       ProfileScope ps(KC_GEMM_FC, s);
       NOVA_PROPAGATE(tc::launch(hh, D, static_cast<const bf16*>(h->w_fc1[i]), D, h->b_fc1[i], u1, D, (int)M, D, D,
-                                EPI_BIAS_SILU, s));
+                                EPI_BIAS_SILU, s, 0, flip()));
     }
     {
       ProfileScope ps(KC_GEMM_FC, s);
       NOVA_PROPAGATE(tc::launch(u1, D, static_cast<const bf16*>(h->w_fc2[i]), D, h->b_fc2[i], u2, D, (int)M, D, D,
-                                EPI_BIAS, s));
+                                EPI_BIAS, s, 0, flip()));
     }
     ProfileScope ps(KC_ROW, s);
     NOVA_PROPAGATE((rw::dispatch_vpl<bf16, rw::ResidLauncher>(D, (const bf16*)u2, (const bf16*)x, (const bf16*)gate,
                                                              (const float*)h->gamma[i], (const float*)h->beta[i], x,
-                                                             w.rstat, M, D, s)));
+                                                             w.rstat, M, D, (int)flip(), s)));
   }
   {
     ProfileScope ps(KC_GEMM_ADA, s);
     tc::AdaLNArgs fin = ada;
     fin.gate = nullptr;
     NOVA_PROPAGATE(tc::launch_adaln(a, D, w_il + (size_t)3 * depth * D * D, D, h->b_ada_il + (size_t)3 * depth * D, hh,
-                                    D, fin, (int)M, 2 * D, D, s));
+                                    D, fin, (int)M, 2 * D, D, s, 0, flip()));
   }
   ProfileScope ps(KC_ROW, s);
   return rw::dispatch_vpl<bf16, rw::HeadoutLauncher>(D, (const bf16*)hh, (const float*)h->w_head,
@@ -588,6 +592,7 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   const char* env = std::getenv("NOVA_B200_GEMM");
   h->use_simt_gemm = env != nullptr && std::strcmp(env, "simt") == 0;
   if (const char* env_wide = std::getenv("NOVA_B200_WIDE_ADA_ROWS")) h->wide_ada_rows = std::atoll(env_wide);
+  if (const char* env_alt = std::getenv("NOVA_B200_ALTERNATE")) h->alternate_rows = std::atoi(env_alt) != 0;
   const char* env_graph = std::getenv("NOVA_B200_GRAPH");
   h->use_graphs = env_graph == nullptr || std::atoi(env_graph) != 0;
   if (h->use_graphs && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {

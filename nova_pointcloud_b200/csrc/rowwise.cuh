@@ -379,12 +379,13 @@ template <typename AT, int VPL>
 __global__ void __launch_bounds__(RESID_THREADS, (VPL <= 4 ? 8 : 4))  // 64 registers up to D = 1024, 128 above
 resid_kernel(const AT* __restrict__ u, const AT* __restrict__ x_in, const AT* __restrict__ gate,
              const float* __restrict__ gamma, const float* __restrict__ beta, AT* __restrict__ x_out,
-             float* __restrict__ rowstats, int64_t M, int D) {
+             float* __restrict__ rowstats, int64_t M, int D, int reverse) {
   static_assert(sizeof(AT) == 2, "resid_kernel is the bf16 fused-path kernel");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * RESID_WARPS + warp;
+  int64_t row = (int64_t)blockIdx.x * RESID_WARPS + warp;
   pdl_trigger();
   if (row >= M) return;
+  if (reverse) row = M - 1 - row;  // start on the rows the producer wrote last (still in L2)
   pdl_wait();
   const float inv_d = 1.0f / static_cast<float>(D);
   const uint4* up = reinterpret_cast<const uint4*>(u + row * D) + lane;
@@ -621,9 +622,9 @@ struct EmbedLauncher {
 template <typename AT, int VPL>
 struct ResidLauncher {
   static int run(const AT* u, const AT* x_in, const AT* gate, const float* gamma, const float* beta, AT* x_out,
-                 float* rowstats, int64_t M, int D, cudaStream_t s) {
+                 float* rowstats, int64_t M, int D, int reverse, cudaStream_t s) {
     launch_pdl(resid_kernel<AT, VPL>, dim3((unsigned)ceil_div(M, RESID_WARPS)), dim3(RESID_THREADS), 0, s, u, x_in, gate,
-               gamma, beta, x_out, rowstats, M, D);
+               gamma, beta, x_out, rowstats, M, D, reverse);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   }
