@@ -283,7 +283,7 @@ def main():
 
     # ---- secondary legs (rank 0, reported beside the headline; bounded to ~2 s)
     extras = {}
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:  # single-GPU only: other ranks must not wait on rank 0's extras
         try:  # set-by-set autoregressive generation (the reference's generate_frame pattern): 64 cosine-schedule sets
             sizes = nb.partition.cosine_num_preds(N, 64)
             gen = torch.Generator(device=dev).manual_seed(7)
