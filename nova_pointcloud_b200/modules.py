@@ -15,6 +15,7 @@ from __future__ import annotations
 from typing import Optional, Tuple
 
 import torch
+from einops import rearrange
 from torch import nn
 
 from . import ops
@@ -22,13 +23,18 @@ from ._lib import NovaError
 
 
 class PatchEmbed(nn.Module):
-    """Parameter holder + layout helpers of the reference PatchEmbed (embeddings.py:139-166)."""
+    """Holds the patch-embedding parameters (``proj``: Conv2d with kernel = stride = patch) under the reference's
+    names and converts between image layout (B,C,H*p,W*p) and token layout (B,N,p*p*C).  Token order follows the
+    reference's ``patchify`` (embeddings.py:152-158): row-major over patches, inside a patch (p_h, p_w, C) with the
+    channel fastest.  ``height`` / ``width`` (in patches) are remembered from the last 4-D input, as there."""
 
-    def __init__(self, image_dim, embed_dim, patch_size):
+    def __init__(self, image_dim: int, embed_dim: int, patch_size: int):
         super().__init__()
-        self.height = self.width = None
-        self.image_dim, self.patch_size = image_dim, patch_size
-        self.proj = nn.Conv2d(image_dim, embed_dim, patch_size, patch_size)
+        self.image_dim = image_dim
+        self.patch_size = patch_size
+        self.height = None
+        self.width = None
+        self.proj = nn.Conv2d(image_dim, embed_dim, kernel_size=patch_size, stride=patch_size)
 
     @property
     def hw(self) -> Tuple[int, int]:
@@ -36,19 +42,15 @@ class PatchEmbed(nn.Module):
 
     def set_hw(self, x: torch.Tensor):
         if x.dim() == 4:
-            self.height, self.width = x.size(-2) // self.patch_size, x.size(-1) // self.patch_size
+            self.height, self.width = x.shape[-2] // self.patch_size, x.shape[-1] // self.patch_size
 
     def patchify(self, x: torch.Tensor) -> torch.Tensor:
-        """(B,C,H*p,W*p) -> (B,N,p*p*C), channel fastest (embeddings.py:152-154)."""
         p = self.patch_size
-        x = x.reshape(-1, self.image_dim, self.height, p, self.width, p)
-        return x.permute(0, 2, 4, 3, 5, 1).flatten(1, 2).flatten(2, 4).contiguous()
+        return rearrange(x, "b c (h p) (w q) -> b (h w) (p q c)", p=p, q=p, h=self.height, w=self.width).contiguous()
 
     def unpatchify(self, x: torch.Tensor) -> torch.Tensor:
-        """Inverse of :meth:`patchify` (embeddings.py:156-158)."""
         p = self.patch_size
-        x = x.reshape(-1, self.height, self.width, p, p, self.image_dim)
-        return x.permute(0, 5, 1, 3, 2, 4).flatten(2, 3).flatten(3, 4).contiguous()
+        return rearrange(x, "b (h w) (p q c) -> b c (h p) (w q)", p=p, q=p, h=self.height, w=self.width).contiguous()
 
 
 class Projector(nn.Module):
@@ -74,9 +76,12 @@ class AdaLayerNormZero(nn.Module):
 class DiffusionBlock(nn.Module):
     def __init__(self, dim):
         super().__init__()
-        self.dim, self.mlp_checkpointing = dim, False  # attribute poked by training pipelines
+        self.dim = dim
+        self.mlp_checkpointing = False  # attribute poked by the reference's training pipelines
+        # construction order = the reference's (norm1, proj, norm2): same seed => same random init
         self.norm1 = AdaLayerNormZero(dim, num_stats=3, eps=1e-6)
-        self.proj, self.norm2 = Projector(dim, dim, dim), nn.LayerNorm(dim)
+        self.proj = Projector(dim, dim, dim)
+        self.norm2 = nn.LayerNorm(dim)
 
 
 class TimeCondEmbed(nn.Module):

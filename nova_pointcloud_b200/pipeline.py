@@ -28,30 +28,43 @@ from .modules import DiffusionMLP
 from .schedulers import FlowMatchEulerDiscreteScheduler
 
 
-class GuidanceScaler(object):
-    def __init__(self, **kwargs):
-        self.guidance_scale = kwargs.get("guidance_scale", 1)
-        self.guidance_trunc = kwargs.get("guidance_trunc", 0)
-        self.guidance_renorm = kwargs.get("guidance_renorm", 1)
-        self.image_guidance_scale = kwargs.get("image_guidance_scale", 0)
-        self.spatiotemporal_guidance_scale = kwargs.get("spatiotemporal_guidance_scale", 0)
-        self.min_guidance_scale = kwargs.get("min_guidance_scale", None) or self.guidance_scale
-        self.inc_guidance_scale = self.guidance_scale - self.min_guidance_scale
-        if self.extra_pass:
+class GuidanceScaler:
+    """The numbers of classifier-free guidance and their per-set decay; the arithmetic on velocities
+    (scale / renorm / truncation) runs inside ``nova_head_sample``.
+
+    Behaviour follows the reference class: the floor of the decay is ``min_guidance_scale`` (the scale itself when
+    none is given), ``decay_guidance_scale(d)`` sets ``scale = floor + (initial - floor) * d``, ``clone()`` copies
+    the CURRENT numbers, ``expand(x)`` doubles the batch while guidance is on.
+    """
+
+    _NUMBERS = ("guidance_scale", "guidance_trunc", "guidance_renorm", "image_guidance_scale",
+                "spatiotemporal_guidance_scale", "min_guidance_scale")
+
+    def __init__(self, guidance_scale=1, guidance_trunc=0, guidance_renorm=1, image_guidance_scale=0,
+                 spatiotemporal_guidance_scale=0, min_guidance_scale=None, **_unused):
+        if image_guidance_scale + spatiotemporal_guidance_scale > 0:
             raise NovaError("three-pass guidance (image / spatiotemporal) is not on the point-cloud path")
+        floor = min_guidance_scale if min_guidance_scale else guidance_scale
+        self.guidance_scale = guidance_scale
+        self.guidance_trunc = guidance_trunc
+        self.guidance_renorm = guidance_renorm
+        self.image_guidance_scale = image_guidance_scale
+        self.spatiotemporal_guidance_scale = spatiotemporal_guidance_scale
+        self.min_guidance_scale = floor
+        self.inc_guidance_scale = guidance_scale - floor
 
     @property
     def extra_pass(self) -> bool:
-        return self.image_guidance_scale + self.spatiotemporal_guidance_scale > 0
+        return False  # rejected in __init__
 
-    def clone(self):
-        return GuidanceScaler(**self.__dict__)
+    def clone(self) -> "GuidanceScaler":
+        return GuidanceScaler(**{k: getattr(self, k) for k in self._NUMBERS})
 
     def decay_guidance_scale(self, decay=0):
-        self.guidance_scale = self.inc_guidance_scale * decay + self.min_guidance_scale
+        self.guidance_scale = self.min_guidance_scale + self.inc_guidance_scale * decay
 
     def expand(self, x: torch.Tensor) -> torch.Tensor:
-        """[x; x] along the batch when guidance is on (guidance_scaler.py:46-50)."""
+        """[x; x] along the batch while guidance is on, else x."""
         return torch.cat([x, x]) if self.guidance_scale > 1 else x
 
 

@@ -11,41 +11,56 @@ called as ``f(patch_size=, image_dim=, cond_dim=)`` (transformer_nova.py:48-53,7
 
 from __future__ import annotations
 
-import collections
 import functools
 
 from .modules import DiffusionMLP
 
 
-class Registry(object):
-    def __init__(self, name):
-        self.name = name
-        self.registry = collections.OrderedDict()
+class Registry:
+    """Name -> factory table.  Written against the behaviour of the reference class, not its code:
 
-    def has(self, key) -> bool:
-        return key in self.registry
+    * ``register(name_or_names, func=None, **defaults)`` binds ``defaults`` to ``func`` and files the bound
+      factory under every given name; with ``func=None`` it returns a decorator that leaves ``func`` unchanged;
+    * ``get(name, default=None)``: ``None`` for ``name is None``, the factory if present, else ``default`` when
+      one is given, else ``KeyError``;  ``has`` / ``try_get`` never raise;  ``registry`` exposes the table.
+    """
+
+    def __init__(self, name: str):
+        self.name = name
+        self._table = {}
+
+    @property
+    def registry(self):
+        return self._table
+
+    def _file(self, names, func, defaults):
+        factory = functools.partial(func, **defaults)
+        for key in (names if isinstance(names, (list, tuple)) else (names,)):
+            self._table[key] = factory
 
     def register(self, name, func=None, **kwargs):
-        def decorated(inner_function):
-            for key in name if isinstance(name, (tuple, list)) else [name]:
-                self.registry[key] = functools.partial(inner_function, **kwargs)
-            return inner_function
+        if func is None:
+            def as_decorator(fn):
+                self._file(name, fn, kwargs)
+                return fn
 
-        if func is not None:
-            return decorated(func)
-        return decorated
+            return as_decorator
+        self._file(name, func, kwargs)
+        return func
+
+    def has(self, key) -> bool:
+        return key in self._table
+
+    def try_get(self, name):
+        return self._table.get(name)
 
     def get(self, name, default=None):
         if name is None:
             return None
-        if not self.has(name):
-            if default is not None:
-                return default
-            raise KeyError("`%s` is not registered in <%s>." % (name, self.name))
-        return self.registry[name]
-
-    def try_get(self, name):
-        return self.get(name) if self.has(name) else None
+        factory = self._table.get(name, default)
+        if factory is None:
+            raise KeyError(f"`{name}` is not registered in <{self.name}>.")
+        return factory
 
 
 POINT_CLOUD_DECODERS = Registry("point_cloud_decoders")

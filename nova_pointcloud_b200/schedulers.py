@@ -25,66 +25,88 @@ class FlowMatchEulerDiscreteSchedulerOutput:
     prev_sample: torch.Tensor
 
 
+def _shift_sigmas(sigma: np.ndarray, shift: float) -> np.ndarray:
+    """sigma <- s*sigma / (1 + (s-1)*sigma) on a float32 grid (float32 arithmetic, numerator and
+    denominator formed separately, then one division: the order the golden schedules pin)."""
+    numerator = shift * sigma
+    denominator = 1 + (shift - 1) * sigma
+    return numerator / denominator
+
+
+def _exp_time_shift(mu: float, power: float, t):
+    """Dynamic shifting: e^mu / (e^mu + (1/t - 1)^power)."""
+    e = math.exp(mu)
+    return e / (e + (1 / t - 1) ** power)
+
+
 class FlowMatchEulerDiscreteScheduler:
+    """Host-side schedule + device-side Euler step.
+
+    Attributes the sampling loop reads: ``timesteps`` (float32 numpy, shifted sigma * 1000), ``sigmas``
+    (list of S+1 Python floats, last one 0), ``_step_index`` (reset by ``denoise``), ``config``, ``shift``.
+    """
+
     order = 1
 
-    def __init__(self, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False):
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 1.0, use_dynamic_shifting: bool = False):
         self.config = types.SimpleNamespace(num_train_timesteps=num_train_timesteps, shift=shift,
                                             use_dynamic_shifting=use_dynamic_shifting)
-        timesteps = np.arange(1, num_train_timesteps + 1, dtype="float32")[::-1]
-        sigmas, self._shift = timesteps / num_train_timesteps, shift
+        self._shift = shift
+        # training-time grid 1, (n-1)/n, ..., 1/n: only its two ends matter for sampling (sigma_max / sigma_min)
+        grid = np.arange(num_train_timesteps, 0, -1).astype("float32") / num_train_timesteps
         if not use_dynamic_shifting:
-            sigmas = shift * sigmas / (1 + (shift - 1) * sigmas)
-        self.timesteps = torch.as_tensor(sigmas * num_train_timesteps)
-        self.sigmas = torch.as_tensor(sigmas)
-        self.sigma_min, self.sigma_max = float(sigmas[-1]), float(sigmas[0])
+            grid = _shift_sigmas(grid, shift)
+        self.sigmas = torch.from_numpy(np.ascontiguousarray(grid))
+        self.timesteps = self.sigmas * num_train_timesteps
+        self.sigma_max, self.sigma_min = float(grid[0]), float(grid[-1])
         self.timestep = self.sigma = None
-        self._begin_index = self._step_index = None
         self.num_inference_steps = None
+        self._begin_index = None
+        self._step_index = None
 
-    shift = property(lambda self: self._shift)
-    step_index = property(lambda self: self._step_index)
-    begin_index = property(lambda self: self._begin_index)
+    @property
+    def shift(self) -> float:
+        return self._shift
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    @property
+    def begin_index(self):
+        return self._begin_index
 
     def set_shift(self, shift: float):
         self._shift = shift
 
-    def _sigma_to_t(self, sigma):
-        return sigma * self.config.num_train_timesteps
-
     def time_shift(self, mu: float, sigma: float, t):
-        return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** sigma)
+        return _exp_time_shift(mu, sigma, t)
 
-    def index_for_timestep(self, timestep, schedule_timesteps=None):
-        ts = np.asarray(self.timesteps if schedule_timesteps is None else schedule_timesteps)
-        indices = np.nonzero(ts == np.float32(timestep))[0]
-        if len(indices) == 0:
+    def index_for_timestep(self, timestep, schedule_timesteps=None) -> int:
+        grid = np.asarray(self.timesteps if schedule_timesteps is None else schedule_timesteps)
+        hits = np.flatnonzero(grid == np.float32(timestep))
+        if hits.size == 0:
             raise NovaError(f"timestep {timestep} is not on the schedule")
-        return int(indices[1 if len(indices) > 1 else 0])
+        return int(hits[1] if hits.size > 1 else hits[0])  # a repeated value resolves to its second occurrence
 
-    def _init_step_index(self, timestep):
-        self._step_index = self.index_for_timestep(timestep) if self.begin_index is None else self._begin_index
-
-    def set_timesteps(self, num_inference_steps, mu=None):
+    def set_timesteps(self, num_inference_steps: int, mu=None):
+        """S points from sigma_max*1000 down to sigma_min*1000 (float32 linspace), shifted; sigmas gets a final 0."""
+        n_train = self.config.num_train_timesteps
         self.num_inference_steps = num_inference_steps
-        t_max, t_min = self._sigma_to_t(self.sigma_max), self._sigma_to_t(self.sigma_min)
-        timesteps = np.linspace(t_max, t_min, num_inference_steps, dtype="float32")
-        sigmas = timesteps / self.config.num_train_timesteps
-        if self.config.use_dynamic_shifting:
-            sigmas = self.time_shift(mu, 1.0, sigmas)
-        else:
-            sigmas = self.shift * sigmas / (1 + (self.shift - 1) * sigmas)
-        self.sigmas = sigmas.tolist() + [0]
-        self.timesteps = sigmas * self.config.num_train_timesteps
-        self._begin_index = self._step_index = None
+        raw = np.linspace(self.sigma_max * n_train, self.sigma_min * n_train, num_inference_steps, dtype="float32")
+        sigma = raw / n_train
+        sigma = _exp_time_shift(mu, 1.0, sigma) if self.config.use_dynamic_shifting else _shift_sigmas(sigma, self._shift)
+        self.timesteps = sigma * n_train
+        self.sigmas = [float(v) for v in sigma] + [0]
+        self._begin_index = None
+        self._step_index = None
 
     def step(self, model_output, timestep, sample, generator=None, return_dict=True):
-        """prev_sample = model_output * dt + sample on the device (CUDA only)."""
-        if self.step_index is None:
-            self._init_step_index(timestep)
-        dt = self.sigmas[self.step_index + 1] - self.sigmas[self.step_index]
+        """prev_sample = model_output * dt + sample on the device (CUDA only), dt = sigma[i+1] - sigma[i]."""
+        if self._step_index is None:
+            self._step_index = self._begin_index if self._begin_index is not None else self.index_for_timestep(timestep)
+        i = self._step_index
+        dt = self.sigmas[i + 1] - self.sigmas[i]
         prev_sample = torch.ops.nova_b200.euler_step(model_output, sample.to(model_output.dtype), float(dt))
-        self._step_index += 1
-        if not return_dict:
-            return (prev_sample,)
-        return FlowMatchEulerDiscreteSchedulerOutput(prev_sample=prev_sample)
+        self._step_index = i + 1
+        return FlowMatchEulerDiscreteSchedulerOutput(prev_sample=prev_sample) if return_dict else (prev_sample,)
