@@ -27,7 +27,8 @@
 namespace nova {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;   // BM = rows per CTA, BN = tile columns
+constexpr int BM = 128, BK = 64, UMMA_K = 16;   // BM = rows per CTA; tile columns BN are a template parameter
+constexpr int BN_FULL = 256;                    // the large-M tile (and the only one EPI_ADALN supports)
 constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
@@ -37,15 +38,17 @@ constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;             // one warp's 32 x 64 
 
 // Per-CTA shared-memory plan for cta_group CG (1: one CTA per 128x256 tile, 2: a CTA pair per
 // 256x256 tile, each CTA holding its 128 rows of A and HALF of the W tile).
-template <int CG>
+template <int CG, int BN>
 struct Plan {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "tile columns: 64 / 128 (small M: more, shorter tiles) or 256");
   static constexpr int B_ROWS = BN / CG;                         // W rows this CTA loads per stage
-  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;          // 32 KB / 16 KB
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB / 32 KB
-  static constexpr int STAGES = CG == 1 ? 4 : 6;                 // 192 KB of operand ring either way
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;          // BN = 256: 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // BN = 256: 48 KB / 32 KB
+  static constexpr int RING = 192 * 1024 / STAGE_BYTES;          // up to 192 KB of operand ring ...
+  static constexpr int STAGES = RING > 8 ? 8 : RING;             // ... in at most 8 stages (4 / 6 at BN = 256)
   static constexpr int OFF_CSTAGE = STAGES * STAGE_BYTES;        // 4 warps x 2 buffers x 4 KB
   static constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;  // one BN fp32 bias tile
-  static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+  static constexpr int OFF_BAR = OFF_BIAS + BN_FULL * 4;
   // 230 656 B: with the 1 KB the hardware reserves per CTA this leaves >= 1 KB of the SM's 228 KB, so a
   // CTA of a shared-memory-free kernel (the HBM-bound row kernels, launched on a second stream) can be
   // co-resident with a persistent GEMM CTA and its memory traffic overlaps the MMAs.
@@ -281,12 +284,13 @@ __device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-template <int EPI, int CG>
+template <int EPI, int CG, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
             const EpiParams p, uint32_t* dbg) {
-  using P = Plan<CG>;
+  using P = Plan<CG, BN>;
+  static_assert(EPI != EPI_ADALN || BN == BN_FULL, "the AdaLN epilogue pairs 128 scale + 128 shift columns per tile");
   constexpr int STAGES = P::STAGES, STAGE_BYTES = P::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = smem_raw;
@@ -538,6 +542,7 @@ uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (de
 extern uint32_t* g_debug_host;  // the same words, host pointer
 int num_sms();
 int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
+int tile_columns_override();   // env NOVA_B200_TILE_N=64|128|256 forces the tile columns of the plain GEMMs (tests)
 
 struct AdaLNArgs {
   const bf16* x = nullptr;   // [M, ldx]
@@ -548,13 +553,13 @@ struct AdaLNArgs {
   int features = 0;          // D: mod tiles cover 2 D weight rows
 };
 
-template <int EPI, int CG>
+template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false) {
-  using P = Plan<CG>;
+  using P = Plan<CG, BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, CG, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          P::SMEM_BYTES));
     attr_done = true;
   }
@@ -590,7 +595,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG>, ta, tb, tc_, tc2, p, debug_word()));
+  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG, BN>, ta, tb, tc_, tc2, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
@@ -604,11 +609,25 @@ inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const 
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0,
                "tcgen05 gemm: operands must be 16-byte aligned");
   if (cta_group == 0) cta_group = default_cta_group(M);
-  if (cta_group == 2)
-    return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m)
-                           : launch_epi<EPI_BIAS_SILU, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
-  return epi == EPI_BIAS ? launch_epi<EPI_BIAS, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m)
-                         : launch_epi<EPI_BIAS_SILU, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
+  // Tile columns: 256 unless that leaves most SMs without a tile (small M: the set-by-set pattern); then the same
+  // work is cut into 128- or 64-column tiles -- more CTAs busy and a 2-4x shorter MMA chain per launch.
+  const int units = num_sms() / cta_group;
+  const int64_t row_blocks = ceil_div(M, BM * cta_group);
+  int bn = BN_FULL;
+  if (tile_columns_override() > 0) bn = tile_columns_override();
+  else if (row_blocks * ceil_div(N, 256) * 2 <= units) bn = row_blocks * ceil_div(N, 128) * 2 <= units ? 64 : 128;
+#define NOVA_GEMM_CASE(E, G, B) \
+  if (epi == E && cta_group == G && bn == B)  \
+    return launch_epi<E, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
+  NOVA_GEMM_CASE(EPI_BIAS, 2, 256) NOVA_GEMM_CASE(EPI_BIAS_SILU, 2, 256)
+  NOVA_GEMM_CASE(EPI_BIAS, 1, 256) NOVA_GEMM_CASE(EPI_BIAS_SILU, 1, 256)
+  NOVA_GEMM_CASE(EPI_BIAS, 2, 128) NOVA_GEMM_CASE(EPI_BIAS_SILU, 2, 128)
+  NOVA_GEMM_CASE(EPI_BIAS, 1, 128) NOVA_GEMM_CASE(EPI_BIAS_SILU, 1, 128)
+  NOVA_GEMM_CASE(EPI_BIAS, 2, 64) NOVA_GEMM_CASE(EPI_BIAS_SILU, 2, 64)
+  NOVA_GEMM_CASE(EPI_BIAS, 1, 64) NOVA_GEMM_CASE(EPI_BIAS_SILU, 1, 64)
+#undef NOVA_GEMM_CASE
+  set_error("tcgen05 gemm: unsupported epilogue %d / cta_group %d / tile columns %d", epi, cta_group, bn);
+  return NOVA_ERR_INVALID;
 }
 
 // AdaLN statistics GEMM with the modulation fused into the epilogue:
@@ -620,8 +639,9 @@ inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, 
   if (M <= 0 || N <= 0) return NOVA_OK;
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldh % 8 == 0 && ada.ldx % 8 == 0,
                "tcgen05 adaln gemm: K and leading dimensions must be multiples of 8");
-  NOVA_REQUIRE(ada.features % 128 == 0 && (2 * ada.features) % BN == 0 && N >= 2 * ada.features && N % BN == 0,
-               "tcgen05 adaln gemm: features must be a multiple of 128 and N a multiple of %d", BN);
+  NOVA_REQUIRE(ada.features % 128 == 0 && (2 * ada.features) % BN_FULL == 0 && N >= 2 * ada.features &&
+                   N % BN_FULL == 0,
+               "tcgen05 adaln gemm: features must be a multiple of 128 and N a multiple of %d", BN_FULL);
   NOVA_REQUIRE(ada.x && ada.rowstats && (N == 2 * ada.features || ada.gate), "tcgen05 adaln gemm: null operand");
   if (cta_group == 0) cta_group = default_cta_group(M);
   if (cta_group == 2)

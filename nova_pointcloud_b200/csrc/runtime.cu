@@ -135,6 +135,12 @@ int default_cta_group(int M) {
   return M > BM ? 2 : 1;  // a CTA pair needs more than one 128-row slab to be worth it
 }
 
+int tile_columns_override() {
+  const char* env = std::getenv("NOVA_B200_TILE_N");  // read per call: tests switch it between launches
+  const int v = env ? std::atoi(env) : 0;
+  return (v == 64 || v == 128 || v == 256) ? v : 0;
+}
+
 }  // namespace tc
 namespace rw {
 int num_sms_rw() { return tc::num_sms(); }

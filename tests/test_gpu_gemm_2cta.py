@@ -56,6 +56,37 @@ def test_bf16_gemm(impl, M, N, K, epi):
     assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
 
 
+@pytest.mark.parametrize("tile_n", ["64", "128"])
+@pytest.mark.parametrize("impl", ["tcgen05_1cta", "tcgen05_2cta"])
+@pytest.mark.parametrize("M,N,K", [
+    (128, 64, 64),        # one narrow tile
+    (64, 768, 768),       # the small-M fc shape: 12 / 6 tiles instead of 3
+    (300, 200, 104),      # ragged everything
+    (1000, 768, 1536),    # ring wraps with the deeper (8-stage) ring of the narrow tiles
+    (5000, 1024, 256),    # more tiles than SMs
+])
+def test_narrow_tiles(monkeypatch, tile_n, impl, M, N, K):
+    """64- and 128-column tiles (chosen automatically when 256-column tiles would leave most SMs idle)."""
+    from nova_pointcloud_b200 import ops
+
+    monkeypatch.setenv("NOVA_B200_TILE_N", tile_n)
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + int(tile_n))
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    for epi in ("bias", "bias_silu"):
+        out = ops.debug_gemm(A, W, b, impl, epi)
+        torch.cuda.synchronize()
+        ref = ref_gemm(A, W, b, epi)
+        err = (out.float() - ref).abs()
+        tol = 2.0**-8 * ref.abs() + 1e-2
+        assert bool((err <= tol).all()), f"{epi}: max err {float(err.max())} at {int(err.argmax())}"
+    monkeypatch.setenv("NOVA_B200_TILE_N", "256")
+    wide = ops.debug_gemm(A, W, b, impl, "bias")
+    monkeypatch.setenv("NOVA_B200_TILE_N", tile_n)
+    assert torch.equal(wide, ops.debug_gemm(A, W, b, impl, "bias"))  # same k order per output element: same bits
+
+
 @pytest.mark.parametrize("impl", ["tcgen05_2cta", "tcgen05"])
 def test_tcgen05_no_bias_and_repeatability(impl):
     from nova_pointcloud_b200 import ops
