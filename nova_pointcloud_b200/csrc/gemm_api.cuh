@@ -1,0 +1,48 @@
+// Host-side interface of the tcgen05 GEMM (definitions: gemm.cu = gemm_tcgen05.cuh, helpers in runtime.cu).
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace nova {
+namespace tc {
+
+constexpr int BM = 128;       // rows per CTA tile
+constexpr int BK = 64;        // K elements per pipeline stage (one 128 B swizzle atom of bf16)
+constexpr int BN_FULL = 256;  // tile columns at large M (and the only width EPI_ADALN supports)
+
+// K-major bf16 matrix [rows, K] with row stride ld (elements) -> 2D tiled map, 128 B swizzle,
+// box = {64 elements of K, box_rows}.  Out-of-bounds elements are zero-filled by TMA.
+int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows);
+// The same encoding serves the output: [M, N] row-major, box = {64 columns, 32 rows} per TMA store.
+uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (device pointer)
+extern uint32_t* g_debug_host;  // the same words, host pointer
+int num_sms();
+int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
+int tile_columns_override();   // env NOVA_B200_TILE_N=64|128|256 forces the tile columns of the plain GEMMs (tests)
+
+struct AdaLNArgs {
+  const bf16* x = nullptr;   // [M, ldx]
+  int64_t ldx = 0;
+  const float* rowstats = nullptr;  // [M, 2]
+  bf16* gate = nullptr;      // [M, ldg], columns N - 2 * features
+  int64_t ldg = 0;
+  int features = 0;          // D: mod tiles cover 2 D weight rows
+};
+
+// C[M,N] = epi(A[M,K] W[N,K]^T + bias), bf16 in / bf16 out, epi = EPI_BIAS | EPI_BIAS_SILU.
+// cta_group: 0 = automatic (CTA pairs once there are at least 2 x 128 rows), 1, 2.
+// reverse_m: walk the row blocks in descending order (see EpiParams::reverse_m).
+int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,
+           int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false);
+
+// AdaLN statistics GEMM with the modulation fused into the epilogue:
+//   W [2 features + gate_cols, K] packed per 128 features as [scale | shift], then gate rows;
+//   h [M, features] = LN(x)(1 + scale) + shift,  gate [M, gate_cols] = a W_gate^T + b_gate.
+int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* h_out, int64_t ldh,
+                 const AdaLNArgs& ada, int M, int N, int K, cudaStream_t stream, int cta_group = 0,
+                 bool reverse_m = false);
+
+}  // namespace tc
+}  // namespace nova

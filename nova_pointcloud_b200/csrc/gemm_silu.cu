@@ -1,0 +1,3 @@
+// tcgen05 GEMM instantiations, part 1 of 3 (see the NOVA_GEMM_TU note in gemm_tcgen05.cuh).
+#define NOVA_GEMM_TU 1
+#include "gemm_tcgen05.cuh"

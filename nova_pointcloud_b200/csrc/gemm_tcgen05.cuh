@@ -15,6 +15,9 @@
 //   warps 4-7 epilogue       tcgen05.ld 32x32b -> bias (+SiLU) -> bf16 -> st.shared (128B swizzle)
 //                            -> cp.async.bulk.tensor store of 32 x 64 sub-tiles, double buffered
 //
+// This header is compiled by gemm_bias.cu / gemm_silu.cu / gemm_adaln.cu only (each instantiates the kernel
+// variants of one epilogue, NOVA_GEMM_TU selects which); other translation units include gemm_api.cuh.
+//
 // Every mbarrier wait is bounded: on timeout the kernel records where it was stuck in a
 // host-mapped debug word and traps, so a protocol bug surfaces as a CUDA error, not a hang.
 #pragma once
@@ -22,13 +25,13 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "gemm_api.cuh"
 #include "gemm_simt.cuh"  // Epilogue enum
 
 namespace nova {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16;   // BM = rows per CTA; tile columns BN are a template parameter
-constexpr int BN_FULL = 256;                    // the large-M tile (and the only one EPI_ADALN supports)
+constexpr int UMMA_K = 16;  // BM, BK, BN_FULL: gemm_api.cuh; tile columns BN are a template parameter
 constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
@@ -533,26 +536,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 }
 
-// ---------------------------------------------------------------- host side
-// K-major bf16 matrix [rows, K] with row stride ld (elements) -> 2D tiled map, 128 B swizzle,
-// box = {64 elements of K, box_rows}.  Out-of-bounds elements are zero-filled by TMA.
-int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows);
-// The same encoding serves the output: [M, N] row-major, box = {64 columns, 32 rows} per TMA store.
-uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (device pointer)
-extern uint32_t* g_debug_host;  // the same words, host pointer
-int num_sms();
-int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
-int tile_columns_override();   // env NOVA_B200_TILE_N=64|128|256 forces the tile columns of the plain GEMMs (tests)
-
-struct AdaLNArgs {
-  const bf16* x = nullptr;   // [M, ldx]
-  int64_t ldx = 0;
-  const float* rowstats = nullptr;  // [M, 2]
-  bf16* gate = nullptr;      // [M, ldg], columns N - 2 * features
-  int64_t ldg = 0;
-  int features = 0;          // D: mod tiles cover 2 D weight rows
-};
-
+// ---------------------------------------------------------------- host side (declarations: gemm_api.cuh)
 template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false) {
@@ -601,13 +585,47 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
 }
 
 // cta_group selection: 0 = automatic (CTA pairs once there are at least 2 x 128 rows), 1, 2
-inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
-                  int M, int N, int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false) {
+// The instantiations are spread over three translation units so that they compile in parallel:
+//   gemm_bias.cu (NOVA_GEMM_TU == 0): EPI_BIAS kernels + the `launch` dispatcher,
+//   gemm_silu.cu (NOVA_GEMM_TU == 1): EPI_BIAS_SILU kernels,   gemm_adaln.cu (NOVA_GEMM_TU == 2): EPI_ADALN kernels.
+template <int EPI>
+int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
+                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m) {
+#define NOVA_GEMM_CASE(G, B) \
+  if (cta_group == G && bn == B) \
+    return launch_epi<EPI, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
+  NOVA_GEMM_CASE(2, 256) NOVA_GEMM_CASE(1, 256) NOVA_GEMM_CASE(2, 128) NOVA_GEMM_CASE(1, 128) NOVA_GEMM_CASE(2, 64)
+  NOVA_GEMM_CASE(1, 64)
+#undef NOVA_GEMM_CASE
+  set_error("tcgen05 gemm: unsupported cta_group %d / tile columns %d", cta_group, bn);
+  return NOVA_ERR_INVALID;
+}
+int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m);
+int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m);
+
+#if NOVA_GEMM_TU == 1
+int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m) {
+  return launch_plain<EPI_BIAS_SILU>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m);
+}
+#endif
+
+#if NOVA_GEMM_TU == 0
+int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m) {
+  return launch_plain<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m);
+}
+
+int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,
+           int K, int epi, cudaStream_t stream, int cta_group, bool reverse_m) {
   if (M <= 0 || N <= 0) return NOVA_OK;
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tcgen05 gemm: K, lda, ldw must be multiples of 8");
   NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0,
                "tcgen05 gemm: operands must be 16-byte aligned");
+  NOVA_REQUIRE(epi == EPI_BIAS || epi == EPI_BIAS_SILU, "tcgen05 gemm: unsupported epilogue %d", epi);
   if (cta_group == 0) cta_group = default_cta_group(M);
   // Tile columns: 256 unless that leaves most SMs without a tile (small M: the set-by-set pattern); then the same
   // work is cut into 128- or 64-column tiles -- more CTAs busy and a 2-4x shorter MMA chain per launch.
@@ -616,26 +634,17 @@ inline int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const 
   int bn = BN_FULL;
   if (tile_columns_override() > 0) bn = tile_columns_override();
   else if (row_blocks * ceil_div(N, 256) * 2 <= units) bn = row_blocks * ceil_div(N, 128) * 2 <= units ? 64 : 128;
-#define NOVA_GEMM_CASE(E, G, B) \
-  if (epi == E && cta_group == G && bn == B)  \
-    return launch_epi<E, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
-  NOVA_GEMM_CASE(EPI_BIAS, 2, 256) NOVA_GEMM_CASE(EPI_BIAS_SILU, 2, 256)
-  NOVA_GEMM_CASE(EPI_BIAS, 1, 256) NOVA_GEMM_CASE(EPI_BIAS_SILU, 1, 256)
-  NOVA_GEMM_CASE(EPI_BIAS, 2, 128) NOVA_GEMM_CASE(EPI_BIAS_SILU, 2, 128)
-  NOVA_GEMM_CASE(EPI_BIAS, 1, 128) NOVA_GEMM_CASE(EPI_BIAS_SILU, 1, 128)
-  NOVA_GEMM_CASE(EPI_BIAS, 2, 64) NOVA_GEMM_CASE(EPI_BIAS_SILU, 2, 64)
-  NOVA_GEMM_CASE(EPI_BIAS, 1, 64) NOVA_GEMM_CASE(EPI_BIAS_SILU, 1, 64)
-#undef NOVA_GEMM_CASE
-  set_error("tcgen05 gemm: unsupported epilogue %d / cta_group %d / tile columns %d", epi, cta_group, bn);
-  return NOVA_ERR_INVALID;
+  return epi == EPI_BIAS ? launch_bias(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m)
+                         : launch_silu(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m);
 }
+#endif
 
+#if NOVA_GEMM_TU == 2
 // AdaLN statistics GEMM with the modulation fused into the epilogue:
 //   W [2 features + gate_cols, K] packed per 128 features as [scale | shift], then gate rows;
 //   h [M, features] = LN(x)(1 + scale) + shift,  gate [M, gate_cols] = a W_gate^T + b_gate.
-inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* h_out,
-                        int64_t ldh, const AdaLNArgs& ada, int M, int N, int K, cudaStream_t stream,
-                        int cta_group = 0, bool reverse_m = false) {
+int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* h_out, int64_t ldh,
+                 const AdaLNArgs& ada, int M, int N, int K, cudaStream_t stream, int cta_group, bool reverse_m) {
   if (M <= 0 || N <= 0) return NOVA_OK;
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldh % 8 == 0 && ada.ldx % 8 == 0,
                "tcgen05 adaln gemm: K and leading dimensions must be multiples of 8");
@@ -648,6 +657,8 @@ inline int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, 
     return launch_epi<EPI_ADALN, 2>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada, reverse_m);
   return launch_epi<EPI_ADALN, 1>(A, lda, W, ldw, bias, h_out, ldh, M, N, K, stream, &ada, reverse_m);
 }
+
+#endif  // NOVA_GEMM_TU == 2
 
 }  // namespace tc
 }  // namespace nova

@@ -22,7 +22,7 @@
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include "gemm_tcgen05.cuh"
+#include "gemm_api.cuh"
 #include "rowwise.cuh"
 
 using namespace nova;
