@@ -308,6 +308,30 @@ def main():
                 "what": "64-set cosine schedule, every set = one fused 25-step call over B*n rows (CUDA-graph replay)"}
         except Exception as e:  # report, never hide
             extras["set_by_set"] = {"error": str(e)[:300]}
+        try:  # classifier-free guidance (the default of the reference's non-point-cloud pipelines): 2x rows per cloud
+            Bg = max(B // 2, 1)
+            gs = nb.GuidanceScaler(guidance_scale=5.0)
+            zg = torch.cat([z_d[:Bg], torch.zeros_like(z_d[:Bg])])
+
+            def guided_pass():
+                return nb.denoise(head, sched, zg, noise_d[:Bg], gs)
+
+            for _ in range(3):
+                guided_pass()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                guided_pass()
+            e1.record()
+            torch.cuda.synchronize()
+            g_ms = e0.elapsed_time(e1) / 2
+            extras["guided"] = {"value": Bg / (g_ms * 1e-3), "unit": "clouds/s", "ms_per_pass": g_ms, "clouds": Bg,
+                                "rows_per_head_call": 2 * Bg * N, "guidance_scale": 5.0,
+                                "what": "two-pass classifier-free guidance fused into the loop ([cond; uncond] rows, "
+                                        "v = vu + (vc - vu) s, Euler update in one kernel per step)"}
+        except Exception as e:
+            extras["guided"] = {"error": str(e)[:300]}
         try:  # Chamfer scorer, BASELINE configs[4]: 256 pairs of 2048 x 2048 points
             Bc, Nc = 256, 2048
             gc = torch.Generator(device=dev).manual_seed(11)
