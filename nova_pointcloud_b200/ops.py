@@ -8,6 +8,7 @@ torch supplies device memory and the current stream; all arithmetic happens in t
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -29,7 +30,9 @@ def _stream() -> C.c_void_p:
 class HeadHandle:
     """Owner of one ``nova_head_t``: packed weights of a DiffusionMLP on one device."""
 
-    _registry: Dict[int, "HeadHandle"] = {}
+    # id -> handle for the custom ops (their schema carries an int, not an object); weak, so that a handle -- and
+    # the device arena + CUDA graphs it owns -- is freed when its DiffusionMLP goes away
+    _registry: "weakref.WeakValueDictionary[int, HeadHandle]" = weakref.WeakValueDictionary()
     _next_id = 1
 
     def __init__(self, depth: int, width: int, cond_width: int, token_dim: int, dtype: torch.dtype, device):

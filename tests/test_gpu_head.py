@@ -238,6 +238,33 @@ def test_graph_replay_of_the_denoise_loop_is_bit_identical(monkeypatch, mode, dt
     assert torch.equal(other_schedule, eager3)
 
 
+def test_handle_is_released_with_its_module():
+    """The packed-weights arena (device memory the library owns) and the loop graphs die with the module."""
+    import gc
+
+    import nova_pointcloud_b200 as nb
+    from nova_pointcloud_b200 import ops
+
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    head = nb.synth.make_head(1024, 6, dtype=torch.bfloat16)
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(2)
+    noise, z = nb.synth.make_inputs(1, 64, 1024, dtype=torch.bfloat16)
+    for _ in range(3):
+        nb.denoise(head, sched, z, noise)
+    torch.cuda.synchronize()
+    hid = head._handle.id
+    held = free0 - torch.cuda.mem_get_info()[0]
+    assert hid in ops.HeadHandle._registry and held > 100 * 2**20  # > 100 MB of packed bf16 weights
+    del head, noise, z
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    assert hid not in ops.HeadHandle._registry
+    assert free0 - torch.cuda.mem_get_info()[0] < held - 100 * 2**20
+
+
 def test_weights_repack_after_update_and_errors():
     import nova_pointcloud_b200 as nb
 
