@@ -238,6 +238,32 @@ def test_graph_replay_of_the_denoise_loop_is_bit_identical(monkeypatch, mode, dt
     assert torch.equal(other_schedule, eager3)
 
 
+@pytest.mark.parametrize("name,depth,D,Dc,patch,chan,H,W", [
+    ("mlp_d6w1536 (NOVA-1.4B, xyz tokens)", 6, 1536, 1536, 1, 3, 300, 1),
+    ("mlp_d3w1280 (T2V head: token dim 16, cond width 1024)", 3, 1280, 1024, 2, 4, 10, 13),
+    ("mlp_d6w768 with the registry default token dim 16", 6, 768, 768, 2, 4, 37, 40),
+])
+def test_registry_heads_bf16_forward_and_sample(name, depth, D, Dc, patch, chan, H, W):
+    """Every registry width, including the generic (T != 3) embed / head kernels and Dc != D, in bf16:
+    one forward and a 3-step sample against the fp32 oracle on the bf16-rounded weights."""
+    import nova_pointcloud_b200 as nb
+
+    B = 2
+    head, x, z, t, _ = make_case(depth, D, Dc, B, H, W, patch=patch, chan=chan)
+    head = head.to(torch.bfloat16)
+    sd = cpu_sd(head, torch.float32)
+    zb = z.bfloat16()
+    ref = OH.head_forward(sd, x.bfloat16().float(), t, zb.float())
+    head = head.cuda()
+    out = head(x.cuda().bfloat16(), t.cuda(), zb.cuda())
+    assert relmax(out.float(), ref) < BF16_TOL, name
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(3)
+    got = nb.denoise(head, sched, zb.cuda(), x.cuda())
+    want = OL.denoise(sd, zb.float(), x, num_steps=3)
+    assert relmax(got, want) < BF16_TOL, name
+
+
 def test_handle_is_released_with_its_module():
     """The packed-weights arena (device memory the library owns) and the loop graphs die with the module."""
     import gc
