@@ -21,7 +21,8 @@ OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libnova_b200.so")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
-SOURCES = ["gemm_adaln.cu", "gemm_bias.cu", "gemm_silu.cu", "head.cu", "runtime.cu", "chamfer.cu"]
+SOURCES = ["rowwise_row_bf16.cu", "rowwise_row_f32.cu", "rowwise_fused.cu", "gemm_adaln.cu", "gemm_bias.cu", "gemm_silu.cu",
+           "head.cu", "runtime.cu", "chamfer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -160,6 +160,17 @@ int gemm<bf16>(const nova_head* h, const bf16* A, int64_t lda, const bf16* W, in
   return tc::launch(A, lda, W, ldw, bias, C, ldc, (int)M, N, K, epi, s);
 }
 
+template <typename AT>
+int launch_row_any(const rw::RowParams& p, bool has_prev, int out, cudaStream_t s);
+template <>
+int launch_row_any<float>(const rw::RowParams& p, bool has_prev, int out, cudaStream_t s) {
+  return rw::launch_row_f32(p, has_prev, out, s);
+}
+template <>
+int launch_row_any<bf16>(const rw::RowParams& p, bool has_prev, int out, cudaStream_t s) {
+  return rw::launch_row_bf16(p, has_prev, out, s);
+}
+
 struct TimeList {
   float v[MAX_STEPS];
 };
@@ -224,8 +235,7 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
   }
   {
     ProfileScope ps(KC_ROW, s);
-    NOVA_PROPAGATE((rw::dispatch_vpl<bf16, rw::EmbedLauncher>(D, io.x_tok, io.x_rows, h->w_patchT, h->b_patch, x,
-                                                             w.rstat, M, D, T, s)));
+    NOVA_PROPAGATE(rw::embed_bf16(io.x_tok, io.x_rows, h->w_patchT, h->b_patch, x, w.rstat, M, D, T, s));
   }
   tc::AdaLNArgs ada{};
   ada.x = x; ada.ldx = D; ada.rowstats = w.rstat; ada.gate = gate; ada.ldg = D; ada.features = D;
@@ -250,9 +260,7 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
                                 EPI_BIAS, s, 0, flip()));
     }
     ProfileScope ps(KC_ROW, s);
-    NOVA_PROPAGATE((rw::dispatch_vpl<bf16, rw::ResidLauncher>(D, (const bf16*)u2, (const bf16*)x, (const bf16*)gate,
-                                                             (const float*)h->gamma[i], (const float*)h->beta[i], x,
-                                                             w.rstat, M, D, (int)flip(), s)));
+    NOVA_PROPAGATE(rw::resid_bf16(u2, x, gate, h->gamma[i], h->beta[i], x, w.rstat, M, D, (int)flip(), s));
   }
   {
     ProfileScope ps(KC_GEMM_ADA, s);
@@ -262,9 +270,7 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
                                     D, fin, (int)M, 2 * D, D, s, 0, flip()));
   }
   ProfileScope ps(KC_ROW, s);
-  return rw::dispatch_vpl<bf16, rw::HeadoutLauncher>(D, (const bf16*)hh, (const float*)h->w_head,
-                                                     (const float*)h->b_head, io.v_out, io.x_tok, io.xt_out, io.dt, M,
-                                                     D, T, s);
+  return rw::headout_bf16(hh, h->w_head, h->b_head, io.v_out, io.x_tok, io.xt_out, io.dt, M, D, T, s);
 }
 
 template <typename AT>
@@ -300,7 +306,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   p.scale_off = depth > 0 ? 0 : final_off;
   {
     ProfileScope ps(KC_ROW, s);
-    NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/false, /*out=*/depth > 0 ? 0 : 1, s));
+    NOVA_PROPAGATE(launch_row_any<AT>(p, /*has_prev=*/false, /*out=*/depth > 0 ? 0 : 1, s));
   }
   for (int i = 0; i < depth; ++i) {
     {
@@ -319,7 +325,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
     p.beta = h->beta[i];
     p.scale_off = last ? final_off : static_cast<int64_t>(3) * (i + 1) * D;
     ProfileScope ps(KC_ROW, s);
-    NOVA_PROPAGATE(rw::launch_row<AT>(p, /*has_prev=*/true, /*out=*/last ? 1 : 0, s));
+    NOVA_PROPAGATE(launch_row_any<AT>(p, /*has_prev=*/true, /*out=*/last ? 1 : 0, s));
   }
   return NOVA_OK;
 }

@@ -835,5 +835,19 @@ __global__ void permute_patch_kernel(const TS* __restrict__ src, float* __restri
   dst[i] = to_float(src[((int64_t)(d * C + c) * p + ph) * p + pw]);
 }
 
+
+// ------------------------------------------------------------------ out-of-line entry points
+// The heavy instantiations (8 widths x kernel variants) live in their own translation units so that they build
+// in parallel with head.cu:  rowwise_row_f32.cu, rowwise_row_bf16.cu (launch_row) and rowwise_fused.cu (the
+// fused-dataflow kernels).  head.cu calls only these.
+int launch_row_f32(const RowParams& p, bool has_prev, int out, cudaStream_t stream);
+int launch_row_bf16(const RowParams& p, bool has_prev, int out, cudaStream_t stream);
+int embed_bf16(const float* x_tok, int64_t x_rows, const float* WpT, const float* bp, bf16* x_out, float* rowstats,
+               int64_t M, int D, int T, cudaStream_t stream);
+int resid_bf16(const bf16* u, const bf16* x_in, const bf16* gate, const float* gamma, const float* beta, bf16* x_out,
+               float* rowstats, int64_t M, int D, int reverse, cudaStream_t stream);
+int headout_bf16(const bf16* y, const float* Wh, const float* bh, float* v_out, const float* xt_in, float* xt_out, float dt,
+                 int64_t M, int D, int T, cudaStream_t stream);
+
 }  // namespace rw
 }  // namespace nova
