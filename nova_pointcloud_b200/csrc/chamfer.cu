@@ -15,6 +15,8 @@
 // their partial minima meet in shared memory at the end.  Loads of the xyz stream are
 // coalesced float reads; bandwidth is irrelevant here (16.8 MB for 1.07 G pair evaluations),
 // the limiter is fp32 issue rate: 3 FADD + 3 FFMA/FMUL + compare/select per pair.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nova {
@@ -117,8 +119,108 @@ nn_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t N, i
   }
 }
 
+
+// ------------------------------------------------------------------ one sweep, both directions (distance only)
+// Every |a_i - b_j|^2 is evaluated ONCE and feeds both minima: the running minimum of query i (a register) and
+// the minimum of target j over the warp's 32 * SQ queries.  The second one is a reduction ACROSS lanes; doing it
+// per target would cost a 5-step shuffle tree per 4 pair evaluations, so targets are taken 32 at a time and the
+// 32 x 32 (target x lane) partial minima are reduced with one butterfly transpose: 31 shuffles per 32 targets,
+// after which lane l holds the warp's minimum for target l.  Warps and CTAs then meet through atomicMin on the
+// bit pattern of d^2 (non-negative floats order like unsigned integers): shared memory first, global once per tile.
+#ifndef NOVA_CHAMFER_SQ
+#define NOVA_CHAMFER_SQ 4
+#endif
+#ifndef NOVA_CHAMFER_SWARPS
+#define NOVA_CHAMFER_SWARPS 4
+#endif
+constexpr int SQ = NOVA_CHAMFER_SQ;          // queries per lane
+constexpr int SWARPS = NOVA_CHAMFER_SWARPS;  // each warp owns its own 32 * SQ queries and sweeps every target
+constexpr int STHREADS = SWARPS * 32;
+constexpr int SQPB = SWARPS * 32 * SQ;  // 512 queries per CTA
+constexpr int STILE = 1024;       // targets per shared-memory tile (multiple of 32)
+
+__global__ void __launch_bounds__(STHREADS)
+nn_sym_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t N, int64_t M, float* __restrict__ d1,
+              unsigned int* __restrict__ d2sq_bits) {
+  __shared__ float4 tile[STILE];
+  __shared__ unsigned int tmin[STILE];
+  const int64_t cloud = blockIdx.y;
+  const float* qry = a + cloud * N * 3;
+  const float* tgt = b + cloud * M * 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q0 = (int64_t)blockIdx.x * SQPB + warp * (32 * SQ);
+  float qx[SQ], qy[SQ], qz[SQ], best[SQ];
+#pragma unroll
+  for (int k = 0; k < SQ; ++k) {
+    int64_t qi = q0 + k * 32 + lane;
+    if (qi >= N) qi = N - 1;  // duplicates of a valid query change neither minimum
+    qx[k] = qry[qi * 3 + 0];
+    qy[k] = qry[qi * 3 + 1];
+    qz[k] = qry[qi * 3 + 2];
+    best[k] = 3.4e38f;
+  }
+  for (int64_t t0 = 0; t0 < M; t0 += STILE) {
+    const int cnt = static_cast<int>(M - t0 < STILE ? M - t0 : STILE);
+    const int cnt32 = (cnt + 31) & ~31;
+    __syncthreads();
+    float* tf = reinterpret_cast<float*>(tile);
+    for (int i = threadIdx.x; i < cnt32 * 4; i += STHREADS) {
+      const int pt = i >> 2, c = i & 3;
+      tf[i] = (pt < cnt && c < 3) ? tgt[(t0 + pt) * 3 + c] : (pt < cnt ? 0.f : 1e18f);  // padding: a point far away
+    }
+    for (int i = threadIdx.x; i < cnt32; i += STHREADS) tmin[i] = 0x7F7F7F7Fu;
+    __syncthreads();
+    for (int g = 0; g < cnt32; g += 32) {
+      float pm[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float4 p = tile[g + t];
+        float m = 3.4e38f;
+#pragma unroll
+        for (int k = 0; k < SQ; ++k) {
+          const float dx = qx[k] - p.x, dy = qy[k] - p.y, dz = qz[k] - p.z;
+          const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          best[k] = fminf(best[k], d);
+          m = fminf(m, d);
+        }
+        pm[t] = m;
+      }
+      // butterfly transpose-reduce: lane l ends with min over the 32 lanes of pm[l]
+#pragma unroll
+      for (int r = 16; r >= 1; r >>= 1) {
+        const bool upper = (lane & r) != 0;
+#pragma unroll
+        for (int i = 0; i < r; ++i) {
+          const float keep = upper ? pm[i + r] : pm[i];
+          const float give = upper ? pm[i] : pm[i + r];
+          pm[i] = fminf(keep, __shfl_xor_sync(0xffffffffu, give, r));
+        }
+      }
+      atomicMin(&tmin[g + lane], __float_as_uint(pm[0]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += STHREADS) atomicMin(&d2sq_bits[cloud * M + t0 + i], tmin[i]);
+  }
+#pragma unroll
+  for (int k = 0; k < SQ; ++k) {
+    const int64_t qi = q0 + k * 32 + lane;
+    if (qi < N) d1[cloud * N + qi] = sqrtf(best[k]);
+  }
+}
+
+// d2 <- sqrt(d2^2) in place (the buffer holds float bit patterns written by atomicMin)
+__global__ void sqrt_inplace_kernel(float* __restrict__ d, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = sqrtf(d[i]);
+}
+
 }  // namespace chamfer
 }  // namespace nova
+
+static bool chamfer_one_sweep() {  // NOVA_B200_CHAMFER_SWEEPS=2 keeps the two-sweep distance-only kernel (A/B runs)
+  const char* e = std::getenv("NOVA_B200_CHAMFER_SWEEPS");
+  return e == nullptr || std::atoi(e) != 2;
+}
 
 extern "C" int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_t N, int64_t M, float* d1, float* d2,
                                int32_t* idx1, int32_t* idx2, void* stream) {
@@ -133,7 +235,15 @@ extern "C" int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_
   if (idx1 != nullptr || idx2 != nullptr)
     chamfer::nn_kernel<true><<<grid, chamfer::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, b, N, M, d1, d2, idx1,
                                                                                             idx2);
-  else
+  else if (chamfer_one_sweep()) {
+    // distance only: one sweep over the N x M pairs feeds both directions (3 launches: init, sweep, sqrt)
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NOVA_CHECK_CUDA(cudaMemsetAsync(d2, 0x7F, sizeof(float) * B * M, s));  // 0x7F7F7F7F = 3.39e38
+    dim3 sgrid((unsigned)ceil_div(N, chamfer::SQPB), (unsigned)B);
+    chamfer::nn_sym_kernel<<<sgrid, chamfer::STHREADS, 0, s>>>(a, b, N, M, d1, reinterpret_cast<unsigned int*>(d2));
+    NOVA_CHECK_LAUNCH();
+    chamfer::sqrt_inplace_kernel<<<(unsigned)ceil_div(B * M, 256), 256, 0, s>>>(d2, B * M);
+  } else
     chamfer::nn_kernel<false><<<grid, chamfer::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, b, N, M, d1, d2,
                                                                                              nullptr, nullptr);
   NOVA_CHECK_LAUNCH();
