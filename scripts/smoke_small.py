@@ -1,4 +1,4 @@
-"""Small driver for compute-sanitizer (one tool per gpurun call): both bf16 dataflows, the fp32 handle,
+"""Small end-to-end driver (written for compute-sanitizer, which this GPU pool refuses; useful as a quick smoke run): both bf16 dataflows, the fp32 handle,
 guidance, pred_ids, graph replay and both Chamfer kernels on tiny shapes."""
 import sys
 
