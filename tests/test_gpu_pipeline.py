@@ -109,6 +109,27 @@ def test_full_size_batch_invariance_and_ragged_batches():
     assert relmax(full[3:4], ref) < 5e-2
 
 
+@pytest.mark.parametrize("name,D,N,B", [("cfg3: NOVA-0.6B, 1024 points, batch 64", 1024, 1024, 64),
+                                       ("cfg4 per-GPU shard: NOVA-1.4B, 2048 points, 32 clouds", 1536, 2048, 32)])
+def test_full_size_batch_invariance_other_configs(name, D, N, B):
+    """BASELINE configs[2] and [3] at their full per-GPU sizes: a cloud sampled alone equals its slice of the batch
+    bit for bit (rows are independent), and one oracle cloud pins the run to the reference arithmetic."""
+    import nova_pointcloud_b200 as nb
+
+    head = nb.synth.make_head(D, 6, dtype=torch.bfloat16)
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(25)
+    noise, z = nb.synth.make_inputs(B, N, D, dtype=torch.bfloat16)
+    full = nb.denoise(head, sched, z, noise)
+    assert full.shape == (B, N, 3) and bool(torch.isfinite(full).all())
+    for b in (0, B - 1):
+        # N >= 1024 rows keeps the single cloud on the same (fused-AdaLN) dataflow as the batch
+        alone = nb.denoise(head, sched, z[b:b + 1].repeat(2, 1, 1), noise[b:b + 1].repeat(2, 1, 1, 1))
+        assert torch.equal(alone[0], full[b]) and torch.equal(alone[1], full[b]), (name, b)
+    ref = OL.denoise(cpu_sd(head, torch.float32), z[1:2].float().cpu(), noise[1:2].cpu(), num_steps=25)
+    assert relmax(full[1:2], ref) < 5e-2, name
+
+
 def test_degenerate_shapes():
     """Empty and minimal inputs: zero clouds, a zero-token set, one token, one cloud of one point."""
     import nova_pointcloud_b200 as nb
