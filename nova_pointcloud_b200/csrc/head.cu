@@ -1,17 +1,22 @@
 // The diffusion head (DiffusionMLP) and its fused sampling loop on sm_100a.
 //
-// One head step over M rows (reference: diffnext/models/diffusion_mlp.py:89-99):
+// One head step over M rows (reference: diffnext/models/diffusion_mlp.py:89-99) exists in two dataflows.
 //
-//   prep      a = silu(c + temb_s),  x = PatchEmbed(x_tok)                      [row-wise]
+// "wide" (fp32 parity handle; bf16 handle at <= wide_ada_rows rows, where a step is latency-bound):
+//   prep      a = silu(c + temb_s)                                               [row-wise]
 //   G_ada     st = a W_ada^T + b_ada        all 3*depth+2 AdaLN statistics in ONE GEMM, N = 20 D
-//   row       h = LN(x)(1+scale_0)+shift_0                                       [row-wise]
+//   row       x = PatchEmbed(x_tok);  h = LN(x)(1+scale_0)+shift_0               [row-wise]
 //   per block G_fc1  u1 = silu(h P1^T + p1)
 //             G_fc2  u2 = u1 P2^T + p2
 //             row    x += LN_aff(u2) * gate_i ;  h = LN(x)(1+scale_{i+1})+shift_{i+1}
 //   last row  ... y = LN(x)(1+scale_f)+shift_f ; v = y H^T + h0 ; x_tok += dt v  (Euler fused)
 //
+// "fused AdaLN" (bf16 handle at large M, head_step_fused): one statistics GEMM per block whose epilogue applies
+// the modulation, so the [M, 20 D] statistics tensor never exists; see the comment on head_step_fused.
+//
 // Step-invariant work is hoisted out of the S-step loop (an algorithmic change, not a port):
 // c = condition_proj(z) once per call, temb_s = timestep_proj(freq(t_s)) as an [S, D] table.
+// The S-step loop itself is captured into a CUDA graph on its second use and replayed afterwards.
 // GEMMs run on tcgen05 tensor cores (bf16 handle) or the SIMT fp32 kernel (fp32 handle).
 #include <cmath>
 #include <cstdlib>
