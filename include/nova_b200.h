@@ -150,6 +150,29 @@ NOVA_API int nova_euler_step(const void* model_output, const void* sample, doubl
 NOVA_API int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_t N, int64_t M, float* d1, float* d2,
                     int32_t* idx1, int32_t* idx2, void* stream);
 
+/*
+ * Neighbourhood ops on the Chamfer tiling (callers either side of the sampling path).
+ * All distances are Euclidean (not squared), exact difference form in fp32; ties keep the lowest index.
+ *
+ * nova_knn: q [B, Nq, 3], t [B, Nt, 3] fp32 -> dist [B, Nq, k] ascending, idx [B, Nq, k] int32 or NULL.
+ *   Replaces the reference's topk(cdist(q, t), k, dim=-1, largest=False)
+ *   (diffnext/models/transformers/transformer_pointcloud_nova.py:84-86,143-144).  1 <= k <= min(32, Nt).
+ *
+ * nova_local_density: points [B, N, 3] -> density [B, N] = mean of the k_neighbors smallest distances after
+ *   the smallest one (self) is dropped.  Replaces compute_local_density(points, k_neighbors=8)
+ *   (transformer_pointcloud_nova.py:81-89).  k_neighbors + 1 <= min(32, N), else an error, as topk raises there.
+ *
+ * nova_softmax_interp: targets [B, S, 3], points [B, N, 3] -> out [B, S, 3],
+ *   out_i = sum_j softmax_j(-|t_i - p_j|) p_j.  Replaces the weighted average of feature_aware_interpolation
+ *   (transformer_pointcloud_nova.py:142-150; the top-k indices computed there are not used by its result).
+ */
+NOVA_API int nova_knn(const float* q, const float* t, int64_t B, int64_t Nq, int64_t Nt, int32_t k, float* dist,
+                      int32_t* idx, void* stream);
+NOVA_API int nova_local_density(const float* points, int64_t B, int64_t N, int32_t k_neighbors, float* density,
+                                void* stream);
+NOVA_API int nova_softmax_interp(const float* targets, const float* points, int64_t B, int64_t S, int64_t N,
+                                 float* out, void* stream);
+
 /* Kernels launched by this library in the calling thread since the last reset (for bench.py). */
 NOVA_API int64_t nova_launch_count(void);
 NOVA_API void nova_launch_count_reset(void);

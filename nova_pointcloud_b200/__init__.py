@@ -30,6 +30,13 @@ from .chamfer import (  # noqa: F401
     dist_chamfer,
     robust_chamfer_distance,
 )
+from .geometry import (  # noqa: F401
+    compute_local_density,
+    density_target_size,
+    dynamic_partition,
+    feature_aware_interpolation,
+    knn,
+)
 from . import partition, synth  # noqa: F401
 
 __version__ = "0.1.0"

@@ -226,6 +226,68 @@ def _(a, b, with_indices=True):
             a.new_empty((B, M) if with_indices else (0,), dtype=torch.int32))
 
 
+def _cloud3(x: torch.Tensor, what: str) -> torch.Tensor:
+    if x.dim() != 3 or x.shape[-1] != 3:
+        raise NovaError(f"{what} expects (B,N,3) point clouds; got {tuple(x.shape)}")
+    return x.contiguous().float()
+
+
+@torch.library.custom_op("nova_b200::knn", mutates_args=(), device_types="cuda")
+def knn(q: torch.Tensor, t: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """k nearest targets of every query: (dist (B,Nq,k) ascending Euclidean, idx (B,Nq,k) int32)."""
+    q, t = _cloud3(q, "knn"), _cloud3(t, "knn")
+    if q.shape[0] != t.shape[0]:
+        raise NovaError(f"knn: batch mismatch {q.shape[0]} vs {t.shape[0]}")
+    B, Nq, Nt = q.shape[0], q.shape[1], t.shape[1]
+    dist = torch.empty(B, Nq, max(int(k), 0), dtype=torch.float32, device=q.device)
+    idx = torch.empty(B, Nq, max(int(k), 0), dtype=torch.int32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(_lib.lib().nova_knn(_ptr(q), _ptr(t), B, Nq, Nt, int(k), _ptr(dist), _ptr(idx), _stream()), "nova_knn")
+    return dist, idx
+
+
+@knn.register_fake
+def _(q, t, k):
+    return (q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.float32),
+            q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32))
+
+
+@torch.library.custom_op("nova_b200::local_density", mutates_args=(), device_types="cuda")
+def local_density(points: torch.Tensor, k_neighbors: int = 8) -> torch.Tensor:
+    """(B,N,3) -> (B,N): mean distance to the k nearest neighbours, the nearest (self) dropped."""
+    points = _cloud3(points, "local_density")
+    B, N = points.shape[0], points.shape[1]
+    out = torch.empty(B, N, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nova_local_density(_ptr(points), B, N, int(k_neighbors), _ptr(out), _stream()),
+              "nova_local_density")
+    return out
+
+
+@local_density.register_fake
+def _(points, k_neighbors=8):
+    return points.new_empty(points.shape[:2], dtype=torch.float32)
+
+
+@torch.library.custom_op("nova_b200::softmax_interp", mutates_args=(), device_types="cuda")
+def softmax_interp(targets: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+    """(B,S,3), (B,N,3) -> (B,S,3): out_i = sum_j softmax_j(-|t_i - p_j|) p_j."""
+    targets, points = _cloud3(targets, "softmax_interp"), _cloud3(points, "softmax_interp")
+    if targets.shape[0] != points.shape[0]:
+        raise NovaError(f"softmax_interp: batch mismatch {targets.shape[0]} vs {points.shape[0]}")
+    B, S, N = targets.shape[0], targets.shape[1], points.shape[1]
+    out = torch.empty(B, S, 3, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nova_softmax_interp(_ptr(targets), _ptr(points), B, S, N, _ptr(out), _stream()),
+              "nova_softmax_interp")
+    return out
+
+
+@softmax_interp.register_fake
+def _(targets, points):
+    return targets.new_empty(targets.shape, dtype=torch.float32)
+
+
 def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: str, epilogue: str) -> torch.Tensor:
     """Test hook over nova_debug_gemm: epi(A W^T + bias) with the named GEMM kernel."""
     impl_id = {"simt": 0, "tcgen05_1cta": 1, "tcgen05_2cta": 2, "tcgen05": 3}[impl]

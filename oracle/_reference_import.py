@@ -107,3 +107,28 @@ def reference_denoiser(ref, head, num_steps=25, shift=1.0):
     sched.set_timesteps(num_steps)
     model = ref.Transformer3DModel(image_encoder=enc, image_decoder=head, sample_scheduler=sched)
     return model, sched
+
+
+GEOMETRY_FUNCTIONS = ("dynamic_partition", "compute_local_density", "adaptive_sampling", "farthest_point_sampling",
+                      "feature_aware_interpolation")
+
+
+def reference_geometry():
+    """The reference's module-level geometry functions (transformer_pointcloud_nova.py:63-152), unmodified.
+
+    The module itself needs the real ``diffusers`` (``ModelMixin``) at import, so the function definitions are
+    taken from its syntax tree and compiled as they stand; their only free name is ``torch``."""
+    import ast
+
+    import torch
+
+    if not reference_available():
+        raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
+    path = os.path.join(REFERENCE_ROOT, "diffnext", "models", "transformers", "transformer_pointcloud_nova.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    ns = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in GEOMETRY_FUNCTIONS:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return types.SimpleNamespace(**{k: ns[k] for k in GEOMETRY_FUNCTIONS})

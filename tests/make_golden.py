@@ -21,7 +21,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle._reference_import import import_reference, reference_denoiser  # noqa: E402
+from oracle._reference_import import import_reference, reference_denoiser, reference_geometry  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -140,6 +140,28 @@ def chamfer_case():
     )
 
 
+def geometry_case():
+    """compute_local_density / feature_aware_interpolation run as they stand in the reference
+    (transformer_pointcloud_nova.py:81-89,128-152).  The interpolation draws its target indices with the global
+    RNG; the seed is set right before the call and the same randperm is replayed to record them."""
+    geo = reference_geometry()
+    g = torch.Generator().manual_seed(515)
+    big = torch.rand(3, 200, 3, generator=g) * 2 - 1          # > 25 points: torch.cdist takes the mm form
+    small = torch.rand(2, 24, 3, generator=g) * 2 - 1         # <= 25 points: exact differences
+    big[1, 7] = big[1, 3]                                      # a duplicated point: two zero distances
+    rec = {"big": big.numpy(), "small": small.numpy()}
+    rec["density_big"] = geo.compute_local_density(big).numpy()
+    rec["density_small"] = geo.compute_local_density(small).numpy()
+    rec["density_small_k3"] = geo.compute_local_density(small, k_neighbors=3).numpy()
+    for name, pts, size in (("big", big, 50), ("small", small, 10)):
+        torch.manual_seed(616)
+        rec[f"interp_{name}"] = geo.feature_aware_interpolation(pts, size).numpy()
+        torch.manual_seed(616)
+        rec[f"interp_{name}_idx"] = torch.randperm(pts.shape[1])[:size].numpy()
+    rec["interp_repeat"] = geo.feature_aware_interpolation(small, 60).numpy()   # N <= target: tile and cut
+    np.savez_compressed(os.path.join(GOLD, "geometry.npz"), **rec)
+
+
 def init_checksums(ref):
     """Checksums of the reference's random init for the BASELINE widths (too big to commit)."""
     rec = {}
@@ -162,6 +184,9 @@ def init_checksums(ref):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(4)
+    if "--only-geometry" in sys.argv:
+        geometry_case()
+        return
     ref = import_reference()
     with torch.no_grad():
         head_case(ref, "head_p1", depth=2, D=128, Dc=96, patch=1, chan=3, B=3, H=24, W=1, n_pred=7, seed=101)
@@ -170,6 +195,7 @@ def main():
         denoise_case(ref, "denoise_shift3", depth=1, D=64, Dc=64, B=2, N=12, n_pred=4, steps=10, shift=3.0, seed=404)
         scheduler_case(ref)
         chamfer_case()
+        geometry_case()
         init_checksums(ref)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import chamfer as OC
+from oracle import geometry as OG
 from oracle import head as OH
 from oracle import loop as OL
 from oracle import partition as OP
@@ -172,3 +173,30 @@ def test_partition_shapes():
     order = np.stack([np.random.default_rng(i).permutation(1024) for i in range(2)])
     parts = OP.split_order(order, n1024)
     assert len(parts) == 63 and np.array_equal(np.concatenate(parts, axis=1), order)
+
+
+def test_geometry_matches_reference(golden_dir):
+    """oracle.geometry against the reference's own compute_local_density / feature_aware_interpolation outputs
+    (<= 25 points the reference's torch.cdist is exact: 1e-6; above it takes the mm form: 1e-4)."""
+    g = np.load(os.path.join(golden_dir, "geometry.npz"))
+    assert np.abs(OG.local_density(g["small"]) - g["density_small"]).max() < 1e-6
+    assert np.abs(OG.local_density(g["small"], 3) - g["density_small_k3"]).max() < 1e-6
+    assert np.abs(OG.local_density(g["big"]) - g["density_big"]).max() < 1e-4
+    for name, tol in (("small", 1e-6), ("big", 1e-4)):
+        idx = g[f"interp_{name}_idx"]
+        assert np.abs(OG.interpolate(g[name], len(idx), idx) - g[f"interp_{name}"]).max() < tol
+    assert np.array_equal(OG.interpolate(g["small"], 60, None).astype(np.float32), g["interp_repeat"])
+
+
+def test_geometry_oracle_edges():
+    p = np.random.default_rng(3).uniform(-1, 1, (1, 40, 3)).astype(np.float32)
+    d, i = OG.knn(p[0], p[0], 5)
+    assert (d[:, 0] == 0).all() and (i[:, 0] == np.arange(40)).all() and (np.diff(d, axis=1) >= 0).all()
+    t = np.array([[0.0, 0, 0], [1, 0, 0], [1, 0, 0], [0, 0, 0], [1, 0, 0]])
+    assert OG.knn(np.array([[1.0, 0, 0]]), t, 4)[1].tolist() == [[1, 2, 4, 0]]  # ties: lowest index first
+    with pytest.raises(ValueError):
+        OG.knn(t, t, 6)
+    far = OG.softmax_interp(p * 300, p * 300)  # weights collapse onto the point itself, no underflow to 0/0
+    assert np.isfinite(far).all() and np.abs(far - p.astype(np.float64) * 300).max() < 1e-3
+    assert OG.target_size(0.5, 15000, 20) == 750 and OG.target_size(-10.0, 15000, 20) == 100
+    assert OG.target_size(10.0, 15000, 20) == 1500

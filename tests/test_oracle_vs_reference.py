@@ -109,3 +109,27 @@ def test_product_module_initialises_like_the_reference(ref):
     assert list(got.keys()) == list(want.keys())
     for k in want:
         assert torch.equal(got[k], want[k]), k
+
+
+@pytest.mark.parametrize("B,N,k,seed", [(2, 20, 8, 1), (1, 25, 4, 2), (3, 150, 8, 3), (1, 600, 8, 4)])
+def test_geometry_live(B, N, k, seed):
+    """oracle.geometry against the reference's functions as they stand (transformer_pointcloud_nova.py:81-152),
+    including the degenerate farthest_point_sampling the product leaves out."""
+    from oracle import geometry as OG
+    from oracle._reference_import import reference_geometry
+
+    geo = reference_geometry()
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(B, N, 3, generator=g) * 2 - 1
+    tol = 1e-6 if N <= 25 else 1e-4  # torch.cdist: exact differences up to 25 points, mm form above
+    assert np.abs(OG.local_density(pts.numpy(), k) - geo.compute_local_density(pts, k).numpy()).max() < tol
+    size = max(1, N // 3)
+    torch.manual_seed(seed + 100)
+    out = geo.feature_aware_interpolation(pts, size).numpy()
+    torch.manual_seed(seed + 100)
+    idx = torch.randperm(N)[:size].numpy()
+    assert np.abs(OG.interpolate(pts.numpy(), size, idx) - out).max() < tol
+    if N <= 25:  # exact distances: the zero diagonal wins every min, so every pick after the start is index 0
+        torch.manual_seed(seed + 200)
+        picked = geo.farthest_point_sampling(pts, 4)
+        assert torch.equal(picked[:, 1:], pts[:, :1].expand(-1, 3, -1))
