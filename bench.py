@@ -369,6 +369,40 @@ def main():
                                                      "sample": "4 pairs, scipy cdist float64 + min (oracle/chamfer.py, demo.py:38-55)"}
         except Exception as e:
             extras["chamfer"] = {"error": str(e)[:300]}
+        try:  # neighbourhood ops on the same tiling: local density of 256 clouds x 2048 points
+            def timed_ms(fn, reps=10):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            sel = torch.randperm(Nc, device=dev, generator=gc)[: Nc // 4]
+            dms = timed_ms(lambda: nb.compute_local_density(pa, 8))
+            kms = timed_ms(lambda: nb.knn(pa, pa, 9))
+            ims = timed_ms(lambda: nb.feature_aware_interpolation(pa, Nc // 4, indices=sel))
+            extras["geometry"] = {
+                "value": Bc / (dms * 1e-3), "unit": "clouds/s", "what": "compute_local_density(k_neighbors=8), %d x %d points" % (Bc, Nc),
+                "ms": dms, "pair_evals_per_s": Bc * Nc * Nc / (dms * 1e-3),
+                "knn_k9_with_indices_ms": kms, "softmax_interp_quarter_ms": ims,
+                "note": "HBM-trivial like Chamfer (%.1f MB in + out per call); bound by fp32 issue + the k-best insertion" % (Bc * Nc * 16 / 1e6)}
+            if not args.no_cpu_baseline:
+                from oracle import geometry as OG
+
+                p_np = pa[:4].cpu().numpy()
+                t0 = time.perf_counter()
+                OG.local_density(p_np, 8)
+                cpu_s = (time.perf_counter() - t0) / 4
+                extras["geometry"]["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "clouds/s", "cores": 1, "kind": "port",
+                                                      "sample": "4 clouds, scipy cdist float64 + stable argsort (oracle/geometry.py, "
+                                                                "transformer_pointcloud_nova.py:81-89)"}
+        except Exception as e:
+            extras["geometry"] = {"error": str(e)[:300]}
 
     if rank == 0:
         flops = algorithmic_flops(D, B * N)  # per GPU per step
