@@ -155,6 +155,49 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def eager_library_sampler(head, sched, z, noise):
+    """The reference's algorithm as eager PyTorch ON THE GPU (cuBLAS GEMMs + ATen element-wise kernels): the
+    "library kernel" bar of SURVEY 8(d).  Written here with torch.nn.functional from the module's state_dict; it
+    is a reported comparator only -- neither the product path nor the oracle.  Like the reference it recomputes
+    the condition projection every step and carries the latent in the model dtype
+    (transformer_3d.py:102-113, diffusion_mlp.py:89-99, scheduling_cfm.py:125-140)."""
+    import math
+
+    import torch.nn.functional as F
+
+    sd = dict(head.state_dict())
+    dt_model = z.dtype
+    depth = sum(1 for k in sd if k.startswith("blocks.") and k.endswith(".norm1.proj.weight"))
+    wp = sd["patch_embed.proj.weight"]
+    w_tok = wp.permute(0, 2, 3, 1).reshape(wp.shape[0], -1).contiguous()
+    freq = torch.exp(torch.arange(128, device=z.device, dtype=torch.float32) * (-math.log(10000.0) / 128))
+
+    def mlp2(prefix, x):
+        return F.linear(F.silu(F.linear(x, sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"])),
+                        sd[prefix + ".fc2.weight"], sd[prefix + ".fc2.bias"])
+
+    def adaln(prefix, x, zt, k):
+        st = F.linear(F.silu(zt), sd[prefix + ".proj.weight"], sd[prefix + ".proj.bias"]).chunk(k, dim=-1)
+        return F.layer_norm(x, (x.shape[-1],), None, None, 1e-6) * (1 + st[0]) + st[1], st[2:]
+
+    x = noise.squeeze(-1).transpose(1, 2).to(dt_model)  # (B,3,N,1) -> tokens (B,N,3)
+    sig = sched.sigmas
+    for i, t in enumerate(sched.timesteps):
+        emb = torch.full((x.shape[0], 1), float(t), device=z.device) * freq
+        temb = mlp2("time_cond_embed.timestep_proj", torch.cat([emb.cos(), emb.sin()], dim=-1).to(dt_model))
+        zt = mlp2("time_cond_embed.condition_proj", z) + temb.unsqueeze(1)
+        h = F.linear(x, w_tok, sd["patch_embed.proj.bias"])
+        for b in range(depth):
+            y, (gate,) = adaln(f"blocks.{b}.norm1", h, zt, 3)
+            u = mlp2(f"blocks.{b}.proj", y)
+            u = F.layer_norm(u, (u.shape[-1],), sd[f"blocks.{b}.norm2.weight"], sd[f"blocks.{b}.norm2.bias"], 1e-5)
+            h = u * gate + h
+        y, _ = adaln("norm", h, zt, 2)
+        v = F.linear(y, sd["head.weight"], sd["head.bias"])
+        x = v * (sig[i + 1] - sig[i]) + x
+    return x.float()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -403,6 +446,27 @@ def main():
                                                                 "transformer_pointcloud_nova.py:81-89)"}
         except Exception as e:
             extras["geometry"] = {"error": str(e)[:300]}
+        try:  # the reference's algorithm as eager PyTorch on this GPU: the library-kernel bar
+            with torch.no_grad():
+                ref_out = eager_library_sampler(head, sched, z_d, noise_d)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    eager_library_sampler(head, sched, z_d, noise_d)
+                e1.record()
+                torch.cuda.synchronize()
+                lms = e0.elapsed_time(e1) / 2
+                ours = nb.denoise(head, sched, z_d, noise_d)
+            extras["library_bar"] = {
+                "value": B / (lms * 1e-3), "unit": "clouds/s", "ms_per_step": lms,
+                "what": "the reference algorithm as eager PyTorch bf16 on the same GPU (cuBLAS + ATen kernels, ~130 "
+                        "launches per diffusion step, condition projection recomputed every step, bf16 latent); a "
+                        "comparator, not the product path",
+                "speedup_of_this_build": lms / ms,
+                "rel_max_diff_of_outputs": float((ours - ref_out).abs().max() / ref_out.abs().max())}
+        except Exception as e:
+            extras["library_bar"] = {"error": str(e)[:300]}
 
     if rank == 0:
         flops = algorithmic_flops(D, B * N)  # per GPU per step

