@@ -16,6 +16,7 @@ reference's arithmetic for the hot path named in BASELINE.json:
                           (diffnext/models/transformers/transformer_3d.py:102-113, guidance_scaler.py:46-87)
 * ``oracle.chamfer``   -- Chamfer variants A/B/C (demo.py:38-55, train_newloss.py:316-349,
                           test_optimize.py:354-383)
+* ``oracle.geometry``  -- kNN / local density / softmax interpolation (transformer_pointcloud_nova.py:81-89,128-152)
 * ``oracle.partition`` -- set schedules (pipeline_nova.py:129-132, transformer_pointcloud_nova.py:63-78,
                           embeddings.py:262-270)
 
