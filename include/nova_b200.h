@@ -173,6 +173,25 @@ NOVA_API int nova_local_density(const float* points, int64_t B, int64_t N, int32
 NOVA_API int nova_softmax_interp(const float* targets, const float* points, int64_t B, int64_t S, int64_t N,
                                  float* out, void* stream);
 
+/*
+ * Training-mode arithmetic either side of the head, forward only.
+ *
+ * nova_add_noise: x, noise [tokens, T] fp32, t_idx [tokens] int64 into the scheduler's training tables
+ *   sigma_table / t_table [n_train] fp32 -> x_t = sigma * noise + (1 - sigma) * x (rounded like the reference:
+ *   mul, mul, add) and, when t_out != NULL, t_out [tokens] = t_table[t_idx] (the per-token timestep the head takes).
+ *   Replaces FlowMatchEulerDiscreteScheduler.add_noise (diffnext/schedulers/scheduling_cfm.py:106-117).
+ *
+ * nova_flow_loss: pred, noise, x [tokens, T] fp32, weight [tokens] fp32 or NULL (all ones) ->
+ *   loss_tok [tokens] = mean_T((pred - (noise - x))^2) * weight / (sum(weight) + 1e-5), scratch2[0] = sum(loss_tok),
+ *   scratch2[1] = sum(weight).  Deterministic (fixed-order single-block reductions).
+ *   Replaces the loss of Transformer3DModel.get_losses (diffnext/models/transformers/transformer_3d.py:91-95).
+ */
+NOVA_API int nova_add_noise(const float* x, const float* noise, const float* sigma_table, const float* t_table,
+                            const int64_t* t_idx, int64_t tokens, int32_t T, int32_t n_train, float* x_t,
+                            float* t_out, void* stream);
+NOVA_API int nova_flow_loss(const float* pred, const float* noise, const float* x, const float* weight,
+                            int64_t tokens, int32_t T, float* loss_tok, float* scratch2, void* stream);
+
 /* Kernels launched by this library in the calling thread since the last reset (for bench.py). */
 NOVA_API int64_t nova_launch_count(void);
 NOVA_API void nova_launch_count_reset(void);

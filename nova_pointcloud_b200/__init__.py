@@ -37,6 +37,7 @@ from .geometry import (  # noqa: F401
     feature_aware_interpolation,
     knn,
 )
+from .training import get_losses  # noqa: F401
 from . import partition, synth  # noqa: F401
 
 __version__ = "0.1.0"

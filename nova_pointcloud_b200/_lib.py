@@ -21,7 +21,7 @@ EXPORTS = [
     "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
     "nova_head_sample", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
-    "nova_knn", "nova_local_density", "nova_softmax_interp",
+    "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_add_noise", "nova_flow_loss",
 ]
 
 
@@ -73,6 +73,10 @@ def _declare(lib):
     lib.nova_local_density.argtypes = [vp, i64, i64, i32, vp, vp]
     lib.nova_softmax_interp.restype = C.c_int
     lib.nova_softmax_interp.argtypes = [vp, vp, i64, i64, i64, vp, vp]
+    lib.nova_add_noise.restype = C.c_int
+    lib.nova_add_noise.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.nova_flow_loss.restype = C.c_int
+    lib.nova_flow_loss.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
     lib.nova_launch_count.restype = i64
     lib.nova_launch_count.argtypes = []
     lib.nova_launch_count_reset.restype = None

@@ -288,6 +288,57 @@ def _(targets, points):
     return targets.new_empty(targets.shape, dtype=torch.float32)
 
 
+@torch.library.custom_op("nova_b200::add_noise", mutates_args=(), device_types="cuda")
+def add_noise(x: torch.Tensor, noise: torch.Tensor, sigma_table: torch.Tensor, t_table: torch.Tensor,
+              t_idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x, noise (..., T) fp32 with leading dims == t_idx's; returns (x_t like x, timestep like t_idx, fp32)."""
+    if x.shape != noise.shape or tuple(x.shape[:t_idx.dim()]) != tuple(t_idx.shape) or x.dim() != t_idx.dim() + 1:
+        raise NovaError(f"add_noise: x/noise {tuple(x.shape)}/{tuple(noise.shape)} do not match t_idx {tuple(t_idx.shape)} + (T,)")
+    x, noise = x.contiguous().float(), noise.contiguous().float()
+    idx = t_idx.contiguous().to(torch.int64)
+    sig, tt = sigma_table.contiguous().float(), t_table.contiguous().float()
+    x_t = torch.empty_like(x)
+    t_out = torch.empty(idx.shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().nova_add_noise(_ptr(x), _ptr(noise), _ptr(sig), _ptr(tt), _ptr(idx), idx.numel(), x.shape[-1],
+                                        sig.numel(), _ptr(x_t), _ptr(t_out), _stream()), "nova_add_noise")
+    return x_t, t_out
+
+
+@add_noise.register_fake
+def _(x, noise, sigma_table, t_table, t_idx):
+    return torch.empty_like(x, dtype=torch.float32), t_idx.new_empty(t_idx.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("nova_b200::flow_loss", mutates_args=(), device_types="cuda")
+def flow_loss(pred: torch.Tensor, noise: torch.Tensor, x: torch.Tensor, weight: Optional[torch.Tensor]
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """pred, noise, x (..., T); weight (...) or None -> (loss_tok (...), [sum(loss_tok), sum(weight)])."""
+    if pred.shape != noise.shape or pred.shape != x.shape:
+        raise NovaError(f"flow_loss: shapes differ {tuple(pred.shape)} {tuple(noise.shape)} {tuple(x.shape)}")
+    pred, noise, x = pred.contiguous().float(), noise.contiguous().float(), x.contiguous().float()
+    lead = pred.shape[:-1]
+    tokens = 1
+    for d in lead:
+        tokens *= d
+    w = None
+    if weight is not None:
+        w = weight.contiguous().float()
+        if w.numel() != tokens:
+            raise NovaError(f"flow_loss: weight has {w.numel()} entries for {tokens} tokens")
+    loss_tok = torch.empty(lead, dtype=torch.float32, device=pred.device)
+    sums = torch.empty(2, dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().nova_flow_loss(_ptr(pred), _ptr(noise), _ptr(x), _ptr(w), tokens, pred.shape[-1], _ptr(loss_tok),
+                                        _ptr(sums), _stream()), "nova_flow_loss")
+    return loss_tok, sums
+
+
+@flow_loss.register_fake
+def _(pred, noise, x, weight):
+    return pred.new_empty(pred.shape[:-1], dtype=torch.float32), pred.new_empty((2,), dtype=torch.float32)
+
+
 def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: str, epilogue: str) -> torch.Tensor:
     """Test hook over nova_debug_gemm: epi(A W^T + bias) with the named GEMM kernel."""
     impl_id = {"simt": 0, "tcgen05_1cta": 1, "tcgen05_2cta": 2, "tcgen05": 3}[impl]

@@ -101,6 +101,41 @@ class FlowMatchEulerDiscreteScheduler:
         self._begin_index = None
         self._step_index = None
 
+    # ---- training-mode surface (scheduling_cfm.py:87-123); only valid before set_timesteps replaces the tables
+    def _training_tables(self):
+        if not isinstance(self.sigmas, torch.Tensor):
+            raise NovaError("add_noise / sample_timesteps need the training tables: use a scheduler on which "
+                            "set_timesteps has not been called (the reference keeps separate noise/sample schedulers)")
+        return self.sigmas, self.timesteps
+
+    def sample_timesteps(self, size, device=None, generator=None):
+        """int64 indices floor(sigmoid(N(0,1)) * num_train_timesteps) of shape `size`."""
+        u = torch.empty(tuple(size), device=device).normal_(0, 1, generator=generator).sigmoid_()
+        return u.mul_(self.config.num_train_timesteps).to(dtype=torch.int64)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        """sigma * noise + (1 - sigma) * x with sigma = sigmas[timesteps] broadcast over the trailing dims; keeps
+        ``self.timestep`` / ``self.sigma`` like the reference.  CUDA only."""
+        sig, tt = self._training_tables()
+        x = original_samples
+        idx = timesteps.to(device=x.device, dtype=torch.int64)
+        if int(idx.min()) < 0 or int(idx.max()) >= sig.numel():
+            raise NovaError(f"add_noise: timestep index outside [0, {sig.numel()})")
+        lead = idx.dim()
+        flat = x.reshape(tuple(x.shape[:lead]) + (-1,)).float()
+        x_t, t = torch.ops.nova_b200.add_noise(flat, noise.reshape(flat.shape).float(), sig.to(x.device),
+                                               tt.to(x.device), idx)
+        self.timestep = t
+        self.sigma = sig.to(device=x.device, dtype=x.dtype)[idx].view(idx.shape + (1,) * (noise.dim() - idx.dim()))
+        return x_t.reshape(x.shape).to(x.dtype)
+
+    def scale_noise(self, sample, timestep, noise):
+        """sigma_i * noise + (1 - sigma_i) * sample at the current inference step (scheduling_cfm.py:119-123)."""
+        if self._step_index is None:
+            self._step_index = self._begin_index if self._begin_index is not None else self.index_for_timestep(timestep)
+        sigma = float(self.sigmas[self._step_index])
+        return sigma * noise + (1.0 - sigma) * sample
+
     def step(self, model_output, timestep, sample, generator=None, return_dict=True):
         """prev_sample = model_output * dt + sample on the device (CUDA only), dt = sigma[i+1] - sigma[i]."""
         if self._step_index is None:

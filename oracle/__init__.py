@@ -17,6 +17,8 @@ reference's arithmetic for the hot path named in BASELINE.json:
 * ``oracle.chamfer``   -- Chamfer variants A/B/C (demo.py:38-55, train_newloss.py:316-349,
                           test_optimize.py:354-383)
 * ``oracle.geometry``  -- kNN / local density / softmax interpolation (transformer_pointcloud_nova.py:81-89,128-152)
+* ``oracle.training``  -- training tables, add_noise, get_losses forward (scheduling_cfm.py:39-49,87-117,
+                          transformer_3d.py:81-95)
 * ``oracle.partition`` -- set schedules (pipeline_nova.py:129-132, transformer_pointcloud_nova.py:63-78,
                           embeddings.py:262-270)
 

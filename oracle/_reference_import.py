@@ -31,7 +31,11 @@ def _install_diffusers_stub():
         return
 
     class _Config(dict):
-        __getattr__ = dict.__getitem__
+        def __getattr__(self, name):  # like diffusers' FrozenDict: a missing key is an AttributeError, so getattr(cfg, k, default) works
+            try:
+                return self[name]
+            except KeyError:
+                raise AttributeError(name) from None
 
     class ConfigMixin:
         pass

@@ -162,6 +162,40 @@ def geometry_case():
     np.savez_compressed(os.path.join(GOLD, "geometry.npz"), **rec)
 
 
+def losses_case(ref):
+    """Transformer3DModel.get_losses (transformer_3d.py:81-95) as it stands, loss_repeat = 4, with a 0/1 mask weight.
+    Its random draws (randn for the noise, then normal for the timestep indices) are replayed from the same seed
+    and stored, so the oracle and the CUDA path can be fed the identical noise and timesteps."""
+    import types
+
+    from oracle import head as OH
+
+    D = 256  # the CUDA head needs widths in multiples of 256; weights are NOT stored: they are the reference's default
+    torch.manual_seed(707)  # init under this seed, which oracle.head.init_state_dict reproduces (checked below)
+    head = ref.DiffusionMLP(1, D, D, patch_size=1, image_dim=3).eval()
+    sd = OH.init_state_dict(1, D, D, 1, 3, seed=707)
+    assert all(torch.equal(sd[k], v) for k, v in head.state_dict().items())
+    enc = torch.nn.Module()
+    enc.patch_embed = head.patch_embed
+    head.patch_embed.height, head.patch_embed.width = 20, 1  # normally left behind by the encoder's forward
+    g = torch.Generator().manual_seed(708)
+    B, N = 3, 20
+    x = torch.randn(B, 3, N, 1, generator=g)
+    z = torch.randn(B, N, D, generator=g)
+    mask = (torch.rand(B, N, 1, generator=g) < 0.7).float()
+    model = ref.Transformer3DModel(image_encoder=enc, image_decoder=head, mask_embed=types.SimpleNamespace(mask=mask),
+                                   noise_scheduler=ref.FlowMatchEulerDiscreteScheduler(1000, shift=1.0))
+    torch.manual_seed(709)
+    with torch.no_grad():
+        out = model.get_losses(z, x)
+    torch.manual_seed(709)
+    noise = torch.randn(4 * B, N, 3)
+    t_idx = torch.normal(0, 1, (4 * B, N)).sigmoid_().mul_(1000).to(torch.int64)
+    np.savez_compressed(os.path.join(GOLD, "losses.npz"), cfg=np.array([1, D, D, 1, 3]), init_seed=np.array(707),
+                        x=x.numpy(), z=z.numpy(), mask=mask.numpy(), noise=noise.numpy(), t_idx=t_idx.numpy(),
+                        loss=np.array(out["loss"].item()))
+
+
 def init_checksums(ref):
     """Checksums of the reference's random init for the BASELINE widths (too big to commit)."""
     rec = {}
@@ -187,6 +221,9 @@ def main():
     if "--only-geometry" in sys.argv:
         geometry_case()
         return
+    if "--only-losses" in sys.argv:
+        losses_case(import_reference())
+        return
     ref = import_reference()
     with torch.no_grad():
         head_case(ref, "head_p1", depth=2, D=128, Dc=96, patch=1, chan=3, B=3, H=24, W=1, n_pred=7, seed=101)
@@ -196,6 +233,7 @@ def main():
         scheduler_case(ref)
         chamfer_case()
         geometry_case()
+        losses_case(ref)
         init_checksums(ref)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

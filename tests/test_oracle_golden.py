@@ -14,6 +14,7 @@ from oracle import head as OH
 from oracle import loop as OL
 from oracle import partition as OP
 from oracle import scheduler as OS
+from oracle import training as OT
 
 
 def load(golden_dir, name):
@@ -200,3 +201,30 @@ def test_geometry_oracle_edges():
     assert np.isfinite(far).all() and np.abs(far - p.astype(np.float64) * 300).max() < 1e-3
     assert OG.target_size(0.5, 15000, 20) == 750 and OG.target_size(-10.0, 15000, 20) == 100
     assert OG.target_size(10.0, 15000, 20) == 1500
+
+
+def test_training_loss_matches_reference(golden_dir):
+    """oracle.training.get_losses against Transformer3DModel.get_losses run as it stands (tests/make_golden.py
+    losses_case): same noise and timestep indices (replayed from the reference's seed) -> the same loss."""
+    d = np.load(os.path.join(golden_dir, "losses.npz"))
+    depth, D, Dc, patch, chan = [int(v) for v in d["cfg"]]
+    sd = OH.init_state_dict(depth, D, Dc, patch, chan, seed=int(d["init_seed"]))  # the reference's default init
+    out = OT.get_losses(sd, torch.from_numpy(d["z"]), torch.from_numpy(d["x"]), torch.from_numpy(d["noise"]),
+                        torch.from_numpy(d["t_idx"]), torch.from_numpy(d["mask"]))
+    assert abs(float(out["loss"]) - float(d["loss"])) <= 1e-6 * abs(float(d["loss"]))
+    # masked-out tokens carry no loss; the per-token losses add up to the scalar
+    w = torch.from_numpy(d["mask"]).repeat(4, 1, 1).squeeze(-1)
+    assert float(out["loss_per_token"][w == 0].abs().max()) == 0.0
+    assert abs(float(out["loss_per_token"].sum()) - float(out["loss"])) < 1e-6
+
+
+def test_training_tables_and_timestep_sampling():
+    sig, tt = OT.training_tables(1000, 1.0)
+    assert sig.shape == (1000,) and float(sig[0]) == 1.0 and abs(float(sig[-1]) - 1e-3) < 1e-9 and float(tt[0]) == 1000.0
+    sig3, _ = OT.training_tables(1000, 3.0)
+    assert abs(float(sig3[500]) - 3 * 0.5 / (1 + 2 * 0.5)) < 1e-6
+    idx = OT.sample_timesteps((64, 50), generator=torch.Generator().manual_seed(0))
+    assert idx.dtype == torch.int64 and int(idx.min()) >= 0 and int(idx.max()) <= 999
+    x, n = torch.randn(2, 5, 3), torch.randn(2, 5, 3)
+    zero = torch.zeros(2, 5, dtype=torch.int64)
+    assert torch.equal(OT.add_noise(x, n, zero, sig), n)  # sigma = 1 at index 0: pure noise
