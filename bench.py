@@ -155,12 +155,13 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def eager_library_sampler(head, sched, z, noise):
+def eager_library_sampler(head, sched, z, noise, compiled=False):
     """The reference's algorithm as eager PyTorch ON THE GPU (cuBLAS GEMMs + ATen element-wise kernels): the
     "library kernel" bar of SURVEY 8(d).  Written here with torch.nn.functional from the module's state_dict; it
     is a reported comparator only -- neither the product path nor the oracle.  Like the reference it recomputes
     the condition projection every step and carries the latent in the model dtype
-    (transformer_3d.py:102-113, diffusion_mlp.py:89-99, scheduling_cfm.py:125-140)."""
+    (transformer_3d.py:102-113, diffusion_mlp.py:89-99, scheduling_cfm.py:125-140).  ``compiled=True`` runs one
+    diffusion step through torch.compile (inductor), the second bar SURVEY names."""
     import math
 
     import torch.nn.functional as F
@@ -180,10 +181,8 @@ def eager_library_sampler(head, sched, z, noise):
         st = F.linear(F.silu(zt), sd[prefix + ".proj.weight"], sd[prefix + ".proj.bias"]).chunk(k, dim=-1)
         return F.layer_norm(x, (x.shape[-1],), None, None, 1e-6) * (1 + st[0]) + st[1], st[2:]
 
-    x = noise.squeeze(-1).transpose(1, 2).to(dt_model)  # (B,3,N,1) -> tokens (B,N,3)
-    sig = sched.sigmas
-    for i, t in enumerate(sched.timesteps):
-        emb = torch.full((x.shape[0], 1), float(t), device=z.device) * freq
+    def one_step(x, t, dt):
+        emb = t.expand(x.shape[0], 1) * freq
         temb = mlp2("time_cond_embed.timestep_proj", torch.cat([emb.cos(), emb.sin()], dim=-1).to(dt_model))
         zt = mlp2("time_cond_embed.condition_proj", z) + temb.unsqueeze(1)
         h = F.linear(x, w_tok, sd["patch_embed.proj.bias"])
@@ -194,7 +193,13 @@ def eager_library_sampler(head, sched, z, noise):
             h = u * gate + h
         y, _ = adaln("norm", h, zt, 2)
         v = F.linear(y, sd["head.weight"], sd["head.bias"])
-        x = v * (sig[i + 1] - sig[i]) + x
+        return v * dt + x
+
+    step_fn = torch.compile(one_step) if compiled else one_step
+    x = noise.squeeze(-1).transpose(1, 2).to(dt_model)  # (B,3,N,1) -> tokens (B,N,3)
+    sig = sched.sigmas
+    for i, t in enumerate(sched.timesteps):
+        x = step_fn(x, torch.full((1, 1), float(t), device=z.device), torch.tensor(sig[i + 1] - sig[i], device=z.device, dtype=dt_model))
     return x.float()
 
 
@@ -208,6 +213,8 @@ def main():
     ap.add_argument("--impl", default="nova", choices=["nova", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the set-by-set and Chamfer legs")
+    ap.add_argument("--compile-bar", action="store_true",
+                    help="also time the reference algorithm under torch.compile (adds ~1-2 min of inductor compile time)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -467,6 +474,25 @@ def main():
                 "rel_max_diff_of_outputs": float((ours - ref_out).abs().max() / ref_out.abs().max())}
         except Exception as e:
             extras["library_bar"] = {"error": str(e)[:300]}
+        if args.compile_bar:
+            try:
+                with torch.no_grad():
+                    for _ in range(2):  # compile + settle
+                        eager_library_sampler(head, sched, z_d, noise_d, compiled=True)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(2):
+                        eager_library_sampler(head, sched, z_d, noise_d, compiled=True)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    cms2 = e0.elapsed_time(e1) / 2
+                extras["library_bar_compiled"] = {"value": B / (cms2 * 1e-3), "unit": "clouds/s", "ms_per_step": cms2,
+                                                  "what": "same algorithm, one diffusion step under torch.compile (inductor), "
+                                                          "bf16, same GPU; a comparator, not the product path",
+                                                  "speedup_of_this_build": cms2 / ms}
+            except Exception as e:
+                extras["library_bar_compiled"] = {"error": str(e)[:300]}
 
     if rank == 0:
         flops = algorithmic_flops(D, B * N)  # per GPU per step
