@@ -358,6 +358,28 @@ def main():
                 "what": "64-set cosine schedule, every set = one fused 25-step call over B*n rows (CUDA-graph replay)"}
         except Exception as e:  # report, never hide
             extras["set_by_set"] = {"error": str(e)[:300]}
+        try:  # the point-cloud pipeline's own partition: 20 equal random subsets (transformer_pointcloud_nova.py:63-78)
+            sizes20 = nb.partition.equal_subset_sizes(N, 20)
+
+            def ar20_pass():
+                return nb.generate_sets(head, sched, z_d, shape, sizes20, None, gen)
+
+            for _ in range(3):
+                ar20_pass()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                ar20_pass()
+            e1.record()
+            torch.cuda.synchronize()
+            ar20_ms = e0.elapsed_time(e1) / 2
+            extras["set_by_set_20"] = {
+                "value": B / (ar20_ms * 1e-3), "unit": "clouds/s", "ms_per_pass": ar20_ms, "sets": 20,
+                "rows_per_head_call": [int(B * min(sizes20)), int(B * max(sizes20))],
+                "what": "20 equal random subsets (dynamic_partition), every set = one fused 25-step call"}
+        except Exception as e:  # report, never hide
+            extras["set_by_set_20"] = {"error": str(e)[:300]}
         try:  # classifier-free guidance (the default of the reference's non-point-cloud pipelines): 2x rows per cloud
             Bg = max(B // 2, 1)
             gs = nb.GuidanceScaler(guidance_scale=5.0)
