@@ -163,6 +163,36 @@ int main(void) {
   for (int i = 0; i < 2 * N; ++i)
     if (h_d1[i] != 0.0f) { fprintf(stderr, "self-distance %g at %d\n", h_d1[i], i); return 1; }
 
+  /* neighbourhood ops on the generated clouds: the nearest neighbour of a point in its own cloud is the point
+     itself (distance 0, index = position), and the local density is the mean of the next 8 distances */
+  float* d_knn;
+  int* d_idx;
+  float* d_dens;
+  CUDA(cudaMalloc((void**)&d_knn, sizeof(float) * 2 * N * 9));
+  CUDA(cudaMalloc((void**)&d_idx, sizeof(int) * 2 * N * 9));
+  CUDA(cudaMalloc((void**)&d_dens, sizeof(float) * 2 * N));
+  CHECK(nova_knn(d_out, d_out, 2, N, N, 9, d_knn, d_idx, stream));
+  CHECK(nova_local_density(d_out, 2, N, 8, d_dens, stream));
+  static float h_knn[2 * N * 9], h_dens[2 * N];
+  static int h_idx[2 * N * 9];
+  CUDA(cudaStreamSynchronize(stream));
+  CUDA(cudaMemcpy(h_knn, d_knn, sizeof(h_knn), cudaMemcpyDeviceToHost));
+  CUDA(cudaMemcpy(h_idx, d_idx, sizeof(h_idx), cudaMemcpyDeviceToHost));
+  CUDA(cudaMemcpy(h_dens, d_dens, sizeof(h_dens), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 2 * N; ++i) {
+    float acc = 0.f;
+    for (int r = 1; r < 9; ++r) acc += h_knn[i * 9 + r];
+    if (h_knn[i * 9] != 0.0f || h_idx[i * 9] != i % N || h_dens[i] != acc / 8.0f) {
+      fprintf(stderr, "kNN/density mismatch at %d: d0 %g idx0 %d density %g vs %g\n", i, h_knn[i * 9], h_idx[i * 9],
+              h_dens[i], acc / 8.0f);
+      return 1;
+    }
+  }
+  if (nova_knn(d_out, d_out, 2, N, N, 33, d_knn, d_idx, stream) == NOVA_OK) {
+    fprintf(stderr, "k = 33 was not rejected\n");
+    return 1;
+  }
+
   /* error path: a too-small workspace must be refused with a message, not crash */
   if (nova_head_sample(head, d_noise, d_z, NULL, B, B, N, N, timesteps, sigmas, S, &g, d_out, d_ws, 1024, stream) != NOVA_ERR_WORKSPACE) {
     fprintf(stderr, "small workspace was not rejected\n");
