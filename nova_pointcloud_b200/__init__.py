@@ -22,6 +22,7 @@ from .pipeline import (  # noqa: F401
     generate_sets,
     sample_sharded,
     shard_range,
+    standard_point_cloud_generation,
 )
 from .chamfer import (  # noqa: F401
     chamfer_distance,

@@ -59,8 +59,8 @@ def feature_aware_interpolation(points, target_size: int, indices: Optional[torc
         out = p.repeat(1, target_size // N + 1, 1)[:, :target_size, :]
     else:
         if indices is None:
-            indices = torch.randperm(N, generator=generator, device=p.device if generator is None or
-                                     generator.device.type == "cuda" else "cpu")[:target_size]
+            gen_dev = generator.device if generator is not None else p.device
+            indices = torch.randperm(N, generator=generator, device=gen_dev)[:target_size]
         indices = torch.as_tensor(indices, device=p.device, dtype=torch.long)
         if indices.numel() != target_size or int(indices.min()) < 0 or int(indices.max()) >= N:
             raise NovaError("feature_aware_interpolation: indices must be target_size positions inside the cloud")
@@ -74,7 +74,7 @@ def dynamic_partition(points: torch.Tensor, k: int = 20, generator: Optional[tor
     if points.dim() != 3:
         raise NovaError(f"dynamic_partition expects (B,N,dim); got {tuple(points.shape)}")
     n = points.shape[1]
-    gdev = "cpu" if generator is not None and generator.device.type == "cpu" else points.device
+    gdev = generator.device if generator is not None else points.device
     perm = torch.randperm(n, generator=generator, device=gdev).to(points.device)
     size = n // k
     subsets = [points[:, perm[i * size:(i + 1) * size if i < k - 1 else n], :] for i in range(k)]

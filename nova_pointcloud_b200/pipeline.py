@@ -116,6 +116,24 @@ def generate_sets(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler
     return x_tok
 
 
+def standard_point_cloud_generation(point_cloud: torch.Tensor, num_points: int,
+                                    generator: Optional[torch.Generator] = None, noise_scale: float = 0.1) -> torch.Tensor:
+    """The reference's post-processing of one denoised cloud (N,3) -> (num_points,3)
+    (pipeline_nova_pointcloud_gen.py:271-294): random subset when N > num_points, tile-and-cut when N < num_points,
+    ``tanh``, ``+ noise_scale * randn``, clamp to [-1, 1].  The reference draws from the unseeded global RNG; here the
+    draws come from ``generator`` (element-wise torch ops on the cloud's device -- plumbing, not a kernel of this build)."""
+    n = point_cloud.shape[0]
+    gdev = generator.device if generator is not None else point_cloud.device
+    if n > num_points:
+        keep = torch.randperm(n, generator=generator, device=gdev)[:num_points].to(point_cloud.device)
+        point_cloud = point_cloud[keep]
+    elif n < num_points:
+        point_cloud = point_cloud.repeat(num_points // n + 1, 1)[:num_points]
+    point_cloud = torch.tanh(point_cloud)
+    noise = torch.randn(point_cloud.shape, generator=generator, device=gdev, dtype=point_cloud.dtype).to(point_cloud.device)
+    return torch.clamp(point_cloud + noise * noise_scale, -1.0, 1.0)
+
+
 class NOVAPointCloudPipelineOutput:
     def __init__(self, point_clouds: List[np.ndarray], colors: Optional[List[np.ndarray]] = None):
         self.point_clouds = point_clouds
@@ -171,7 +189,7 @@ class NOVAPointCloudGenerationPipeline:
                  generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
                  prompt_embeds: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
                  disable_progress_bar: bool = False, output_type: str = "numpy",
-                 use_autoregressive: Optional[bool] = None, set_schedule: str = "cosine",
+                 use_autoregressive: Optional[bool] = None, set_schedule: str = "cosine", postprocess: bool = False,
                  **kwargs) -> NOVAPointCloudPipelineOutput:
         head = self.transformer
         if head.token_dim != 3:
@@ -215,8 +233,11 @@ class NOVAPointCloudGenerationPipeline:
                 raise NovaError(f"unknown set_schedule {set_schedule!r} (cosine | subsets)")
             tokens = generate_sets(head, self.scheduler, z, shape, sizes, gs, generator)
         # The reference post-processing (randperm / repeat to num_points, tanh, +0.1*randn, clamp) draws
-        # unseeded global-RNG noise and is not reproducible; the denoised points are returned as they are.
+        # unseeded global-RNG noise and is not reproducible; by default the denoised points are returned as they
+        # are, ``postprocess=True`` applies it with draws from ``generator``.
         clouds = [tokens[i] for i in range(batch_total)]
+        if postprocess:
+            clouds = [standard_point_cloud_generation(c, num_points, generator) for c in clouds]
         colors = [c.abs().clamp(0, 1) for c in clouds]
         if output_type == "numpy":
             clouds = [c.cpu().numpy() for c in clouds]

@@ -140,3 +140,19 @@ def test_gather_shards_world_size_2_gloo(total):
         assert p.exitcode == 0
     for _, vals in res:
         assert vals == [float(i) for i in range(total)]
+
+
+def test_standard_point_cloud_generation_contract():
+    """Post-processing of pipeline_nova_pointcloud_gen.py:271-294: subset / tile to num_points, tanh, noise, clamp."""
+    import nova_pointcloud_b200 as nb
+
+    pc = torch.randn(50, 3) * 2
+    up = nb.standard_point_cloud_generation(pc, 120, noise_scale=0.0)
+    assert up.shape == (120, 3) and torch.equal(up, torch.tanh(pc.repeat(3, 1)[:120]))  # 120 // 50 + 1 copies, cut
+    g = torch.Generator().manual_seed(3)
+    down = nb.standard_point_cloud_generation(pc, 20, generator=g, noise_scale=0.0)
+    keep = torch.randperm(50, generator=torch.Generator().manual_seed(3))[:20]
+    assert torch.equal(down, torch.tanh(pc[keep]))
+    same = nb.standard_point_cloud_generation(pc, 50, generator=torch.Generator().manual_seed(4))
+    assert same.shape == (50, 3) and float(same.abs().max()) <= 1.0
+    assert 0.05 < float((same - torch.tanh(pc)).std()) < 0.2  # 0.1-sigma noise, clipped at the box
