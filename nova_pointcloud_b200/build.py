@@ -56,7 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [cc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("NOVA_B200_NVCC_FLAGS", "").split()  # diagnostic builds, e.g. -DNOVA_GEMM_TIMELINE
+        cmd = [cc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:

@@ -311,6 +311,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P::OFF_BAR + 8 * (2 * STAGES + 4));
 
   pdl_trigger();  // the next kernel may be scheduled as soon as resources free up; it waits for our completion itself
+#ifdef NOVA_GEMM_TIMELINE  // diagnostic build (scripts/profile_gemm_timeline.py): SM-clock stamps of CTA 0 in the debug words
+  const long long tl_t0 = clock64();
+#define NOVA_TL_STAMP(word) do { if (dbg && blockIdx.x == 0) { dbg[word] = (uint32_t)(clock64() - tl_t0); } } while (0)
+#else
+#define NOVA_TL_STAMP(word) do { } while (0)
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the CTA pair
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
@@ -343,6 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   // Everything above (barriers, TMEM, tensor-map prefetch) is independent of the preceding kernel and overlaps
   // its tail; from here on global memory written by it is read (A via TMA, x / rowstats) or overwritten (C).
   pdl_wait();
+  if (threadIdx.x == 0) NOVA_TL_STAMP(0);  // prologue done and the preceding kernel complete
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------------------------------------- TMA producer (both CTAs of a pair)
@@ -381,6 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar(stage), phase, dbg, 0x300u | stage);  // TMA bytes landed (both CTAs)
+          if (tile == group && kb == 0) NOVA_TL_STAMP(1);  // first operands landed
           tcgen05_fence_after();
           const uint32_t sa = base + stage * STAGE_BYTES;
           const uint64_t a_desc = make_smem_desc_sw128(sa);
@@ -435,6 +443,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
       mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf);
+      if (tile == group && threadIdx.x == EPI_WARP0 * 32) NOVA_TL_STAMP(2);  // first accumulator complete
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       if (mod_tile) {
@@ -525,6 +534,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging memory must outlive the last stores' reads
+    if (threadIdx.x == EPI_WARP0 * 32) NOVA_TL_STAMP(3);  // epilogue done
   }
   __syncwarp();  // lanes of the single-lane roles reconverge before the CTA-wide barrier
   tcgen05_fence_before();
