@@ -78,7 +78,34 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
+    def _run_nvml(self) -> bool:
+        """Sample through NVML in-process (about 1 ms per sample) so that even a sub-second timed region gets tens
+        of samples; returns False when NVML is unavailable and the nvidia-smi loop should be used instead."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return False
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row slot
+        while not self._stop_evt.is_set():
+            try:
+                mask = int(reasons_fn(h))
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "", "", "", ""]
+                for bit, slot in bits:
+                    row[slot] = "Active" if mask & bit else "Not Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.01)
+        return True
+
     def run(self):
+        if self._run_nvml():
+            return
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
