@@ -178,6 +178,21 @@ row_kernel(const RowParams p) {
   const float inv_d = 1.0f / static_cast<float>(D);
   const AT* st = static_cast<const AT*>(p.st) + row * p.ldst;
 
+  // bf16 handle (the latency-bound small-M dataflow): this row's gate / scale / shift slices of the statistics are
+  // requested now, kept packed (4 registers per 8 values), so that their L2 round trip overlaps the two LayerNorm
+  // reductions instead of following them (the loads below sit behind stores the compiler must assume may alias).
+  constexpr bool PREFETCH = sizeof(AT) == 2;
+  uint4 pg[PREFETCH && HAS_PREV ? VPL : 1], psc[PREFETCH ? VPL : 1], psh[PREFETCH ? VPL : 1];
+  if (PREFETCH) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int e = (i * 32 + lane) * 8;
+      if (HAS_PREV) pg[i] = *reinterpret_cast<const uint4*>(st + p.gate_off + e);
+      psc[i] = *reinterpret_cast<const uint4*>(st + p.scale_off + e);
+      psh[i] = *reinterpret_cast<const uint4*>(st + p.scale_off + D + e);
+    }
+  }
+
   float x[VPL][8];
   if (HAS_PREV) {
     const AT* xin = static_cast<const AT*>(p.x_in) + row * D;
@@ -215,7 +230,7 @@ row_kernel(const RowParams p) {
     for (int i = 0; i < VPL; ++i) {
       const int e = (i * 32 + lane) * 8;
       float g[8], ga[8], be[8];
-      load8(st + p.gate_off + e, g);
+      if (PREFETCH) unpack8(pg[i], g); else load8(st + p.gate_off + e, g);
       load8(p.gamma + e, ga);
       load8(p.beta + e, be);
 #pragma unroll
@@ -233,8 +248,13 @@ row_kernel(const RowParams p) {
   for (int i = 0; i < VPL; ++i) {
     const int e = (i * 32 + lane) * 8;
     float sc[8], sh[8];
-    load8(st + p.scale_off + e, sc);
-    load8(st + p.scale_off + D + e, sh);
+    if (PREFETCH) {
+      unpack8(psc[i], sc);
+      unpack8(psh[i], sh);
+    } else {
+      load8(st + p.scale_off + e, sc);
+      load8(st + p.scale_off + D + e, sh);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[i][j] = fmaf((x[i][j] - mean) * rstd, 1.0f + sc[j], sh[j]);
     if (OUT == 0) store8(static_cast<AT*>(p.h_out) + row * D + e, x[i]);
