@@ -193,6 +193,17 @@ row_kernel(const RowParams p) {
     }
   }
 
+  // same for the fp32 LayerNorm affine of the block tail while the registers allow it (D <= 1024)
+  constexpr bool PREFETCH_AFFINE = PREFETCH && HAS_PREV && VPL <= 4;
+  float pga[PREFETCH_AFFINE ? VPL : 1][8], pbe[PREFETCH_AFFINE ? VPL : 1][8];
+  if (PREFETCH_AFFINE) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      load8(p.gamma + (i * 32 + lane) * 8, pga[i]);
+      load8(p.beta + (i * 32 + lane) * 8, pbe[i]);
+    }
+  }
+
   float x[VPL][8];
   if (HAS_PREV) {
     const AT* xin = static_cast<const AT*>(p.x_in) + row * D;
@@ -231,11 +242,14 @@ row_kernel(const RowParams p) {
       const int e = (i * 32 + lane) * 8;
       float g[8], ga[8], be[8];
       if (PREFETCH) unpack8(pg[i], g); else load8(st + p.gate_off + e, g);
-      load8(p.gamma + e, ga);
-      load8(p.beta + e, be);
+      if (!PREFETCH_AFFINE) {
+        load8(p.gamma + e, ga);
+        load8(p.beta + e, be);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float ln = fmaf((u[i][j] - mean) * rstd, ga[j], be[j]);
+        const float ln = PREFETCH_AFFINE ? fmaf((u[i][j] - mean) * rstd, pga[i][j], pbe[i][j])
+                                         : fmaf((u[i][j] - mean) * rstd, ga[j], be[j]);
         x[i][j] = fmaf(ln, g[j], x[i][j]);
       }
       if (OUT == 0) store8(xout + e, x[i]);
