@@ -62,6 +62,23 @@ def test_product_fails_loudly_without_cuda():
         nb.chamfer_distance(torch.zeros(4, 3), torch.zeros(4, 3))
     with pytest.raises(NotImplementedError):
         torch.ops.nova_b200.euler_step(torch.zeros(4), torch.zeros(4), 0.1)
+    # the neighbourhood and training-mode entry points added later: same rule, no CPU arithmetic behind them
+    pts = torch.zeros(1, 16, 3)
+    with pytest.raises(nb.NovaError):
+        nb.compute_local_density(pts)
+    with pytest.raises(nb.NovaError):
+        nb.knn(pts, pts, 4)
+    with pytest.raises(nb.NovaError):
+        nb.feature_aware_interpolation(pts, 4)
+    for call in (lambda: torch.ops.nova_b200.knn(pts, pts, 4), lambda: torch.ops.nova_b200.local_density(pts, 8),
+                 lambda: torch.ops.nova_b200.softmax_interp(pts, pts),
+                 lambda: torch.ops.nova_b200.flow_loss(pts, pts, pts, None),
+                 lambda: torch.ops.nova_b200.add_noise(pts, pts, torch.ones(10), torch.ones(10),
+                                                       torch.zeros(1, 16, dtype=torch.int64))):
+        with pytest.raises(NotImplementedError):
+            call()
+    with pytest.raises((nb.NovaError, NotImplementedError)):
+        nb.get_losses(head, nb.FlowMatchEulerDiscreteScheduler(), torch.zeros(1, 4, 64), torch.zeros(1, 3, 4, 1))
 
 
 def test_product_does_not_import_oracle():
