@@ -199,8 +199,9 @@ NOVA_API void nova_launch_count_reset(void);
 /*
  * In-situ kernel timing for bench.py: while enabled (per calling thread), CUDA events are recorded on
  * the launching stream around every launch of these kernel classes:
- *   0 = AdaLN GEMM (M x 20D x D), 1 = other GEMMs (fc1 / fc2 / condition), 2 = row kernels, 3 = prep, 4 = other.
- * nova_profile_read sums the elapsed ms and launches per class (arrays of >= 5 entries), then clears.
+ *   0 = AdaLN GEMM (M x 20D x D), 1 = other GEMMs (fc1 / fc2 / condition), 2 = row kernels, 3 = prep, 4 = other,
+ *   5 = the cluster chain kernel (small M: all stages of a step after the statistics GEMM in one launch).
+ * nova_profile_read sums the elapsed ms and launches per class (arrays of >= 6 entries), then clears.
  */
 NOVA_API int nova_profile_enable(int32_t on);
 NOVA_API int nova_profile_read(double* ms_by_class, int64_t* launches_by_class, int32_t n_classes);
@@ -223,6 +224,12 @@ NOVA_API int nova_debug_gemm(const void* A, const void* W, const float* bias, vo
 NOVA_API int nova_debug_adaln_gemm(const void* A, const void* W, const float* bias, const void* x, void* h_out,
                                    void* gate_out, int64_t M, int64_t D, int64_t K, int32_t n_stats,
                                    int32_t cta_group, void* stream);
+
+/*
+ * Test hook: SM-clock stamps (cycles since kernel entry) of cluster 0 / CTA 0 of the last chain-kernel launch
+ * (csrc/chain_tcgen05.cu), 8 slots per stage; recorded only when NOVA_B200_CHAIN_TIMELINE=1.  Synchronises the device.
+ */
+NOVA_API int nova_debug_chain_timeline(int64_t* out, int32_t n);
 
 /* Test hook: the 4 host-mapped words a tcgen05 kernel writes before trapping on a barrier timeout. */
 NOVA_API int nova_debug_words(uint32_t* out4);

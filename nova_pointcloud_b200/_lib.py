@@ -21,7 +21,7 @@ EXPORTS = [
     "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
     "nova_head_sample", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
-    "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_add_noise", "nova_flow_loss",
+    "nova_debug_chain_timeline", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_add_noise", "nova_flow_loss",
 ]
 
 
@@ -89,6 +89,8 @@ def _declare(lib):
     lib.nova_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]
     lib.nova_debug_adaln_gemm.restype = C.c_int
     lib.nova_debug_adaln_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
+    lib.nova_debug_chain_timeline.restype = C.c_int
+    lib.nova_debug_chain_timeline.argtypes = [C.POINTER(C.c_int64), i32]
     lib.nova_debug_words.restype = C.c_int
     lib.nova_debug_words.argtypes = [C.POINTER(C.c_uint32)]
 

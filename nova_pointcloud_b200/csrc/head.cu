@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_api.cuh"
+#include "chain_api.cuh"
 #include "rowwise.cuh"
 
 using namespace nova;
@@ -113,6 +114,13 @@ struct nova_head {
   // 21 launches per step; its [M, 20 D] statistics tensor is small there.  NOVA_B200_WIDE_ADA_ROWS overrides.
   int64_t wide_ada_rows = 1024;
   bool fused(int64_t rows) const { return cfg.dtype == NOVA_BF16 && !use_simt_gemm && rows > wide_ada_rows; }
+  // Wide dataflow, bf16: everything after the statistics GEMM (patch embed, 6 x (fc1, fc2, block tail + next
+  // modulation), head + Euler: 19 dependent launches) runs as ONE cluster kernel (chain_tcgen05.cu) in which a
+  // cluster of 8 CTAs owns 128 rows for the whole chain.  NOVA_B200_CHAIN=0 restores the launch chain (bit-identical).
+  bool use_chain = false;  // v1 is slower than the launch chain (TMA operand ingest per stage); opt-in until it wins
+  bool chained(int64_t rows) const {
+    return use_chain && cfg.dtype == NOVA_BF16 && !use_simt_gemm && !fused(rows) && chain::supported(cfg.width);
+  }
 };
 
 namespace {
@@ -317,6 +325,20 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
     ProfileScope ps(KC_GEMM_ADA, s);
     NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.a), D, static_cast<const AT*>(h->w_ada), D, h->b_ada,
                             static_cast<AT*>(w.st), n_ada, M, n_ada, D, EPI_BIAS, s));
+  }
+  if (h->chained(M)) {
+    chain::ChainParams cp{};
+    cp.M = M; cp.D = D; cp.T = T; cp.depth = depth;
+    cp.x = static_cast<bf16*>(w.x); cp.h = static_cast<bf16*>(w.h);
+    cp.u1 = static_cast<bf16*>(w.u1); cp.u2 = static_cast<bf16*>(w.u2);
+    cp.st = static_cast<const bf16*>(io.st_pre ? io.st_pre : w.st); cp.ldst = n_ada;
+    cp.fc_params = h->b_fc1[0];  // b_fc1 | b_fc2 | gamma | beta per block, contiguous in the arena
+    cp.x_tok = io.x_tok; cp.x_rows = io.x_rows; cp.Wp = h->w_patch; cp.bp = h->b_patch;
+    cp.Wh = h->w_head; cp.bh = h->b_head; cp.v_out = io.v_out; cp.xt_out = io.xt_out; cp.dt = io.dt;
+    static const bool want_timeline = std::getenv("NOVA_B200_CHAIN_TIMELINE") != nullptr;  // diagnostic only
+    cp.timeline = chain::timeline_buffer(want_timeline);
+    ProfileScope ps(KC_CHAIN, s);
+    return chain::launch(cp, static_cast<const bf16*>(h->w_fc1[0]), s);
   }
   rw::RowParams p{};
   p.M = M; p.D = D; p.T = T;
@@ -645,6 +667,7 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   h->wide_ada_rows = std::max<int64_t>(1024, static_cast<int64_t>(2.1e9 / (static_cast<double>(cfg->width) * cfg->width)));
   if (const char* env_wide = std::getenv("NOVA_B200_WIDE_ADA_ROWS")) h->wide_ada_rows = std::atoll(env_wide);
   if (const char* env_alt = std::getenv("NOVA_B200_ALTERNATE")) h->alternate_rows = std::atoi(env_alt) != 0;
+  if (const char* env_chain = std::getenv("NOVA_B200_CHAIN")) h->use_chain = std::atoi(env_chain) != 0;
   const char* env_graph = std::getenv("NOVA_B200_GRAPH");
   h->use_graphs = env_graph == nullptr || std::atoi(env_graph) != 0;
   if (h->use_graphs && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {

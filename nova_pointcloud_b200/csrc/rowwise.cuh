@@ -168,12 +168,17 @@ __device__ __forceinline__ void row_stats(const float (&v)[VPL][8], float inv_d,
 // HAS_PREV: x <- LN_affine(u; 1e-5) * gate + x        (tail of the block that just ran)
 // then      y  = LN(x; 1e-6) * (1 + scale) + shift     (AdaLN of the next consumer)
 // OUT == 0: h_out <- y.   OUT == 1: v = Wh y + bh; optional Euler update of the latent.
-template <typename AT, int VPL, bool HAS_PREV, int OUT>
-__global__ void __launch_bounds__(THREADS)
-row_kernel(const RowParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
-  if (row >= p.M) return;
+// COHERENT (the cluster chain kernel, chain_tcgen05.cu): u and x were written earlier in the SAME kernel, u by other
+// CTAs of the cluster, so they are read with L2-coherent loads (ld.global.cg) instead of through L1.
+__device__ __forceinline__ void load8_cg(const bf16* p, float (&v)[8]) {
+  uint4 raw;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p));
+  unpack8(raw, v);
+}
+__device__ __forceinline__ void load8_cg(const float* p, float (&v)[8]) { load8(p, v); }
+
+template <typename AT, int VPL, bool HAS_PREV, int OUT, bool COHERENT = false>
+__device__ __forceinline__ void row_body(const RowParams& p, const int64_t row, const int lane) {
   const int D = p.D;
   const float inv_d = 1.0f / static_cast<float>(D);
   const AT* st = static_cast<const AT*>(p.st) + row * p.ldst;
@@ -208,7 +213,9 @@ row_kernel(const RowParams p) {
   if (HAS_PREV) {
     const AT* xin = static_cast<const AT*>(p.x_in) + row * D;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) load8(xin + (i * 32 + lane) * 8, x[i]);
+    for (int i = 0; i < VPL; ++i) {
+      if (COHERENT) load8_cg(xin + (i * 32 + lane) * 8, x[i]); else load8(xin + (i * 32 + lane) * 8, x[i]);
+    }
   } else {
     // PatchEmbed with K = T (embeddings.py:146,165): too skinny for a GEMM, fused here
     const float* xt = p.x_tok + (row % p.x_rows) * p.T;
@@ -233,7 +240,9 @@ row_kernel(const RowParams p) {
     const AT* uin = static_cast<const AT*>(p.u) + row * D;
     float u[VPL][8];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) load8(uin + (i * 32 + lane) * 8, u[i]);
+    for (int i = 0; i < VPL; ++i) {
+      if (COHERENT) load8_cg(uin + (i * 32 + lane) * 8, u[i]); else load8(uin + (i * 32 + lane) * 8, u[i]);
+    }
     float mean, rstd;
     row_stats<VPL>(u, inv_d, 1e-5f, mean, rstd);
     AT* xout = static_cast<AT*>(p.x_out) + row * D;
@@ -293,6 +302,15 @@ row_kernel(const RowParams p) {
       }
     }
   }
+}
+
+template <typename AT, int VPL, bool HAS_PREV, int OUT>
+__global__ void __launch_bounds__(THREADS)
+row_kernel(const RowParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= p.M) return;
+  row_body<AT, VPL, HAS_PREV, OUT>(p, row, lane);
 }
 
 template <typename AT, int VPL>

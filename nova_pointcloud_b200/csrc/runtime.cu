@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_api.cuh"
+#include "chain_api.cuh"
 #include "rowwise.cuh"
 
 namespace nova {
@@ -278,4 +279,16 @@ extern "C" int nova_debug_adaln_gemm(const void* A, const void* W, const float* 
   cudaFree(b_il);
   cudaFree(rstat);
   return rc;
+}
+
+// Test hook: SM-clock stamps of the last chain-kernel launch (cluster 0, CTA 0), 8 per stage; see chain_tcgen05.cu.
+// Needs NOVA_B200_CHAIN_TIMELINE=1 in the environment of the process.  Synchronises the device.
+extern "C" int nova_debug_chain_timeline(int64_t* out, int32_t n) {
+  NOVA_REQUIRE(out != nullptr && n > 0, "nova_debug_chain_timeline: bad arguments");
+  long long* buf = chain::timeline_buffer(false);
+  NOVA_REQUIRE(buf != nullptr, "nova_debug_chain_timeline: no timeline was recorded (set NOVA_B200_CHAIN_TIMELINE=1)");
+  const int m = n < chain::TIMELINE_SLOTS ? n : chain::TIMELINE_SLOTS;
+  NOVA_CHECK_CUDA(cudaDeviceSynchronize());
+  NOVA_CHECK_CUDA(cudaMemcpy(out, buf, m * sizeof(long long), cudaMemcpyDeviceToHost));
+  return NOVA_OK;
 }

@@ -377,7 +377,7 @@ def launch_count_reset():
     _lib.lib().nova_launch_count_reset()
 
 
-KERNEL_CLASSES = ("gemm_ada", "gemm_fc", "row", "prep", "other")
+KERNEL_CLASSES = ("gemm_ada", "gemm_fc", "row", "prep", "other", "chain")
 
 
 def profile_enable(on: bool):
