@@ -21,6 +21,7 @@ struct ChainParams {
   const float* x_tok;  // [x_rows, T] latent of the selected tokens
   int64_t x_rows;
   const float* Wp;     // [D, T] token-order patch-embed weight
+  const float* WpT;    // [T, D] its transpose
   const float* bp;     // [D]
   const float* Wh;     // [T, D]
   const float* bh;     // [T]
@@ -32,6 +33,8 @@ struct ChainParams {
 };
 
 bool supported(int D);
+// rows up to which the chain kernel beats the separate launches: all ceil(M / 64) clusters resident at once
+int64_t profitable_rows(int D);
 // w_stack: the fc weights of all blocks as one K-major matrix [2 depth D, D]: fc1_0 | fc2_0 | fc1_1 | ...
 int launch(const ChainParams& p, const bf16* w_stack, cudaStream_t stream);
 constexpr int TIMELINE_SLOTS = 8 * 64;

@@ -18,6 +18,10 @@
 //   R stages: the 64 warps of the cluster take the 128 rows (rw::row_body, the arithmetic of the fused row kernel).
 // Activations (x, h, u1, u2: 128 x D bf16 each per cluster) stay in L2; stores are made visible to the other CTAs'
 // TMA loads by fence.proxy.async + barrier.cluster (release / acquire).
+//
+// This header is compiled by chain_r64.cu and chain_r128.cu (rows per cluster; NOVA_CHAIN_ROWS selects which).
+#pragma once
+
 #include <cuda.h>
 
 #define NOVA_GEMM_TU 99  // PTX wrappers only, no GEMM instantiations
@@ -31,25 +35,47 @@ namespace chain {
 using namespace nova::tc;
 
 constexpr int CL = 8;                  // CTAs per cluster
-constexpr int ROWS = 128;              // rows per cluster = UMMA M
 constexpr int CH_THREADS = 256;
-constexpr int A_STAGES = 4;
-constexpr int A_BYTES = ROWS * BK * 2;  // 16 KB per k-block
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-template <int VPL>
+// ROWS = rows per cluster: 128, or 64 (twice the clusters, half the activation bytes every CTA has to take in per
+// stage and one row per warp in the R stages: the better choice while 8 * ceil(M / 64) CTAs still fit on the chip).
+// The A operand of a stage (h or u1, ROWS x D) is needed by all 8 CTAs: the k-blocks are dealt round-robin to the
+// CTAs, each loads its k-blocks ONCE and MULTICASTS them into the same shared-memory offset of all 8 CTAs (a TMA
+// issue costs the issuing thread ~250 cycles, so 12 / 8 issues per CTA and stage instead of 12 matter).
+template <int VPL, int ROWS>
 struct ChainPlan {
+  static_assert(ROWS == 64 || ROWS == 128, "rows per cluster");
   static constexpr int W_COLS = 32 * VPL;             // output columns per CTA (D / 8)
-  static constexpr int W_BYTES = W_COLS * BK * 2;     // one k-block of the W slice (multiple of 1024)
-  static constexpr int NUM_K = 4 * VPL;               // D / 64
-  static constexpr int W_MAX = (SMEM_LIMIT - 2048 - A_STAGES * A_BYTES) / W_BYTES;
-  static constexpr int W_STAGES = W_MAX < NUM_K ? W_MAX : NUM_K;
-  static constexpr int OFF_W = A_STAGES * A_BYTES;
+  static constexpr int NUM_K = 4 * VPL;               // D / 64 k-blocks per stage
+  // The single-thread producer / MMA loops pay ~100-250 cycles per mbarrier wait, tcgen05.commit and TMA issue, far
+  // more than the 4 MMAs of one k-block take, so the rings are managed in GROUPS of KG k-blocks: one wait, one
+  // expect_tx and one commit per group (measured: 845 cycles per k-block with per-k-block barriers).
+  static constexpr int KG_A = VPL <= 3 ? 4 : 2;       // k-blocks per A group
+  static constexpr int KG_W = 2;                      // k-blocks per W group (finer: the W ring is what runs ahead)
+  static constexpr int GPS_A = NUM_K / KG_A;          // groups per stage
+  static constexpr int GPS_W = NUM_K / KG_W;
+  static constexpr int A_KB_BYTES = ROWS * BK * 2;    // one k-block of A: 16 KB / 8 KB
+  static constexpr int W_KB_BYTES = W_COLS * BK * 2;  // one k-block of the W slice (multiple of 1024)
+  static constexpr int A_BYTES = KG_A * A_KB_BYTES;   // one group
+  static constexpr int W_BYTES = KG_W * W_KB_BYTES;
+  static constexpr int PAD = 0;
+  static constexpr int AVAIL = SMEM_LIMIT - 3072 - PAD;
+  // A ring: a whole stage if that is <= 96 KB (64 rows) / 128 KB (128 rows), so that every load of a stage is issued
+  // the moment its barrier opens; the W ring takes the rest (at least two groups) and runs ahead of the stage boundary
+  static constexpr int A_BUDGET = (ROWS == 64 ? 96 : 128) * 1024 / A_BYTES;
+  static constexpr int A_FIT = (AVAIL - 2 * W_BYTES) / A_BYTES;
+  static constexpr int A_WANT = A_BUDGET < A_FIT ? A_BUDGET : A_FIT;
+  static constexpr int A_STAGES = A_WANT < GPS_A ? A_WANT : GPS_A;   // ring depths in groups
+  static constexpr int W_FIT = (AVAIL - A_STAGES * A_BYTES) / W_BYTES;
+  static constexpr int W_STAGES = W_FIT < GPS_W ? W_FIT : GPS_W;
+  static constexpr int OFF_W = A_STAGES * A_BYTES + PAD;
   static constexpr int OFF_BIAS = OFF_W + W_STAGES * W_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 1024;     // w <= 256 floats
   static constexpr int SMEM_BYTES = OFF_BAR + 512;
   static constexpr int TMEM_COLS_ALLOC = W_COLS <= 32 ? 32 : W_COLS <= 64 ? 64 : W_COLS <= 128 ? 128 : 256;
-  static_assert(W_STAGES >= 3, "W ring too shallow");
+  static_assert(NUM_K % KG_A == 0 && KG_A % KG_W == 0, "k-blocks per stage must be whole groups");
+  static_assert(A_STAGES >= 1 && (GPS_A == 1 || A_STAGES >= 2) && W_STAGES >= 2, "rings too shallow");
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory plan exceeds 227 KB");
 };
 
@@ -57,7 +83,32 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void all_bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// 2D tiled TMA load multicast to the CTAs in `mask`: data and complete_tx land at the same offsets in each of them
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* t, uint32_t bar, uint32_t dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(t)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `mask` once all prior MMAs of this thread have retired
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+// one lane of a converged warp (the others skip); keeps the surrounding address arithmetic warp-uniform
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // Stage boundary: every global store of this CTA becomes visible to the whole cluster, generic and async proxy alike.
 __device__ __forceinline__ void stage_barrier() {
@@ -67,12 +118,15 @@ __device__ __forceinline__ void stage_barrier() {
   fence_proxy_async_all();
 }
 
-template <int VPL>
+template <int VPL, int ROWS>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_u1,
              const __grid_constant__ CUtensorMap tmap_w, const ChainParams p, uint32_t* dbg) {
-  using P = ChainPlan<VPL>;
-  constexpr int W_COLS = P::W_COLS, NUM_K = P::NUM_K, W_STAGES = P::W_STAGES;
+  using P = ChainPlan<VPL, ROWS>;
+  constexpr int W_COLS = P::W_COLS, KG_A = P::KG_A, KG_W = P::KG_W, GPS_A = P::GPS_A, GPS_W = P::GPS_W;
+  constexpr int W_STAGES = P::W_STAGES, A_STAGES = P::A_STAGES;
+  constexpr int A_BYTES = P::A_BYTES;
+  constexpr uint16_t ALL_CTAS = (1u << CL) - 1u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   const uint32_t base = smem_u32(smem_raw);
@@ -103,7 +157,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
   const int64_t row0 = static_cast<int64_t>(blockIdx.x / CL) * ROWS;  // first row of this cluster
   const int D = p.D, depth = p.depth;
   const int n_f = 2 * depth;           // F stages of the step
-  const int total_k = n_f * NUM_K;     // k-blocks over all F stages
+  const int total_ga = n_f * GPS_A, total_gw = n_f * GPS_W;  // k-block groups over all F stages
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_h);
@@ -111,7 +165,8 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
     prefetch_tmap(&tmap_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    // emptyA: one multicast tcgen05.commit arrival from each of the 8 CTAs (a slot is free once ALL have consumed it)
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), CL); }
     for (int s = 0; s < W_STAGES; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
@@ -124,24 +179,27 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
 
   // ---- W producer state (warp 0, lane 0): weights never depend on this or the preceding kernel
   int w_issued = 0;
-  auto issue_w = [&](int g) {  // global k-block index over all F stages
-    const int f = g / NUM_K, kb = g - f * NUM_K, s = g % W_STAGES;
+  auto issue_w = [&](int g) {  // global W group index over all F stages
+    const int f = g / GPS_W, j = g - f * GPS_W, s = g % W_STAGES;
     mbar_wait(emptyW(s), (static_cast<uint32_t>(g / W_STAGES) & 1u) ^ 1u, dbg, 0x500u | s);
     mbar_expect_tx(fullW(s), P::W_BYTES);
-    tma_load_2d(&tmap_w, fullW(s), base + P::OFF_W + s * P::W_BYTES, kb * BK, f * D + static_cast<int>(rank) * W_COLS);
+#pragma unroll
+    for (int k = 0; k < KG_W; ++k)
+      tma_load_2d(&tmap_w, fullW(s), base + P::OFF_W + s * P::W_BYTES + k * P::W_KB_BYTES, (j * KG_W + k) * BK,
+                  f * D + static_cast<int>(rank) * W_COLS);
   };
   if (warp == 0 && lane == 0) {
-    const int lim = total_k < W_STAGES ? total_k : W_STAGES;
+    const int lim = total_gw < W_STAGES ? total_gw : W_STAGES;
     while (w_issued < lim) issue_w(w_issued++);
   }
   pdl_wait();  // from here on: st (the statistics GEMM of this step) and x_tok (the previous step) are read
   if (threadIdx.x == 0) stamp(0, 6);
 
-  // ---- row stages: warp (rank, warp) of the cluster takes rows g, g + 64 of the 128
+  // ---- row stages: warp (rank, warp) of the cluster takes rows g (and g + 64 when the cluster owns 128 rows)
   rw::RowParams rp{};
   rp.M = p.M; rp.D = D; rp.T = p.T;
   rp.x_in = p.x; rp.x_out = p.x; rp.u = p.u2; rp.st = p.st; rp.ldst = p.ldst; rp.h_out = p.h;
-  rp.x_tok = p.x_tok; rp.x_rows = p.x_rows; rp.Wp = p.Wp; rp.bp = p.bp; rp.Wh = p.Wh; rp.bh = p.bh;
+  rp.x_tok = p.x_tok; rp.x_rows = p.x_rows; rp.Wp = p.Wp; rp.WpT = p.WpT; rp.bp = p.bp; rp.Wh = p.Wh; rp.bh = p.bh;
   rp.v_out = p.v_out; rp.xt_in = p.x_tok; rp.xt_out = p.xt_out; rp.dt = p.dt;
   const int64_t final_off = static_cast<int64_t>(3) * depth * D;
   const int wg = static_cast<int>(rank) * (CH_THREADS / 32) + warp;  // 0..63
@@ -166,46 +224,70 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
     if (warp == 0) {
       if (lane == 0) {  // ------------------------------------------------ TMA producer
         const CUtensorMap* ta = second ? &tmap_u1 : &tmap_h;
-        for (int kb = 0; kb < NUM_K; ++kb) {
-          const int g = f * NUM_K + kb, s = g % A_STAGES;
+        for (int j = 0; j < GPS_A; ++j) {
+          const int g = f * GPS_A + j, s = g % A_STAGES;
           mbar_wait(emptyA(s), (static_cast<uint32_t>(g / A_STAGES) & 1u) ^ 1u, dbg, 0x100u | s);
-          mbar_expect_tx(fullA(s), A_BYTES);
-          tma_load_2d(ta, fullA(s), base + s * A_BYTES, kb * BK, static_cast<int>(row0));
-          if (w_issued <= g) issue_w(w_issued++);
+          mbar_expect_tx(fullA(s), A_BYTES);  // KG_A k-blocks, whoever of the 8 CTAs multicasts them
+#pragma unroll
+          for (int k = 0; k < KG_A; ++k) {
+            const int kb = j * KG_A + k;
+            if (static_cast<uint32_t>(kb + f) % CL == rank)  // my turn (rotated by stage: 12 k-blocks over 8 CTAs)
+              tma_load_2d_mc(ta, fullA(s), base + s * A_BYTES + k * P::A_KB_BYTES, kb * BK, static_cast<int>(row0), ALL_CTAS);
+          }
+          // the W groups this A group is multiplied with, if the run-ahead has not issued them yet
+          const int gw_need = f * GPS_W + (j + 1) * (KG_A / KG_W);
+          while (w_issued < gw_need) issue_w(w_issued++);
         }
         stamp(1 + f, 1);
         // run ahead: weights of the following stage(s) into the slots this stage's MMAs free
-        const int ahead = (f + 1) * NUM_K + W_STAGES;
-        const int lim = total_k < ahead ? total_k : ahead;
+        const int ahead = (f + 1) * GPS_W + W_STAGES;
+        const int lim = total_gw < ahead ? total_gw : ahead;
         while (w_issued < lim) issue_w(w_issued++);
       }
     } else if (warp == 1) {
-      if (lane == 0) {  // ------------------------------------------------ MMA issuer
+      {  // ---------------------------------------------------------------- MMA issuer
+        // The whole warp walks the loop (waits, descriptor arithmetic: warp-uniform, so it can stay in uniform
+        // registers) and one elected lane issues; with a single-lane loop every tcgen05.mma cost ~61 cycles of
+        // R2UR traffic + issue, more than the instruction takes on the tensor pipe at these tile sizes.
         constexpr uint32_t idesc = make_idesc_bf16(ROWS, W_COLS);
         tcgen05_fence_after();
-        for (int kb = 0; kb < NUM_K; ++kb) {
-          const int g = f * NUM_K + kb, sa = g % A_STAGES, sw = g % W_STAGES;
-          mbar_wait(fullA(sa), static_cast<uint32_t>(g / A_STAGES) & 1u, dbg, 0x300u | sa);
-          mbar_wait(fullW(sw), static_cast<uint32_t>(g / W_STAGES) & 1u, dbg, 0x600u | sw);
+        for (int j = 0; j < GPS_W; ++j) {
+          const int gw = f * GPS_W + j, sw = gw % W_STAGES;
+          const int kb0 = j * KG_W;                       // first k-block of this W group
+          const int ga = f * GPS_A + kb0 / KG_A, sa = ga % A_STAGES;
+          if (kb0 % KG_A == 0) mbar_wait(fullA(sa), static_cast<uint32_t>(ga / A_STAGES) & 1u, dbg, 0x300u | sa);
+          mbar_wait(fullW(sw), static_cast<uint32_t>(gw / W_STAGES) & 1u, dbg, 0x600u | sw);
           tcgen05_fence_after();
-          if (kb == 0) stamp(1 + f, 2);
-          const uint64_t a_desc = make_smem_desc_sw128(base + sa * A_BYTES);
-          const uint64_t b_desc = make_smem_desc_sw128(base + P::OFF_W + sw * P::W_BYTES);
+          if (j == 0 && lane == 0) stamp(1 + f, 2);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(emptyA(sa));
-          umma_commit(emptyW(sw));
+            for (int kk = 0; kk < KG_W; ++kk) {
+              const uint64_t a_desc = make_smem_desc_sw128(base + sa * A_BYTES + (kb0 % KG_A + kk) * P::A_KB_BYTES);
+              const uint64_t b_desc = make_smem_desc_sw128(base + P::OFF_W + sw * P::W_BYTES + kk * P::W_KB_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc, (j > 0 || kk > 0 || k > 0) ? 1u : 0u);
+            }
+            // a slot nobody will refill needs no release (and no arrival may reach a CTA that has already exited)
+            if (gw + W_STAGES < total_gw) umma_commit(emptyW(sw));
+            if ((kb0 + KG_W) % KG_A == 0 && ga + A_STAGES < total_ga) umma_commit_mc(emptyA(sa), ALL_CTAS);
+          }
+          __syncwarp();
         }
-        umma_commit(tfull);
-        stamp(1 + f, 3);
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
+        if (lane == 0) stamp(1 + f, 3);
       }
     } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue: thread = row
       const int q = warp & 3, tid_e = threadIdx.x - EPI_WARP0 * 32;
       const float* bias = p.fc_params + (static_cast<int64_t>(4) * blk + (second ? 1 : 0)) * D + static_cast<int>(rank) * W_COLS;
       for (int j = tid_e; j < W_COLS; j += 128) bias_s[j] = __ldg(bias + j);
       epi_bar_sync();
-      const int64_t row = row0 + q * 32 + lane;
+      // accumulator rows -> TMEM lanes: M = 128: row r in lane r; M = 64: row r in lane (r % 16) + 32 (r / 16), i.e.
+      // every epilogue warp holds ROWS / 4 rows in its first lanes (cute::UMMA tmem_frg_1sm, "half subpartitions")
+      constexpr int RPW = ROWS / 4;
+      const int64_t row = row0 + q * RPW + lane;
+      const bool have_row = lane < RPW && row < p.M;
       bf16* out = (second ? p.u2 : p.u1) + row * D + static_cast<int>(rank) * W_COLS;
       mbar_wait(tfull, static_cast<uint32_t>(f) & 1u, dbg, 0x400u);
       if (tid_e == 0) stamp(1 + f, 4);
@@ -216,7 +298,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
         uint32_t ra[32];
         tmem_ld_32x32(t_row + cc * 32, ra);
         tmem_ld_wait();
-        if (row < p.M) {
+        if (have_row) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
@@ -264,27 +346,23 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
 }
 
 // ---------------------------------------------------------------- host side
-namespace {
-struct DeviceAttr {
-  bool done[64] = {};
-};
-template <int VPL>
+template <int VPL, int ROWS>
 int set_attrs() {
-  static DeviceAttr attr;  // per device: the attribute belongs to the function ON a device
+  static bool done[64] = {};  // per device: the attribute belongs to the function ON a device
   int dev = 0;
   NOVA_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr.done[dev]) {
-    NOVA_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ChainPlan<VPL>::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) attr.done[dev] = true;
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<VPL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ChainPlan<VPL, ROWS>::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) done[dev] = true;
   }
   return NOVA_OK;
 }
 
-template <int VPL>
+template <int VPL, int ROWS>
 int launch_vpl(const ChainParams& p, const bf16* w_stack, int64_t w_rows, cudaStream_t stream) {
-  using P = ChainPlan<VPL>;
-  NOVA_PROPAGATE(set_attrs<VPL>());
+  using P = ChainPlan<VPL, ROWS>;
+  NOVA_PROPAGATE((set_attrs<VPL, ROWS>()));
   CUtensorMap th, tu, tw;
   NOVA_PROPAGATE(make_tmap_kmajor(&th, p.h, p.M, p.D, p.D, ROWS));
   NOVA_PROPAGATE(make_tmap_kmajor(&tu, p.u1, p.M, p.D, p.D, ROWS));
@@ -303,40 +381,77 @@ int launch_vpl(const ChainParams& p, const bf16* w_stack, int64_t w_rows, cudaSt
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel<VPL>, th, tu, tw, p, debug_word()));
+  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel<VPL, ROWS>, th, tu, tw, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
-}  // namespace
 
-bool supported(int D) { return D > 0 && D % 256 == 0 && D <= 2048; }
-
-long long* timeline_buffer(bool create) {
-  static long long* buf = nullptr;
-  if (buf == nullptr && create) {
-    if (cudaMalloc(&buf, TIMELINE_SLOTS * sizeof(long long)) != cudaSuccess) buf = nullptr;
-    else cudaMemset(buf, 0, TIMELINE_SLOTS * sizeof(long long));
+// clusters of this kernel the device can hold at once (cached per device); 0 if the query fails
+template <int VPL, int ROWS>
+int max_clusters_vpl() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] == 0) {
+    if (set_attrs<VPL, ROWS>() != NOVA_OK) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * 64);
+    cfg.blockDim = dim3(CH_THREADS);
+    cfg.dynamicSmemBytes = ChainPlan<VPL, ROWS>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, chain_kernel<VPL, ROWS>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    cached[dev] = n > 0 ? n : -1;
   }
-  return buf;
+  return cached[dev] > 0 ? cached[dev] : 0;
 }
 
-int launch(const ChainParams& p, const bf16* w_stack, cudaStream_t stream) {
-  if (p.M <= 0) return NOVA_OK;
-  NOVA_REQUIRE(supported(p.D), "chain kernel: unsupported width %d", p.D);
-  const int64_t w_rows = static_cast<int64_t>(2) * p.depth * p.D;
-  switch (p.D / 256) {
-    case 1: return launch_vpl<1>(p, w_stack, w_rows, stream);
-    case 2: return launch_vpl<2>(p, w_stack, w_rows, stream);
-    case 3: return launch_vpl<3>(p, w_stack, w_rows, stream);
-    case 4: return launch_vpl<4>(p, w_stack, w_rows, stream);
-    case 5: return launch_vpl<5>(p, w_stack, w_rows, stream);
-    case 6: return launch_vpl<6>(p, w_stack, w_rows, stream);
-    case 7: return launch_vpl<7>(p, w_stack, w_rows, stream);
-    case 8: return launch_vpl<8>(p, w_stack, w_rows, stream);
+template <int ROWS>
+int max_clusters_rows(int D) {
+  switch (D / 256) {
+    case 1: return max_clusters_vpl<1, ROWS>();
+    case 2: return max_clusters_vpl<2, ROWS>();
+    case 3: return max_clusters_vpl<3, ROWS>();
+    case 4: return max_clusters_vpl<4, ROWS>();
+    case 5: return max_clusters_vpl<5, ROWS>();
+    case 6: return max_clusters_vpl<6, ROWS>();
+    case 7: return max_clusters_vpl<7, ROWS>();
+    case 8: return max_clusters_vpl<8, ROWS>();
     default: break;
   }
+  return 0;
+}
+
+template <int ROWS>
+int launch_rows(const ChainParams& p, const bf16* w_stack, cudaStream_t stream) {
+  const int64_t w_rows = static_cast<int64_t>(2) * p.depth * p.D;
+  switch (p.D / 256) {
+    case 1: return launch_vpl<1, ROWS>(p, w_stack, w_rows, stream);
+    case 2: return launch_vpl<2, ROWS>(p, w_stack, w_rows, stream);
+    case 3: return launch_vpl<3, ROWS>(p, w_stack, w_rows, stream);
+    case 4: return launch_vpl<4, ROWS>(p, w_stack, w_rows, stream);
+    case 5: return launch_vpl<5, ROWS>(p, w_stack, w_rows, stream);
+    case 6: return launch_vpl<6, ROWS>(p, w_stack, w_rows, stream);
+    case 7: return launch_vpl<7, ROWS>(p, w_stack, w_rows, stream);
+    case 8: return launch_vpl<8, ROWS>(p, w_stack, w_rows, stream);
+    default: break;
+  }
+  set_error("chain kernel: unsupported width %d", p.D);
   return NOVA_ERR_INVALID;
 }
+
+int launch_rows64(const ChainParams& p, const bf16* w_stack, cudaStream_t stream);
+int max_clusters64(int D);
+int launch_rows128(const ChainParams& p, const bf16* w_stack, cudaStream_t stream);
 
 }  // namespace chain
 }  // namespace nova

@@ -95,9 +95,12 @@ struct nova_head {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fork_ada = true;
   int64_t fork_ada_rows = 640;
+  bool fork_rows_forced = false;
   bool can_fork(int64_t rows, int steps) const {
+    // with the cluster chain kernel (8 CTAs per 64 rows) the rest of the chip is free for the forked statistics GEMM
+    // over the kernel's whole row range: 3.02 -> 2.63 ms per 25-step call at 768 rows
     return fork_ada && side_stream != nullptr && cfg.dtype == NOVA_BF16 && !use_simt_gemm && !fused(rows) && steps > 1 &&
-           rows > 0 && rows <= fork_ada_rows;
+           rows > 0 && (rows <= fork_ada_rows || (!fork_rows_forced && chained(rows)));
   }
   mutable std::mutex graph_mutex;
   mutable std::vector<LoopGraph> graphs;
@@ -117,9 +120,9 @@ struct nova_head {
   // Wide dataflow, bf16: everything after the statistics GEMM (patch embed, 6 x (fc1, fc2, block tail + next
   // modulation), head + Euler: 19 dependent launches) runs as ONE cluster kernel (chain_tcgen05.cu) in which a
   // cluster of 8 CTAs owns 128 rows for the whole chain.  NOVA_B200_CHAIN=0 restores the launch chain (bit-identical).
-  bool use_chain = false;  // v1 is slower than the launch chain (TMA operand ingest per stage); opt-in until it wins
+  bool use_chain = true;
   bool chained(int64_t rows) const {
-    return use_chain && cfg.dtype == NOVA_BF16 && !use_simt_gemm && !fused(rows) && chain::supported(cfg.width);
+    return use_chain && cfg.dtype == NOVA_BF16 && !use_simt_gemm && !fused(rows) && rows <= chain::profitable_rows(cfg.width);
   }
 };
 
@@ -333,7 +336,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
     cp.u1 = static_cast<bf16*>(w.u1); cp.u2 = static_cast<bf16*>(w.u2);
     cp.st = static_cast<const bf16*>(io.st_pre ? io.st_pre : w.st); cp.ldst = n_ada;
     cp.fc_params = h->b_fc1[0];  // b_fc1 | b_fc2 | gamma | beta per block, contiguous in the arena
-    cp.x_tok = io.x_tok; cp.x_rows = io.x_rows; cp.Wp = h->w_patch; cp.bp = h->b_patch;
+    cp.x_tok = io.x_tok; cp.x_rows = io.x_rows; cp.Wp = h->w_patch; cp.WpT = h->w_patchT; cp.bp = h->b_patch;
     cp.Wh = h->w_head; cp.bh = h->b_head; cp.v_out = io.v_out; cp.xt_out = io.xt_out; cp.dt = io.dt;
     static const bool want_timeline = std::getenv("NOVA_B200_CHAIN_TIMELINE") != nullptr;  // diagnostic only
     cp.timeline = chain::timeline_buffer(want_timeline);
@@ -343,7 +346,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   rw::RowParams p{};
   p.M = M; p.D = D; p.T = T;
   p.x_in = w.x; p.x_out = w.x; p.u = w.u2; p.st = io.st_pre ? io.st_pre : w.st; p.ldst = n_ada; p.h_out = w.h;
-  p.x_tok = io.x_tok; p.x_rows = io.x_rows; p.Wp = h->w_patch; p.bp = h->b_patch;
+  p.x_tok = io.x_tok; p.x_rows = io.x_rows; p.Wp = h->w_patch; p.WpT = h->w_patchT; p.bp = h->b_patch;
   p.Wh = h->w_head; p.bh = h->b_head;
   p.v_out = io.v_out; p.xt_in = io.x_tok; p.xt_out = io.xt_out; p.dt = io.dt;
   const int64_t final_off = static_cast<int64_t>(3) * depth * D;
@@ -675,7 +678,10 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
     cudaGetLastError();
   }
   if (const char* env_fork = std::getenv("NOVA_B200_FORK_ADA")) h->fork_ada = std::atoi(env_fork) != 0;
-  if (const char* env_fork_rows = std::getenv("NOVA_B200_FORK_ADA_ROWS")) h->fork_ada_rows = std::atoll(env_fork_rows);
+  if (const char* env_fork_rows = std::getenv("NOVA_B200_FORK_ADA_ROWS")) {
+    h->fork_ada_rows = std::atoll(env_fork_rows);
+    h->fork_rows_forced = true;
+  }
   if (h->capture_stream != nullptr && h->fork_ada) {
     if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

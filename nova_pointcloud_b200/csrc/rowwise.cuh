@@ -127,6 +127,7 @@ struct RowParams {
   const float* x_tok;  // [x_rows, T]
   int64_t x_rows;
   const float* Wp;     // [D, T] token-order patch-embed weight
+  const float* WpT;    // [T, D] its transpose: vector loads (same fmaf chain per feature: bias, then t = 0, 1, ..)
   const float* bp;     // [D]
   const void* u;       // [M, D]   fc2 output of the finished block (HAS_PREV)
   const void* st;      // [M, ldst] all AdaLN statistics of this step
@@ -221,17 +222,24 @@ __device__ __forceinline__ void row_body(const RowParams& p, const int64_t row, 
     const float* xt = p.x_tok + (row % p.x_rows) * p.T;
     AT* xout = static_cast<AT*>(p.x_out) + row * D;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int e = (i * 32 + lane) * 8;
+    for (int i = 0; i < VPL; ++i) load8(p.bp + (i * 32 + lane) * 8, x[i]);
+    for (int t = 0; t < p.T; ++t) {
+      const float xv = xt[t];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float acc = p.bp[e + j];
-        for (int t = 0; t < p.T; ++t) acc = fmaf(xt[t], p.Wp[(int64_t)(e + j) * p.T + t], acc);
-        x[i][j] = acc;
+      for (int i = 0; i < VPL; ++i) {
+        float w[8];
+        load8(p.WpT + (int64_t)t * D + (i * 32 + lane) * 8, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[i][j] = fmaf(xv, w[j], x[i][j]);
       }
-      if (OUT == 0) {
+    }
+    if (OUT == 0) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int e = (i * 32 + lane) * 8;
         store8(xout + e, x[i]);
-        load8(xout + e, x[i]);  // continue from the stored (rounded) residual, like every later block
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[i][j] = to_float(from_float<AT>(x[i][j]));  // continue from the stored (rounded) residual
       }
     }
   }
@@ -284,21 +292,36 @@ __device__ __forceinline__ void row_body(const RowParams& p, const int64_t row, 
   }
 
   if (OUT == 1) {
-    for (int t = 0; t < p.T; ++t) {
-      const float* w = p.Wh + (int64_t)t * D;
-      float acc = 0.f;
+    // velocity head: outputs in groups of 3 (T = 3 for xyz tokens) whose weight loads and warp reductions overlap;
+    // every output keeps its own fmaf chain and butterfly, so the values do not depend on the grouping
+    for (int t0 = 0; t0 < p.T; t0 += 3) {
+      float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        float wv[8];
-        load8(w + (i * 32 + lane) * 8, wv);
+      for (int g = 0; g < 3; ++g) {
+        if (t0 + g < p.T) {
+          const float* w = p.Wh + (int64_t)(t0 + g) * D;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(x[i][j], wv[j], acc);
+          for (int i = 0; i < VPL; ++i) {
+            float wv[8];
+            load8(w + (i * 32 + lane) * 8, wv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[g] = fmaf(x[i][j], wv[j], acc[g]);
+          }
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        const float v = acc + p.bh[t];
-        if (p.v_out) p.v_out[row * p.T + t] = v;
-        if (p.xt_out) p.xt_out[row * p.T + t] = __fadd_rn(__fmul_rn(v, p.dt), p.xt_in[row * p.T + t]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o);
+      }
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int t = t0 + g;
+        if (lane == g && t < p.T) {
+          const float v = acc[g] + p.bh[t];
+          if (p.v_out) p.v_out[row * p.T + t] = v;
+          if (p.xt_out) p.xt_out[row * p.T + t] = __fadd_rn(__fmul_rn(v, p.dt), p.xt_in[row * p.T + t]);
+        }
       }
     }
   }

@@ -25,6 +25,7 @@ def _head(depth, D, chain, T3=True):
 
     old = os.environ.get("NOVA_B200_CHAIN")
     os.environ["NOVA_B200_CHAIN"] = "1" if chain else "0"
+    os.environ["NOVA_B200_CHAIN_ROWS"] = "1000000"  # also above the row count where the library would switch back
     try:
         head = nb.synth.make_head(D, depth, dtype=torch.bfloat16, device="cuda", patch_size=1 if T3 else 2,
                                   image_dim=3 if T3 else 4)
