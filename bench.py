@@ -22,7 +22,12 @@ Printed JSON (one line, rank 0):
                         hoisted work not credited) / step time
   kernel_shares       : in-situ share of the step per kernel class
   gemm_alone          : the plain tcgen05 GEMM at M x 20D x D timed alone (burst regime)
-  cpu_baseline        : the CPU oracle (port of the reference's torch code) on a bounded sample
+  cpu_baseline        : the reference's own Transformer3DModel.denoise (baseline/_ref, copied by build() from
+                        /root/reference; the oracle port when that copy is absent) on a bounded sample, host cores
+  target_shape / strong_cfg3 / cfg4 / chamfer_sharded : the other BASELINE.json configs, at every --gpus N:
+                        NOVA-0.6B 2048-point shape (the >= 60 % target), cfg3 = 64 clouds TOTAL sharded over the
+                        ranks (strong scaling), cfg4 = NOVA-1.4B 32 x 2048 per GPU with its all-gather, cfg5 = 256
+                        Chamfer pairs sharded over the ranks
 """
 
 from __future__ import annotations
@@ -131,54 +136,154 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_baseline_run(width, points, sample_clouds, threads, repeats=1):
-    """Time the CPU oracle (port of the reference's DiffusionMLP + scheduler loop, fp32) on a bounded sample."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_runner(width, threads):
+    """(kind, fn): fn(z, noise) runs one 25-step denoise of the reference algorithm on the host cores, fp32.
+
+    kind == "reference": the reference's OWN modules (Transformer3DModel.denoise driving DiffusionMLP and
+    FlowMatchEulerDiscreteScheduler, transformer_3d.py:102-113), imported unmodified from baseline/_ref -- the copy
+    __graft_entry__.build() makes from /root/reference -- or from /root/reference itself where it is mounted.
+    kind == "port": oracle/loop.py, when neither exists."""
+    torch.set_num_threads(threads)
+    for root in (REF_DIR, "/root/reference"):
+        if os.path.isdir(os.path.join(root, "diffnext")):
+            os.environ["NOVA_REFERENCE_ROOT"] = root
+            break
+    from oracle import _reference_import as RI
+
+    RI.REFERENCE_ROOT = os.environ.get("NOVA_REFERENCE_ROOT", RI.REFERENCE_ROOT)
+    if RI.reference_available():
+        ref = RI.import_reference()
+        torch.manual_seed(1337)
+        head = ref.DiffusionMLP(DEPTH, width, width, patch_size=1, image_dim=3).eval()
+        model, _ = RI.reference_denoiser(ref, head, num_steps=S_STEPS)
+        gs = ref.GuidanceScaler(guidance_scale=1)
+
+        def run(z, noise):
+            with torch.no_grad():
+                return model.denoise(z, noise, gs)
+
+        return "reference", run
     from oracle import head as OH
     from oracle import loop as OL
 
-    torch.set_num_threads(threads)
     sd = OH.init_state_dict(DEPTH, width, width, 1, 3, seed=1337)
+
+    def run_port(z, noise):
+        with torch.no_grad():
+            return OL.denoise(sd, z, noise, num_steps=S_STEPS)
+
+    return "port", run_port
+
+
+def _cpu_inputs(width, points, clouds):
     g = torch.Generator().manual_seed(2024)
-    noise = torch.randn(sample_clouds, 3, points, 1, generator=g)
-    z = torch.randn(sample_clouds, points, width, generator=g)
-    with torch.no_grad():
-        OL.denoise(sd, z[:1, :64], noise[:1, :, :64], num_steps=2)  # warm the thread pool
-        best = float("inf")
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            OL.denoise(sd, z, noise, num_steps=S_STEPS)
-            best = min(best, time.perf_counter() - t0)
-    return sample_clouds / best, best
+    noise = torch.randn(clouds, 3, points, 1, generator=g)
+    z = torch.randn(clouds, points, width, generator=g)
+    return z, noise
+
+
+def cpu_baseline_run(width, points, sample_clouds, threads, repeats=1):
+    """Time the reference's denoise loop (fp32, host cores) on a bounded sample of `sample_clouds` clouds."""
+    kind, run = _reference_runner(width, threads)
+    z, noise = _cpu_inputs(width, points, sample_clouds)
+    run(z[:1, :64], noise[:1, :, :64])  # warm the thread pool
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run(z, noise)
+        best = min(best, time.perf_counter() - t0)
+    return sample_clouds / best, best, kind
+
+
+def cpu_cfg1(threads):
+    """BASELINE.json configs[0] exactly: D = 1024, 4 clouds x 1024 points, 25 steps, fp32; 1 warm-up + best of 3."""
+    kind, run = _reference_runner(1024, threads)
+    z, noise = _cpu_inputs(1024, 1024, 4)
+    run(z, noise)
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        run(z, noise)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": 4 / best, "unit": "clouds/s", "seconds_best_of_3": best, "kind": kind, "cores": threads,
+            "token_steps_per_s": 4 * 1024 * S_STEPS / best,
+            "what": "BASELINE configs[0]: DiffusionMLP(6,1024,1024) + flow-match Euler, 4 x 1024 points, 25 steps, fp32"}
+
+
+def cpu_chamfer(threads):
+    """Chamfer on the host: variant A per pair with scipy cdist float64 (demo.py:44-53, 1 core) and batched
+    torch.cdist fp32 on all cores (train_newloss.py:337, test_optimize.py:366), 16 pairs of 2048 x 2048."""
+    import numpy as np
+    from oracle import chamfer as OC
+
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(11)
+    a = torch.rand(16, 2048, 3, generator=g) * 2 - 1
+    b = torch.rand(16, 2048, 3, generator=g) * 2 - 1
+    a_np, b_np = a.numpy(), b.numpy()
+    t0 = time.perf_counter()
+    for i in range(4):
+        OC.chamfer_a(a_np[i], b_np[i])
+    scipy_s = (time.perf_counter() - t0) / 4
+    torch.cdist(a[:2], b[:2])
+    t0 = time.perf_counter()
+    d = torch.cdist(a, b)
+    _ = d.min(dim=2).values.mean(dim=1) + d.min(dim=1).values.mean(dim=1)
+    cdist_s = (time.perf_counter() - t0) / 16
+    return {"scipy_float64_1core_pairs_per_s": 1.0 / scipy_s, "torch_cdist_fp32_allcores_pairs_per_s": 1.0 / cdist_s,
+            "cores": threads, "sample": "4 pairs (scipy) / 16 pairs (torch.cdist) of 2048 x 2048 points"}
+
+
+def bench_config(args, wl, world):
+    D, N, B = wl["width"], wl["points"], wl["batch"]
+    return {"workload": args.workload + ": " + wl["desc"], "points": N, "width": D, "depth": DEPTH,
+            "diffusion_steps": S_STEPS, "clouds_per_gpu": B, "rows_per_head_call": B * N,
+            "parallelism": f"dp{world} (clouds sharded, one all-gather of outputs)",
+            "l2": "inputs larger than L2 (126 MB): every [M, D] bf16 activation is "
+                  f"{B * N * D * 2 / 1e6:.0f} MB and a diffusion step streams ~85 of them "
+                  f"({85 * B * N * D * 2 / 1e9:.1f} GB) through HBM; weights {32 * D * D * 2 / 1e6:.0f} MB stay L2-resident"}
 
 
 def run_reference_arm(args, wl):
-    """--impl reference: the reference's own algorithm on the host cores (oracle port: the reference is
-    Python/torch and cannot travel to the GPU box; oracle/ restates it call for call)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, on this arm's
+    config / metric / unit; every step is a bounded sample (2 clouds) of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_clouds = 1
-    vals = []
+    sample_clouds = 2
+    vals, kind = [], "port"
     for i in range(args.warmup + args.steps):
-        v, secs = cpu_baseline_run(wl["width"], wl["points"], sample_clouds, threads)
+        v, secs, kind = cpu_baseline_run(wl["width"], wl["points"], sample_clouds, threads)
         if i >= args.warmup:
             vals.append((v, secs))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(s for _, s in vals) / len(vals)
+    sample = (f"{sample_clouds} clouds x {wl['points']} tokens x {S_STEPS} steps per step, fp32, "
+              + ("the reference's own Transformer3DModel.denoise + DiffusionMLP + FlowMatchEulerDiscreteScheduler "
+                 "(baseline/_ref, unmodified)" if kind == "reference" else "oracle/loop.py denoise (port: no reference copy present)")
+              + "; the CPU is throughput-flat in the number of clouds")
     line = {
         "impl": "reference", "metric": "point_clouds_per_sec", "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "points": wl["points"], "width": wl["width"],
-                   "diffusion_steps": S_STEPS, "clouds_per_step": sample_clouds},
+        "config": bench_config(args, wl, args.gpus),
         "head_tokens_per_s": value * wl["points"],
-        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_clouds} cloud x {wl['points']} tokens x {S_STEPS} steps per step, fp32, "
-                                   f"oracle/loop.py denoise (reference algorithm, condition projection not hoisted)"},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["cfg1"] = cpu_cfg1(threads)
+    except Exception as e:  # report, never hide
+        line["cfg1"] = {"error": str(e)[:300]}
+    try:
+        line["chamfer_cpu"] = cpu_chamfer(threads)
+    except Exception as e:
+        line["chamfer_cpu"] = {"error": str(e)[:300]}
     print(json.dumps(line), flush=True)
 
 
@@ -240,8 +345,10 @@ def main():
     ap.add_argument("--impl", default="nova", choices=["nova", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the set-by-set and Chamfer legs")
-    ap.add_argument("--compile-bar", action="store_true",
-                    help="also time the reference algorithm under torch.compile (adds ~1-2 min of inductor compile time)")
+    ap.add_argument("--no-compile-bar", action="store_true",
+                    help="skip the torch.compile comparator (the inductor build of one diffusion step takes ~1 min)")
+    ap.add_argument("--no-north-star", action="store_true",
+                    help="skip the other BASELINE.json configs (target_shape, strong_cfg3, cfg4, chamfer_sharded)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -357,6 +464,103 @@ def main():
         del A, W, bias
     except Exception as e:  # report, never hide
         gemm = {"error": str(e)[:300]}
+
+    # ---- the other BASELINE.json configs, on every rank (sharded), at every --gpus N
+    north = {}
+    if not args.no_north_star:
+        def sharded_leg(width, points, clouds_local, clouds_total, steps=3, warmup=3):
+            """One data-parallel sampling leg: this rank's shard + the all-gather, CUDA events, max over ranks."""
+            hd = nb.synth.make_head(width, DEPTH, dtype=torch.bfloat16, device=dev)
+            n_d, zz = nb.synth.make_inputs(max(clouds_local, 1), points, width, seed=4242 + rank, dtype=torch.bfloat16, device=dev)
+            n_d, zz = n_d[:clouds_local], zz[:clouds_local]
+
+            def one():
+                if clouds_local > 0:
+                    local = nb.denoise(hd, sched, zz, n_d)
+                else:  # more ranks than clouds: this rank only takes part in the collective
+                    local = torch.empty(0, points, T, device=dev)
+                return nb.gather_shards(local, clouds_total)
+
+            ms_leg, launches_leg, clk = timed(one, steps, warmup)
+            ops.profile_enable(True)
+            one()
+            torch.cuda.synchronize()
+            pr = ops.profile_read()
+            ops.profile_enable(False)
+            del hd, n_d, zz
+            return ms_leg, launches_leg, clk, pr
+
+        def leg_record(width, points, clouds_local, clouds_total, ms_leg, pr, clk, what):
+            fl = algorithmic_flops(width, max(clouds_local, 0) * points)
+            tf_leg = fl / (ms_leg * 1e-3) / 1e12
+            ada_ms_, ada_n_ = pr["gemm_ada"]
+            n_ada_ = (3 * DEPTH + 2) * width
+            ada_tf_ = (2.0 * clouds_local * points * n_ada_ * width * S_STEPS / max(ada_n_, 1)) / (ada_ms_ / max(ada_n_, 1) * 1e-3) / 1e12 if ada_n_ else 0.0
+            tot = sum(v[0] for v in pr.values()) or 1.0
+            return {"value": clouds_total / (ms_leg * 1e-3), "unit": "clouds/s", "ms_per_pass": ms_leg, "n_gpus": world,
+                    "clouds_total": clouds_total, "clouds_this_gpu": clouds_local, "points": points, "width": width,
+                    "rows_per_head_call": clouds_local * points, "what": what,
+                    "step_roofline": {"bound": "tensor", "achieved": tf_leg, "peak": pk["sustained"], "unit": "TFLOP/s",
+                                      "frac": tf_leg / pk["sustained"], "frac_of_burst": tf_leg / pk["burst"]},
+                    "roofline": {"bound": "tensor", "achieved": ada_tf_, "peak": pk["sustained"], "unit": "TFLOP/s",
+                                 "frac": ada_tf_ / pk["sustained"], "frac_of_burst": ada_tf_ / pk["burst"],
+                                 "kernel": "AdaLN statistics GEMM, in situ (rank 0)", "launches_timed": ada_n_},
+                    "kernel_shares": {k: round(v[0] / tot, 4) for k, v in pr.items() if v[1]},
+                    "clocks": clk}
+
+        try:  # the shape the >= 60 % target is stated on: NOVA-0.6B head, 2048 points, 32 clouds per GPU (weak)
+            m_, _, c_, pr_ = sharded_leg(1024, 2048, 32, 32 * world)
+            north["target_shape"] = leg_record(1024, 2048, 32, 32 * world, m_, pr_, c_,
+                                               "NOVA-0.6B (mlp_d6w1024) 2048-point sampling, 32 clouds per GPU, bf16, one all-gather")
+        except Exception as e:  # report, never hide
+            north["target_shape"] = {"error": str(e)[:300]}
+        try:  # BASELINE configs[2]: 64 clouds TOTAL, 1024 points, D = 1024, sharded over the ranks (strong scaling)
+            lo, hi = nb.shard_range(64, rank, world)
+            m_, _, c_, pr_ = sharded_leg(1024, 1024, hi - lo, 64)
+            north["strong_cfg3"] = leg_record(1024, 1024, hi - lo, 64, m_, pr_, c_,
+                                              "BASELINE configs[2]: NOVA-0.6B 1024-point sampling, batch 64 TOTAL sharded over "
+                                              "the ranks (strong scaling: compare value across --gpus 1/2/4/8)")
+            north["strong_cfg3"]["scaling"] = "strong"
+        except Exception as e:
+            north["strong_cfg3"] = {"error": str(e)[:300]}
+        try:  # BASELINE configs[3]: NOVA-1.4B, 2048 points, 32 clouds per GPU (= 256 on 8 GPUs), all-gather of (B,2048,3) fp32
+            m_, _, c_, pr_ = sharded_leg(1536, 2048, 32, 32 * world, steps=2)
+            north["cfg4"] = leg_record(1536, 2048, 32, 32 * world, m_, pr_, c_,
+                                       "BASELINE configs[3]: NOVA-1.4B (mlp_d6w1536) 2048-point sampling, 32 clouds per GPU "
+                                       "(batch 256 on 8 GPUs), NCCL all-gather of the outputs inside the timed region")
+            north["cfg4"]["allgather_bytes"] = 32 * world * 2048 * 3 * 4
+        except Exception as e:
+            north["cfg4"] = {"error": str(e)[:300]}
+        try:  # BASELINE configs[4]: Chamfer, 256 pairs of 2048 x 2048 in total, sharded over the ranks
+            Bc, Nc = 256, 2048
+            lo, hi = nb.shard_range(Bc, rank, world)
+            gc = torch.Generator(device=dev).manual_seed(11 + rank)
+            pa = torch.rand(hi - lo, Nc, 3, device=dev, generator=gc) * 2 - 1
+            pb = torch.rand(hi - lo, Nc, 3, device=dev, generator=gc) * 2 - 1
+
+            def chamfer_pass():
+                cd = nb.chamfer_distance(pa, pb).float().unsqueeze(-1).unsqueeze(-1)  # (b,1,1): per-pair Chamfer A
+                return nb.gather_shards(cd, Bc)
+
+            cms, _, _ = timed(chamfer_pass, 10, 3)
+            pair_evals = 2.0 * Bc * Nc * Nc  # directed
+            # fp32 issue bound: >= 8 thread instructions per undirected pair (3 sub, 3 mul/fma, 2 min); the chip issues
+            # 148 SMs x 4 schedulers x 32 lanes per clock at the maximum SM clock
+            issue_peak = 148 * 4 * 32 * 1.965e9 / 8.0 * 2.0  # directed pair evaluations per second
+            north["chamfer_sharded"] = {
+                "value": Bc / (cms * 1e-3), "unit": "cloud pairs/s", "ms": cms, "pairs_total": Bc, "pairs_this_gpu": hi - lo,
+                "n_gpus": world, "points": Nc, "pair_evals_per_s": pair_evals / (cms * 1e-3),
+                "what": "BASELINE configs[4]: Chamfer A of 256 x (2048 vs 2048), pairs sharded over the ranks, one all-gather "
+                        "of the per-pair distances; timed through the public chamfer_distance call",
+                "roofline": {"bound": "fp32_issue", "achieved": pair_evals / (cms * 1e-3) / 1e12, "peak": issue_peak * world / 1e12,
+                             "unit": "T directed pair-evals/s", "frac": pair_evals / (cms * 1e-3) / (issue_peak * world),
+                             "note": "algorithmically HBM-trivial (16.8 MB per 2.1 G pair evaluations); the bound is fp32 "
+                                     "instruction issue: 8 thread instructions per undirected pair, 148 x 4 x 32 lanes per clock "
+                                     "at 1.965 GHz; includes the Python-side reductions and the all-gather of this call"}}
+            del pa, pb
+        except Exception as e:
+            north["chamfer_sharded"] = {"error": str(e)[:300]}
+        barrier()
 
     # ---- secondary legs (rank 0, reported beside the headline; bounded to ~2 s)
     extras = {}
@@ -548,7 +752,7 @@ def main():
                 "rel_max_diff_of_outputs": float((ours - ref_out).abs().max() / ref_out.abs().max())}
         except Exception as e:
             extras["library_bar"] = {"error": str(e)[:300]}
-        if args.compile_bar:
+        if not args.no_compile_bar:
             try:
                 with torch.no_grad():
                     for _ in range(2):  # compile + settle
@@ -591,12 +795,7 @@ def main():
             "metric": "point_clouds_per_sec", "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "points": N, "width": D, "depth": DEPTH,
-                       "diffusion_steps": S_STEPS, "clouds_per_gpu": B, "rows_per_head_call": B * N,
-                       "parallelism": f"dp{world} (clouds sharded, one all-gather of outputs)",
-                       "l2": "inputs larger than L2 (126 MB): every [M, D] bf16 activation is "
-                             f"{B * N * D * 2 / 1e6:.0f} MB and a diffusion step streams ~85 of them "
-                             f"({85 * B * N * D * 2 / 1e9:.1f} GB) through HBM; weights {32 * D * D * 2 / 1e6:.0f} MB stay L2-resident"},
+            "config": bench_config(args, wl, world),
             "head_tokens_per_s": value * N,
             "token_steps_per_s": value * N * S_STEPS,
             "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e,
@@ -620,15 +819,18 @@ def main():
             "kernel_shares": shares,
             "gemm_alone": gemm,
         }
+        line.update(north)
         line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            sample_clouds = 1
-            v, secs = cpu_baseline_run(D, N, sample_clouds, threads)
+            sample_clouds = 2
+            v, secs, kind = cpu_baseline_run(D, N, sample_clouds, threads)
             line["cpu_baseline"] = {
-                "value": v, "unit": "clouds/s", "cores": threads, "kind": "port", "seconds": secs,
-                "sample": f"{sample_clouds} cloud x {N} tokens x {S_STEPS} steps, fp32, oracle/loop.py denoise "
-                          "(the reference's algorithm, condition projection not hoisted)"}
+                "value": v, "unit": "clouds/s", "cores": threads, "kind": kind, "seconds": secs,
+                "sample": f"{sample_clouds} clouds x {N} tokens x {S_STEPS} steps, fp32, "
+                          + ("the reference's own Transformer3DModel.denoise (baseline/_ref, unmodified)" if kind == "reference"
+                             else "oracle/loop.py denoise (port: no reference copy present)")
+                          + ", condition projection not hoisted"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define NOVA_B200_ABI_VERSION 1
+#define NOVA_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NOVA_API __attribute__((visibility("default")))
@@ -76,11 +76,16 @@ typedef struct nova_head_config {
   int32_t dtype;      /* nova_dtype: arithmetic type of the handle */
 } nova_head_config;
 
-/* guidance for nova_head_sample (GuidanceScaler two-pass form) */
+/* guidance for nova_head_sample (GuidanceScaler, diffnext/models/guidance_scaler.py:74-87) */
 typedef struct nova_guidance {
   float scale;  /* <= 1: off. > 1: z holds [cond; uncond] (2x rows), v = vu + (vc - vu)*scale */
   float trunc;  /* > 0: guidance is switched off once timestep < trunc (guidance_scaler.py:59-65) */
   float renorm; /* < 1: v *= clamp(|vc| / |v|, renorm, 1), norms per cloud (guidance_scaler.py:67-72) */
+  /* three-pass forms (:78-85): z holds [cond; uncond; third] (3x rows).  At most one is used, image first:
+   *   image_scale > 0:          v = renorm(vu + (vc - v3)*scale) + (v3 - vu)*image_scale      (third = image-only pass)
+   *   spatiotemporal_scale > 0: v = renorm(vu + (vc - vu)*scale) + (vc - v3)*spatiotemporal_scale  (third = perturbed) */
+  float image_scale;
+  float spatiotemporal_scale;
 } nova_guidance;
 
 NOVA_API const char* nova_last_error(void);
@@ -121,8 +126,8 @@ NOVA_API int nova_head_forward(const nova_head_t* h, const float* x_tok, const f
  * The fused sampling loop (denoise): S Euler steps of the head with the condition
  * projection hoisted out of the loop and the latent kept in fp32.
  *   noise_tok [Bx, N, T] fp32   initial latent, token layout
- *   z         [B, N, Dc]        B = Bx (no guidance) or 2*Bx ([cond; uncond])
- *   pred_ids  [B, n] int64 or NULL (rows of the second half must repeat the first half)
+ *   z         [B, N, Dc]        B = Bx (no guidance), 2*Bx ([cond; uncond]) or 3*Bx (three-pass guidance)
+ *   pred_ids  [B, n] int64 or NULL (rows of the later passes must repeat the first Bx rows)
  *   timesteps [S] host fp32, sigmas [S+1] host fp64  (the scheduler's own values)
  *   x_out     [Bx, N, T] fp32   patchify(x_S).  Tokens outside pred_ids follow the
  *                               reference's x <- x + dt*x recurrence (two roundings per step).
@@ -192,6 +197,22 @@ NOVA_API int nova_add_noise(const float* x, const float* noise, const float* sig
 NOVA_API int nova_flow_loss(const float* pred, const float* noise, const float* x, const float* weight,
                             int64_t tokens, int32_t T, float* loss_tok, float* scratch2, void* stream);
 
+/*
+ * Multi-GPU: clouds are sharded data-parallel over one process per GPU, weights replicated, no collective inside the
+ * denoise loop; the ONE collective of the path is an all-gather of the generated points after the last Euler step.
+ * NCCL is resolved at first use (dlopen of libnccl.so.2; inside a PyTorch process the already-loaded NCCL is used).
+ *
+ * nova_comm_unique_id:  rank 0 fills a 128-byte id and ships it to the other ranks by any means (file, socket, MPI).
+ * nova_comm_init_rank:  every rank, with its own device current (cudaSetDevice), joins the communicator.
+ * nova_allgather:       recv [world_size * count_bytes] <- every rank's send [count_bytes], in rank order, on `stream`
+ *                       (thin ncclAllGather; in-place when send == recv + rank * count_bytes).
+ */
+typedef struct nova_comm nova_comm_t; /* opaque (an ncclComm_t) */
+NOVA_API int nova_comm_unique_id(char* out128);
+NOVA_API int nova_comm_init_rank(const char* id128, int32_t world_size, int32_t rank, nova_comm_t** out);
+NOVA_API int nova_comm_destroy(nova_comm_t* comm);
+NOVA_API int nova_allgather(nova_comm_t* comm, const void* send, void* recv, int64_t count_bytes, void* stream);
+
 /* Kernels launched by this library in the calling thread since the last reset (for bench.py). */
 NOVA_API int64_t nova_launch_count(void);
 NOVA_API void nova_launch_count_reset(void);
@@ -231,8 +252,14 @@ NOVA_API int nova_debug_adaln_gemm(const void* A, const void* W, const float* bi
  */
 NOVA_API int nova_debug_chain_timeline(int64_t* out, int32_t n);
 
-/* Test hook: the 4 host-mapped words a tcgen05 kernel writes before trapping on a barrier timeout. */
+/*
+ * The 4 host-mapped status words of the library: [0..2] are written by a tcgen05 kernel before it traps on a barrier
+ * timeout (0xDEAD0000 | code, block, parity); [3] becomes 0xBAD1D5 when a gather / scatter kernel met a pred_id outside
+ * [0, N).  Such an id is never used for indexing (the row reads token 0 / is not written), so nothing is accessed out
+ * of bounds; the reference's gather raises there, a C caller checks this word after synchronising.
+ */
 NOVA_API int nova_debug_words(uint32_t* out4);
+NOVA_API int nova_debug_words_clear(void);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ EXPORTS = [
     "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
     "nova_head_sample", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
-    "nova_debug_chain_timeline", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_add_noise", "nova_flow_loss",
+    "nova_debug_chain_timeline", "nova_debug_words_clear", "nova_comm_unique_id", "nova_comm_init_rank",
+    "nova_comm_destroy", "nova_allgather", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_add_noise", "nova_flow_loss",
 ]
 
 
@@ -31,7 +32,8 @@ class HeadConfig(C.Structure):
 
 
 class Guidance(C.Structure):
-    _fields_ = [("scale", C.c_float), ("trunc", C.c_float), ("renorm", C.c_float)]
+    _fields_ = [("scale", C.c_float), ("trunc", C.c_float), ("renorm", C.c_float), ("image_scale", C.c_float),
+                ("spatiotemporal_scale", C.c_float)]
 
 
 class NovaError(RuntimeError):
@@ -91,6 +93,16 @@ def _declare(lib):
     lib.nova_debug_adaln_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
     lib.nova_debug_chain_timeline.restype = C.c_int
     lib.nova_debug_chain_timeline.argtypes = [C.POINTER(C.c_int64), i32]
+    lib.nova_comm_unique_id.restype = C.c_int
+    lib.nova_comm_unique_id.argtypes = [C.c_char_p]
+    lib.nova_comm_init_rank.restype = C.c_int
+    lib.nova_comm_init_rank.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
+    lib.nova_comm_destroy.restype = C.c_int
+    lib.nova_comm_destroy.argtypes = [vp]
+    lib.nova_allgather.restype = C.c_int
+    lib.nova_allgather.argtypes = [vp, vp, vp, i64, vp]
+    lib.nova_debug_words_clear.restype = C.c_int
+    lib.nova_debug_words_clear.argtypes = []
     lib.nova_debug_words.restype = C.c_int
     lib.nova_debug_words.argtypes = [C.POINTER(C.c_uint32)]
 
@@ -111,7 +123,7 @@ def lib():
             except OSError as e:  # fail loudly: there is no other implementation
                 raise NovaError(f"cannot load {LIB_PATH}: {e}") from e
             _declare(handle)
-            if handle.nova_abi_version() != 1:
+            if handle.nova_abi_version() != 2:
                 raise NovaError("libnova_b200.so ABI version mismatch; rebuild with python -m nova_pointcloud_b200.build")
             _lib = handle
     return _lib
@@ -127,3 +139,14 @@ def debug_words():
     arr = (C.c_uint32 * 4)()
     lib().nova_debug_words(arr)
     return [int(v) for v in arr]
+
+
+BAD_IDS_FLAG = 0xBAD1D5
+
+
+def bad_pred_ids_seen(clear: bool = False) -> bool:
+    """True if a gather / scatter kernel met a pred_id outside [0, N) since the last clear (synchronise first)."""
+    seen = debug_words()[3] == BAD_IDS_FLAG
+    if clear:
+        lib().nova_debug_words_clear()
+    return seen

@@ -348,15 +348,8 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
 // ---------------------------------------------------------------- host side
 template <int VPL, int ROWS>
 int set_attrs() {
-  static bool done[64] = {};  // per device: the attribute belongs to the function ON a device
-  int dev = 0;
-  NOVA_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !done[dev]) {
-    NOVA_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<VPL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ChainPlan<VPL, ROWS>::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) done[dev] = true;
-  }
-  return NOVA_OK;
+  static std::atomic<unsigned long long> done{0ull};  // one bit per device
+  return ensure_smem_attr(reinterpret_cast<const void*>(chain_kernel<VPL, ROWS>), ChainPlan<VPL, ROWS>::SMEM_BYTES, &done);
 }
 
 template <int VPL, int ROWS>

@@ -3,6 +3,8 @@
 
 #include <cuda.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace nova {
@@ -18,7 +20,9 @@ int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K,
 // The same encoding serves the output: [M, N] row-major, box = {64 columns, 32 rows} per TMA store.
 uint32_t* debug_word();  // host-mapped [4] words written on barrier timeout (device pointer)
 extern uint32_t* g_debug_host;  // the same words, host pointer
-int num_sms();
+int num_sms();  // SM count of the current device
+// sets cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device); thread-safe
+int ensure_smem_attr(const void* func, int bytes, std::atomic<unsigned long long>* done_mask);
 int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
 int tile_columns_override();   // env NOVA_B200_TILE_N=64|128|256 forces the tile columns of the plain GEMMs (tests)
 

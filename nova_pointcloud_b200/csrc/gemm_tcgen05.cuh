@@ -551,12 +551,8 @@ template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false) {
   using P = Plan<CG, BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    NOVA_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, CG, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         P::SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0ull};  // one bit per device
+  NOVA_PROPAGATE(ensure_smem_attr(reinterpret_cast<const void*>(gemm_kernel<EPI, CG, BN>), P::SMEM_BYTES, &attr_done));
   CUtensorMap ta, tb, tc_, tc2;
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
   NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, P::B_ROWS));

@@ -35,7 +35,7 @@ using namespace nova;
 
 namespace {
 constexpr int MAX_DEPTH = 16;
-constexpr int MAX_STEPS = 256;
+constexpr int MAX_STEPS = rw::MAX_STEPS;
 }  // namespace
 
 // One captured S-step loop of nova_head_sample: everything in it touches only the caller's workspace, so a
@@ -128,6 +128,13 @@ struct nova_head {
 
 namespace {
 
+// Host-mapped word [3] of the library's debug words: set to 0xBAD1D5 by the gather / scatter kernels when a pred_id is
+// outside [0, N) (the id is then not used for indexing: nothing is read or written out of bounds).  nova_debug_words.
+uint32_t* bad_ids_word() {
+  uint32_t* d = tc::debug_word();
+  return d ? d + 3 : nullptr;
+}
+
 struct Carver {
   uint8_t* base;
   size_t off = 0;
@@ -203,9 +210,7 @@ int launch_row_any<bf16>(const rw::RowParams& p, bool has_prev, int out, cudaStr
   return rw::launch_row_bf16(p, has_prev, out, s);
 }
 
-struct TimeList {
-  float v[MAX_STEPS];
-};
+using TimeList = rw::StepList;
 __global__ void fill_times_kernel(float* dst, const TimeList tl, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = tl.v[i];
@@ -386,8 +391,8 @@ int check_call(const nova_head* h, int64_t B, int64_t Bx, int64_t N, int64_t n, 
   }
   NOVA_REQUIRE(B >= 0 && N >= 0 && n >= 0 && n <= N, "%s: bad sizes B=%lld N=%lld n=%lld", who, (long long)B,
                (long long)N, (long long)n);
-  NOVA_REQUIRE(Bx == B || 2 * Bx == B, "%s: x batch %lld must equal or halve z batch %lld", who, (long long)Bx,
-               (long long)B);
+  NOVA_REQUIRE(Bx == B || 2 * Bx == B || 3 * Bx == B, "%s: z batch %lld must be 1, 2 or 3 times the x batch %lld", who,
+               (long long)B, (long long)Bx);
   NOVA_REQUIRE(B * n < (1ll << 31), "%s: too many rows", who);
   const size_t need = nova_head_workspace_bytes(h, B * n, steps);
   if (B * n > 0 && (ws == nullptr || ws_bytes < need)) {
@@ -413,13 +418,14 @@ int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_p
   if (pred_ids) {
     const int64_t nvec = M * (Dc / 8);
     rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, pred_ids, static_cast<AT*>(w.zsel), B, N,
-                                                                           n, Dc);
+                                                                           n, Dc, bad_ids_word());
     NOVA_CHECK_LAUNCH();
     z_rows = static_cast<const AT*>(w.zsel);
   }
   const float* x_rows = x_tok;
   if (pred_ids || Bx != B) {
-    rw::gather_tok_kernel<<<(unsigned)ceil_div(M * T, 256), 256, 0, s>>>(x_tok, pred_ids, w.xsel, B, Bx, N, n, T);
+    rw::gather_tok_kernel<<<(unsigned)ceil_div(M * T, 256), 256, 0, s>>>(x_tok, pred_ids, w.xsel, B, Bx, N, n, T,
+                                                                         bad_ids_word());
     NOVA_CHECK_LAUNCH();
     x_rows = w.xsel;
   }
@@ -436,21 +442,22 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   const int T = h->T(), Dc = h->Dc();
   const int64_t M = B * n, Mx = Bx * n;
   const bool guided = g != nullptr && g->scale > 1.0f;
+  // three-pass guidance (guidance_scaler.py:78-85): image first, as the reference's scale() tests it first
+  const int gmode = !guided ? 0 : g->image_scale > 0.f ? 1 : g->spatiotemporal_scale > 0.f ? 2 : 0;
+  const float gscale3 = gmode == 1 ? g->image_scale : gmode == 2 ? g->spatiotemporal_scale : 0.f;
   TimeList dts{};
   for (int i = 0; i < S; ++i) dts.v[i] = static_cast<float>(sigmas[i + 1] - sigmas[i]);
   const bool has_unpred = pred_ids != nullptr && n < N;
-  auto unpredicted = [&](const Workspace& wk, const float* ratios) -> int {
-    // tokens outside the set: x <- (ratio*x)*dt + x per step (ratio == 1 without guidance renorm)
+  auto unpredicted = [&](const float* ratios) -> int {
+    // tokens outside the set: x <- (ratio*x)*dt + x per step (ratio == 1 without guidance renorm); the step sizes
+    // travel by value, so the empty-set call (M == 0, no workspace required) touches no scratch memory
     const int64_t numel = Bx * N * T;
-    fill_times_kernel<<<1, MAX_STEPS, 0, s>>>(wk.tdev, dts, S);
-    NOVA_CHECK_LAUNCH();
-    rw::unpredicted_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, s>>>(noise_tok, x_out, numel, N * T, Bx, wk.tdev,
-                                                                         ratios, S);
+    rw::unpredicted_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, s>>>(noise_tok, x_out, numel, N * T, Bx, dts, ratios, S);
     NOVA_CHECK_LAUNCH();
     return NOVA_OK;
   };
   if (M == 0) {
-    if (has_unpred) NOVA_PROPAGATE(unpredicted(carve(h, ws, M, S), nullptr));
+    if (has_unpred) NOVA_PROPAGATE(unpredicted(nullptr));
     return NOVA_OK;
   }
   Workspace w = carve(h, ws, M, S);
@@ -459,12 +466,13 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   if (pred_ids) {
     const int64_t nvec = M * (Dc / 8);
     rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, pred_ids, static_cast<AT*>(w.zsel), B, N,
-                                                                           n, Dc);
+                                                                           n, Dc, bad_ids_word());
     NOVA_CHECK_LAUNCH();
     z_rows = static_cast<const AT*>(w.zsel);
   }
   // latent of the selected tokens, fp32, resident in the workspace for all S steps
-  rw::gather_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(noise_tok, pred_ids, w.xsel, Bx, Bx, N, n, T);
+  rw::gather_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(noise_tok, pred_ids, w.xsel, Bx, Bx, N, n, T,
+                                                                        bad_ids_word());
   NOVA_CHECK_LAUNCH();
   TimeList tl{};
   for (int i = 0; i < S; ++i) tl.v[i] = timesteps[i];
@@ -520,7 +528,7 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
         NOVA_PROPAGATE(head_step<AT>(h, w, io, st));
         launch_pdl(rw::cfg_euler_kernel, dim3((unsigned)Bx), dim3(256), 0, st, w.v, w.xsel, Bx, n * T, g->scale,
                    g->renorm, io.dt, renorm_extra ? extra_sumsq : nullptr,
-                   renorm_extra ? ratios + (int64_t)i * Bx : nullptr);
+                   renorm_extra ? ratios + (int64_t)i * Bx : nullptr, gmode, gscale3);
         NOVA_CHECK_LAUNCH();
       } else {
         io.M = Mx;  // no guidance (or truncated): only the conditional rows run; Euler fused into the last row kernel
@@ -545,7 +553,8 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
     };
     mix(timesteps, sizeof(float) * S);
     mix(dts.v, sizeof(float) * S);
-    const float gparams[3] = {guided ? g->scale : 0.f, guided ? g->trunc : 0.f, guided ? g->renorm : 1.f};
+    const float gparams[5] = {guided ? g->scale : 0.f, guided ? g->trunc : 0.f, guided ? g->renorm : 1.f,
+                              static_cast<float>(gmode), gscale3};
     mix(gparams, sizeof(gparams));
     const int64_t shape[6] = {B, Bx, N, n, (int64_t)renorm_extra, (int64_t)T};
     mix(shape, sizeof(shape));
@@ -601,8 +610,9 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
       count_launch((int)captured);
     }
   }
-  if (has_unpred) NOVA_PROPAGATE(unpredicted(w, renorm_extra ? ratios : nullptr));
-  rw::scatter_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(w.xsel, pred_ids, x_out, Bx, N, n, T);
+  if (has_unpred) NOVA_PROPAGATE(unpredicted(renorm_extra ? ratios : nullptr));
+  rw::scatter_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(w.xsel, pred_ids, x_out, Bx, N, n, T,
+                                                                         bad_ids_word());
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
@@ -900,8 +910,10 @@ extern "C" int nova_head_sample(const nova_head_t* h, const float* noise_tok, co
   NOVA_PROPAGATE(check_call(h, B, Bx, N, n, workspace, workspace_bytes, num_steps, "nova_head_sample"));
   NOVA_REQUIRE(pred_ids != nullptr || n == N, "nova_head_sample: n must equal N without pred_ids");
   const bool guided = guidance != nullptr && guidance->scale > 1.0f;
-  NOVA_REQUIRE(guided ? (B == 2 * Bx) : (B == Bx), "nova_head_sample: z batch %lld does not match guidance (x batch %lld)",
-               (long long)B, (long long)Bx);
+  const bool third = guided && (guidance->image_scale > 0.f || guidance->spatiotemporal_scale > 0.f);
+  NOVA_REQUIRE(B == (guided ? (third ? 3 : 2) : 1) * Bx,
+               "nova_head_sample: z batch %lld does not match guidance (x batch %lld, %d pass(es))", (long long)B,
+               (long long)Bx, guided ? (third ? 3 : 2) : 1);
   if (Bx * N == 0) return NOVA_OK;
   NOVA_REQUIRE(noise_tok && z && x_out && (num_steps == 0 || (timesteps_host && sigmas_host)),
                "nova_head_sample: null pointer");

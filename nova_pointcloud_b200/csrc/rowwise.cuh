@@ -17,6 +17,10 @@ namespace rw {
 constexpr int WARPS = 8;           // rows per CTA
 constexpr int THREADS = WARPS * 32;
 constexpr int MAX_T = 64;
+constexpr int MAX_STEPS = 256;
+struct StepList {
+  float v[MAX_STEPS];
+};
 
 // ------------------------------------------------------------------ time embedding
 // hidden[r, d] = silu(b1[d] + sum_k emb(t_r)[k] * W1[d, k]),  emb = [cos(t f), sin(t f)], 256 wide
@@ -66,26 +70,35 @@ temb_fc2_kernel(const float* __restrict__ hidden, int R, const float* __restrict
 // dst[b*n + j, :] = src[b*N + ids[b*n + j], :]   (W elements per row, 8 per thread)
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ src, const int64_t* __restrict__ ids, T* __restrict__ dst,
-                                   int64_t B, int64_t N, int64_t n, int W) {
+                                   int64_t B, int64_t N, int64_t n, int W, uint32_t* bad_ids) {
   const int64_t vec_per_row = W / 8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n * vec_per_row) return;
   const int64_t row = i / vec_per_row, v = i % vec_per_row;
   const int64_t b = row / n;
-  const int64_t srow = b * N + (ids ? ids[row] : row % n);
+  int64_t tok = ids ? ids[row] : row % n;
+  if (tok < 0 || tok >= N) {  // out-of-range id: never index with it (the reference's gather raises); flag and read token 0
+    if (bad_ids && v == 0) *bad_ids = 0xBAD1D5u;
+    tok = 0;
+  }
   float tmp[8];
-  load8(src + srow * W + v * 8, tmp);
+  load8(src + (b * N + tok) * W + v * 8, tmp);
   store8(dst + row * W + v * 8, tmp);
 }
 // small fp32 rows (token latent, T values): dst[b*n+j, :] = src[(b % Bx)*N + ids[b*n+j], :]
 static __global__ void
 gather_tok_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids,
-                                  float* __restrict__ dst, int64_t B, int64_t Bx, int64_t N, int64_t n, int T) {
+                                  float* __restrict__ dst, int64_t B, int64_t Bx, int64_t N, int64_t n, int T,
+                                  uint32_t* bad_ids) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n * T) return;
   const int64_t row = i / T, c = i % T;
   const int64_t b = row / n;
-  const int64_t tok = ids ? ids[row] : row % n;
+  int64_t tok = ids ? ids[row] : row % n;
+  if (tok < 0 || tok >= N) {
+    if (bad_ids && c == 0) *bad_ids = 0xBAD1D5u;
+    tok = 0;
+  }
   dst[i] = src[((b % Bx) * N + tok) * T + c];
 }
 
@@ -763,22 +776,28 @@ __global__ void pack_adaln_kernel(const TS* __restrict__ src, TD* __restrict__ d
 // The reference takes the renorm norms over the head's full (N, T) output, in which tokens outside
 // pred_ids carry the latent itself for both passes (diffusion_mlp.py:99): `extra_sumsq[b] * extra_scale`
 // adds that contribution (sum of squares of the unpredicted latent rows at this step) to both norms.
+// Three-pass forms (guidance_scaler.py:78-85), v3 = v2[2B + b]:
+//   mode 1 (image):          v = renorm(vu + (vc - v3) * s) + (v3 - vu) * s3
+//   mode 2 (spatiotemporal): v = renorm(vu + (vc - vu) * s) + (vc - v3) * s3
+// On rows outside pred_ids all passes carry the latent, so the extra term vanishes there.
 static __global__ void __launch_bounds__(256)
 cfg_euler_kernel(const float* __restrict__ v2, float* __restrict__ x_sel, int64_t B, int64_t len, float scale,
-                 float renorm, float dt, float* __restrict__ extra_sumsq, float* __restrict__ ratio_out) {
+                 float renorm, float dt, float* __restrict__ extra_sumsq, float* __restrict__ ratio_out, int mode,
+                 float scale3) {
   __shared__ float red[2][8];
   pdl_trigger();
   pdl_wait();
   const int64_t b = blockIdx.x;
   const float* vc = v2 + b * len;
   const float* vu = v2 + (B + b) * len;
+  const float* v3 = v2 + (2 * B + b) * len;  // only read when mode != 0
   float* x = x_sel + b * len;
   float ratio = 1.0f;
   if (renorm < 1.0f) {
     float sc = 0.f, sv = 0.f;
     for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
       const float c = vc[i], u = vu[i];
-      const float v = fmaf(c - u, scale, u);
+      const float v = fmaf(c - (mode == 1 ? v3[i] : u), scale, u);
       sc = fmaf(c, c, sc);
       sv = fmaf(v, v, sv);
     }
@@ -812,7 +831,13 @@ cfg_euler_kernel(const float* __restrict__ v2, float* __restrict__ x_sel, int64_
   }
   for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
     const float c = vc[i], u = vu[i];
-    const float v = fmaf(c - u, scale, u) * ratio;
+    float v;
+    if (mode == 0) {
+      v = fmaf(c - u, scale, u) * ratio;
+    } else {
+      const float t = v3[i];
+      v = mode == 1 ? fmaf(t - u, scale3, fmaf(c - t, scale, u) * ratio) : fmaf(c - t, scale3, fmaf(c - u, scale, u) * ratio);
+    }
     x[i] = __fadd_rn(__fmul_rn(v, dt), x[i]);
   }
 }
@@ -846,19 +871,24 @@ unpred_sumsq_kernel(const float* __restrict__ noise, const float* __restrict__ x
 // out[b, tok, :] for predicted tokens <- x_sel;  (pred_ids == nullptr: plain copy)
 static __global__ void
 scatter_tok_kernel(const float* __restrict__ x_sel, const int64_t* __restrict__ ids,
-                                   float* __restrict__ out, int64_t Bx, int64_t N, int64_t n, int T) {
+                                   float* __restrict__ out, int64_t Bx, int64_t N, int64_t n, int T, uint32_t* bad_ids) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bx * n * T) return;
   const int64_t row = i / T, c = i % T;
   const int64_t b = row / n;
   const int64_t tok = ids ? ids[row] : row % n;
+  if (tok < 0 || tok >= N) {  // never write through an out-of-range id
+    if (bad_ids && c == 0) *bad_ids = 0xBAD1D5u;
+    return;
+  }
   out[(b * N + tok) * T + c] = x_sel[i];
 }
 // Tokens outside pred_ids: the head returns its own input there, so the reference's loop
 // does x <- x*dt + x every step (two roundings); reproduce that recurrence exactly.
 static __global__ void
 unpredicted_kernel(const float* __restrict__ noise, float* __restrict__ out, int64_t numel, int64_t per_cloud,
-                   int64_t Bx, const float* __restrict__ dts, const float* __restrict__ ratios, int S) {
+                   int64_t Bx, const StepList dts_list, const float* __restrict__ ratios, int S) {
+  const float* dts = dts_list.v;  // by value: this kernel also runs for an EMPTY set, when there is no workspace
   // With guidance renorm the head output (these rows included) is first scaled by the per-cloud
   // ratio of that step: ratios[s * Bx + b]; nullptr means 1.
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

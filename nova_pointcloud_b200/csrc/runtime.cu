@@ -2,6 +2,7 @@
 // the host-mapped debug words of the tcgen05 kernels, and the small C-ABI entry points.
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -104,7 +105,7 @@ uint32_t* debug_word() {
   static std::once_flag once;
   std::call_once(once, [] {
     uint32_t* host = nullptr;
-    if (cudaHostAlloc(reinterpret_cast<void**>(&host), 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host), 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
       std::memset(host, 0, 4 * sizeof(uint32_t));
       if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host, 0) != cudaSuccess) dev = nullptr;
       g_debug_host = host;
@@ -114,15 +115,31 @@ uint32_t* debug_word() {
 }
 uint32_t* g_debug_host = nullptr;
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+int num_sms() {  // of the CURRENT device: one process may drive several GPUs
+  static std::atomic<int> sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  int v = sms[slot].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    sms[slot].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to a function ON A DEVICE: set it once per (kernel, device),
+// from any host thread (setting it twice is harmless, so a relaxed flag per device is enough).
+int ensure_smem_attr(const void* func, int bytes, std::atomic<unsigned long long>* done_mask) {
+  int dev = 0;
+  NOVA_CHECK_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = dev >= 0 && dev < 64 ? 1ull << dev : 0ull;
+  if (bit == 0ull || (done_mask->load(std::memory_order_acquire) & bit) == 0ull) {
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (bit) done_mask->fetch_or(bit, std::memory_order_release);
+  }
+  return NOVA_OK;
 }
 
 int default_cta_group(int M) {
@@ -200,6 +217,13 @@ extern "C" int nova_device_check(void) {
 extern "C" int nova_debug_words(uint32_t* out4) {
   if (!out4) return NOVA_ERR_INVALID;
   for (int i = 0; i < 4; ++i) out4[i] = tc::g_debug_host ? tc::g_debug_host[i] : 0u;
+  return NOVA_OK;
+}
+
+extern "C" int nova_debug_words_clear(void) {
+  tc::debug_word();  // make sure the words exist
+  if (tc::g_debug_host)
+    for (int i = 0; i < 4; ++i) tc::g_debug_host[i] = 0u;
   return NOVA_OK;
 }
 

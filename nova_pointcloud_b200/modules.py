@@ -110,6 +110,34 @@ class DiffusionMLP(nn.Module):
         self._handle_key = None
 
     # ------------------------------------------------------------------ handle management
+    def invalidate(self):
+        """Drop the packed-weights handle; the next call re-packs from the current parameters.
+
+        The handle is re-packed automatically when a parameter's storage, device, dtype or version counter changes.
+        Updates that bypass the version counter (``p.data.copy_(...)``, ``p.data.mul_(...)`` as in EMA code, or a
+        re-allocation that lands at the same address) are invisible to that key: call ``invalidate()`` after them."""
+        if self._handle is not None:
+            self._handle.close()
+        self._handle, self._handle_key = None, None
+
+    repack = invalidate
+
+    def __getstate__(self):
+        # the handle owns a ctypes pointer into device memory: never copied or pickled; copy.deepcopy(model) (the
+        # reference's ModelEMA), pickle and torch.save(module) get a module that lazily packs its own handle
+        state = self.__dict__.copy()
+        state["_handle"], state["_handle_key"] = None, None
+        return state
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
     def _weights_key(self):
         ps = list(self.parameters())
         return (ps[0].device, ps[0].dtype, tuple((p.data_ptr(), p._version) for p in ps))
@@ -161,10 +189,13 @@ class DiffusionMLP(nn.Module):
         return tok.to(v.dtype).scatter(1, pred_ids.expand(-1, -1, v.size(-1)), v)
 
     def sample_tokens(self, noise_tok, z, timesteps, sigmas, pred_ids=None, guidance_scale=1.0, guidance_trunc=0.0,
-                      guidance_renorm=1.0) -> torch.Tensor:
-        """Fused denoise loop on token layout: (Bx,N,T) fp32 noise -> (Bx,N,T) fp32 sample."""
+                      guidance_renorm=1.0, image_guidance_scale=0.0, spatiotemporal_guidance_scale=0.0) -> torch.Tensor:
+        """Fused denoise loop on token layout: (Bx,N,T) fp32 noise -> (Bx,N,T) fp32 sample.
+
+        z holds Bx, 2 Bx ([cond; uncond]) or 3 Bx ([cond; uncond; third pass]) clouds according to the guidance."""
         h = self.handle()
         ids = None if pred_ids is None else pred_ids.reshape(pred_ids.shape[0], -1)
         return torch.ops.nova_b200.head_sample(noise_tok.float(), z.to(self.dtype), ids, h.id,
                                                [float(t) for t in timesteps], [float(s) for s in sigmas],
-                                               float(guidance_scale), float(guidance_trunc), float(guidance_renorm))
+                                               float(guidance_scale), float(guidance_trunc), float(guidance_renorm),
+                                               float(image_guidance_scale), float(spatiotemporal_guidance_scale))

@@ -17,6 +17,13 @@ from . import _lib
 from ._lib import NOVA_BF16, NOVA_F32, Guidance, HeadConfig, NovaError, check
 
 _DTYPES = {torch.float32: NOVA_F32, torch.bfloat16: NOVA_BF16}
+_STRICT_IDS = bool(int(__import__("os").environ.get("NOVA_B200_CHECK_IDS", "0")))
+
+
+def set_strict_ids(on: bool):
+    """Range-check pred_ids on the host before every launch (one device sync per call); off by default."""
+    global _STRICT_IDS
+    _STRICT_IDS = bool(on)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -110,6 +117,12 @@ def _check_inputs(h: HeadHandle, x_tok, z, pred_ids):
         raise NovaError(f"z dtype {z.dtype} does not match the head's {h.dtype}")
     if pred_ids is not None and (pred_ids.dim() != 2 or pred_ids.shape[0] != z.shape[0] or pred_ids.dtype != torch.int64):
         raise NovaError(f"pred_ids must be int64 (B={z.shape[0]}, n); got {tuple(pred_ids.shape)} {pred_ids.dtype}")
+    if pred_ids is not None and pred_ids.numel() and _STRICT_IDS:
+        # The kernels never index with an id outside [0, N) (they flag it: _lib.bad_pred_ids_seen); strict mode turns
+        # that into the reference's behaviour -- an IndexError before anything is launched -- at the price of a sync.
+        lo, hi = int(pred_ids.min()), int(pred_ids.max())
+        if lo < 0 or hi >= x_tok.shape[1]:
+            raise IndexError(f"pred_ids out of range [0, {x_tok.shape[1]}): min {lo}, max {hi}")
 
 
 @torch.library.custom_op("nova_b200::head_forward", mutates_args=(), device_types="cuda")
@@ -149,7 +162,8 @@ def _(x_tok, t, z, pred_ids, handle):
 @torch.library.custom_op("nova_b200::head_sample", mutates_args=(), device_types="cuda")
 def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[torch.Tensor], handle: int,
                 timesteps: Sequence[float], sigmas: Sequence[float], guidance_scale: float, guidance_trunc: float,
-                guidance_renorm: float) -> torch.Tensor:
+                guidance_renorm: float, image_guidance_scale: float = 0.0,
+                spatiotemporal_guidance_scale: float = 0.0) -> torch.Tensor:
     """The fused S-step denoise loop, (Bx, N, T) fp32.  See nova_head_sample in nova_b200.h."""
     h = HeadHandle.get(handle)
     _check_inputs(h, noise_tok, z, pred_ids)
@@ -166,7 +180,8 @@ def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[tor
         ids = torch.zeros(1, dtype=torch.int64, device=z.device)
     c_t = (C.c_float * max(S, 1))(*[float(v) for v in timesteps])
     c_s = (C.c_double * (S + 1))(*[float(v) for v in sigmas])
-    g = Guidance(float(guidance_scale), float(guidance_trunc), float(guidance_renorm))
+    g = Guidance(float(guidance_scale), float(guidance_trunc), float(guidance_renorm), float(image_guidance_scale),
+                 float(spatiotemporal_guidance_scale))
     out = torch.empty(Bx, N, h.cfg.token_dim, dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device):
         ws = h.workspace(B * n, S)
@@ -176,7 +191,8 @@ def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[tor
 
 
 @head_sample.register_fake
-def _(noise_tok, z, pred_ids, handle, timesteps, sigmas, guidance_scale, guidance_trunc, guidance_renorm):
+def _(noise_tok, z, pred_ids, handle, timesteps, sigmas, guidance_scale, guidance_trunc, guidance_renorm,
+      image_guidance_scale=0.0, spatiotemporal_guidance_scale=0.0):
     return noise_tok.new_empty(noise_tok.shape, dtype=torch.float32)
 
 

@@ -42,8 +42,6 @@ class GuidanceScaler:
 
     def __init__(self, guidance_scale=1, guidance_trunc=0, guidance_renorm=1, image_guidance_scale=0,
                  spatiotemporal_guidance_scale=0, min_guidance_scale=None, **_unused):
-        if image_guidance_scale + spatiotemporal_guidance_scale > 0:
-            raise NovaError("three-pass guidance (image / spatiotemporal) is not on the point-cloud path")
         floor = min_guidance_scale if min_guidance_scale else guidance_scale
         self.guidance_scale = guidance_scale
         self.guidance_trunc = guidance_trunc
@@ -55,7 +53,8 @@ class GuidanceScaler:
 
     @property
     def extra_pass(self) -> bool:
-        return False  # rejected in __init__
+        """A third guidance pass ([cond; uncond; image-only or perturbed], guidance_scaler.py:32-35)."""
+        return self.image_guidance_scale + self.spatiotemporal_guidance_scale > 0
 
     def clone(self) -> "GuidanceScaler":
         return GuidanceScaler(**{k: getattr(self, k) for k in self._NUMBERS})
@@ -64,8 +63,8 @@ class GuidanceScaler:
         self.guidance_scale = self.min_guidance_scale + self.inc_guidance_scale * decay
 
     def expand(self, x: torch.Tensor) -> torch.Tensor:
-        """[x; x] along the batch while guidance is on, else x."""
-        return torch.cat([x, x]) if self.guidance_scale > 1 else x
+        """[x; x] (or [x; x; x] with a third pass) along the batch while guidance is on, else x."""
+        return torch.cat([x] * (3 if self.extra_pass else 2)) if self.guidance_scale > 1 else x
 
 
 @torch.no_grad()
@@ -74,7 +73,7 @@ def denoise(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler, z: t
             ) -> torch.Tensor:
     """Run the diffusion denoising process for one set of tokens.
 
-    z (B',N,Dc) with B' = B or 2B ([cond; uncond]); x (B,C,H*p,W*p) noise; pred_ids (B',n,1).
+    z (B',N,Dc) with B' = B, 2B ([cond; uncond]) or 3B (three-pass guidance); x (B,C,H*p,W*p) noise; pred_ids (B',n,1).
     Returns ``patchify(x_S)`` (B,N,T) fp32.  ``scheduler.set_timesteps`` must have been called.
     """
     gs = guidance_scaler or GuidanceScaler()
@@ -82,7 +81,8 @@ def denoise(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler, z: t
     head.patch_embed.set_hw(x)
     tok = head.patch_embed.patchify(x)
     out = head.sample_tokens(tok, z, scheduler.timesteps, scheduler.sigmas, pred_ids, gs.guidance_scale,
-                             gs.guidance_trunc, gs.guidance_renorm)
+                             gs.guidance_trunc, gs.guidance_renorm, getattr(gs, "image_guidance_scale", 0) or 0,
+                             getattr(gs, "spatiotemporal_guidance_scale", 0) or 0)
     scheduler._step_index = len(scheduler.timesteps)
     return out
 

@@ -27,3 +27,18 @@ def make_case(depth, D, Dc, B, H, W, patch=1, chan=3, seed=7, n_pred=None, devic
     order = torch.rand(B, N, generator=g).argsort(dim=1)
     pred_ids = None if n_pred is None else order[:, :n_pred].unsqueeze(-1).contiguous()
     return head, x, z, t, pred_ids
+
+
+def record(name, value):
+    """Append a measured parity error to gpurun_out/parity_errors.jsonl (copied into profiles/ per round)."""
+    import json
+    import os
+
+    root = os.environ.get("GRAFT_REPO_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, "rel_max_err": float(value)}) + "\n")
+    except OSError:
+        pass

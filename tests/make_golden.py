@@ -215,11 +215,45 @@ def init_checksums(ref):
         json.dump(rec, f, indent=1)
 
 
+def guidance3_case(ref, name="denoise_guidance3", depth=2, D=64, Dc=64, B=2, N=16, n_pred=5, steps=12, shift=1.0, seed=505):
+    """Three-pass guidance (guidance_scaler.py:78-85): z = [cond; uncond; third], pred_ids expanded three times."""
+    torch.manual_seed(seed)
+    head = ref.DiffusionMLP(depth, D, Dc, patch_size=1, image_dim=3).eval()
+    model, sched = reference_denoiser(ref, head, steps, shift)
+    g = torch.Generator().manual_seed(seed + 1)
+    noise = torch.randn(B, 3, N, 1, generator=g)
+    z3 = torch.randn(3 * B, N, Dc, generator=g)
+    order = torch.rand(B, N, generator=g).argsort(dim=1)
+    pred_ids = order[:, :n_pred].unsqueeze(-1).contiguous()
+    p3 = torch.cat([pred_ids] * 3)
+    out = {}
+    out["img"] = model.denoise(z3, noise.clone(), ref.GuidanceScaler(guidance_scale=3.0, image_guidance_scale=1.5), None, p3)
+    out["img_all"] = model.denoise(z3, noise.clone(), ref.GuidanceScaler(guidance_scale=3.0, image_guidance_scale=1.5))
+    out["img_renorm"] = model.denoise(
+        z3, noise.clone(), ref.GuidanceScaler(guidance_scale=3.0, image_guidance_scale=1.5, guidance_renorm=0.6), None, p3)
+    out["st"] = model.denoise(
+        z3, noise.clone(), ref.GuidanceScaler(guidance_scale=3.0, spatiotemporal_guidance_scale=0.8), None, p3)
+    out["st_renorm_trunc"] = model.denoise(
+        z3, noise.clone(), ref.GuidanceScaler(guidance_scale=3.0, spatiotemporal_guidance_scale=0.8, guidance_renorm=0.7,
+                                              guidance_trunc=400.0), None, p3)
+    np.savez_compressed(
+        os.path.join(GOLD, name + ".npz"),
+        cfg=np.array([depth, D, Dc, steps]), shift=np.array(shift),
+        noise=noise.numpy(), z3=z3.numpy(), pred_ids=pred_ids.numpy(),
+        **{"out_" + k: v.numpy() for k, v in out.items()},
+        **sd_np(head.state_dict()),
+    )
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(4)
     if "--only-geometry" in sys.argv:
         geometry_case()
+        return
+    if "--only-guidance3" in sys.argv:
+        with torch.no_grad():
+            guidance3_case(import_reference())
         return
     if "--only-losses" in sys.argv:
         losses_case(import_reference())
@@ -230,6 +264,7 @@ def main():
         head_case(ref, "head_p2", depth=1, D=64, Dc=64, patch=2, chan=4, B=2, H=4, W=6, n_pred=5, seed=202)
         denoise_case(ref, "denoise_small", depth=2, D=128, Dc=128, B=2, N=20, n_pred=6, steps=25, shift=1.0, seed=303)
         denoise_case(ref, "denoise_shift3", depth=1, D=64, Dc=64, B=2, N=12, n_pred=4, steps=10, shift=3.0, seed=404)
+        guidance3_case(ref)
         scheduler_case(ref)
         chamfer_case()
         geometry_case()

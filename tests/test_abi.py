@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.nova_abi_version() == 1
+    assert lib.nova_abi_version() == 2
 
 
 def test_header_has_no_torch_or_cxx_types():

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import cpu_sd, make_case, relmax
+from gpu_util import cpu_sd, make_case, record, relmax
 from oracle import chamfer as OC
 from oracle import head as OH
 from oracle import loop as OL
@@ -85,6 +85,35 @@ def test_sample_fp32_teacher_forced_per_step():
         assert relmax(one, x_next_ref) < FP32_TOL, i
 
 
+def test_cfg1_exact_shape_fp32_teacher_forced():
+    """BASELINE.json configs[0] at its own shape -- DiffusionMLP(6, 1024, 1024), 4 clouds x 1024 points, 25 steps,
+    fp32 -- through the fp32 handle: every Euler step teacher-forced (the oracle's x_t in), velocity and x_{t+1}
+    within 1e-5 of oracle/loop.py, which the golden / live tests pin to transformer_3d.py:102-113."""
+    B, N, D = 4, 1024, 1024
+    head, x, z, _, _ = make_case(6, D, D, B, N, 1, seed=1337)
+    sd = cpu_sd(head)
+    traj = []
+    ref_final = OL.denoise(sd, z, x, num_steps=25, trajectory=traj)
+    head = head.cuda()
+    ts, sig = OS.schedule(25)
+    zc = z.cuda()
+    worst_v = worst_x = 0.0
+    for i, (x_t, v_ref, x_next_ref) in enumerate(traj):
+        v = head(OH.unpatchify(x_t, 1, 3, N, 1).cuda(), torch.full((B,), float(ts[i])).cuda(), zc)
+        one = head.sample_tokens(x_t.cuda(), zc, ts[i : i + 1], sig[i : i + 2])
+        worst_v, worst_x = max(worst_v, relmax(v, v_ref)), max(worst_x, relmax(one, x_next_ref))
+    record("cfg1 fp32 per-step velocity (4 x 1024 x D=1024)", worst_v)
+    record("cfg1 fp32 per-step x_next (4 x 1024 x D=1024)", worst_x)
+    assert worst_v < FP32_TOL and worst_x < FP32_TOL, (worst_v, worst_x)
+    import nova_pointcloud_b200 as nb
+
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(25)
+    e2e = relmax(nb.denoise(head, sched, zc, x.cuda()), ref_final)
+    record("cfg1 fp32 end-to-end 25 steps", e2e)
+    assert e2e < 5e-5  # 25 compounded steps
+
+
 @pytest.mark.parametrize("mode", ["all", "pred", "cfg", "cfg_renorm", "cfg_trunc"])
 def test_sample_fp32_end_to_end(mode):
     import nova_pointcloud_b200 as nb
@@ -117,6 +146,38 @@ def test_sample_fp32_end_to_end(mode):
             assert torch.allclose(out.cpu()[mask], ref[mask], rtol=1e-5, atol=1e-7)
         else:  # reproduced to the last bit
             assert torch.equal(out.cpu()[mask], ref[mask])
+
+
+@pytest.mark.parametrize("mode,kw", [
+    ("img", dict(image_guidance_scale=1.5)),
+    ("img_all", dict(image_guidance_scale=1.5)),
+    ("img_renorm", dict(image_guidance_scale=1.5, guidance_renorm=0.6)),
+    ("st", dict(spatiotemporal_guidance_scale=0.8)),
+    ("st_renorm_trunc", dict(spatiotemporal_guidance_scale=0.8, guidance_renorm=0.7, guidance_trunc=400.0)),
+])
+def test_three_pass_guidance_matches_oracle(mode, kw):
+    """image_guidance_scale / spatiotemporal_guidance_scale (guidance_scaler.py:78-85): the fused loop against the
+    oracle, whose three-pass form is pinned to the reference's own denoise by tests/golden/denoise_guidance3.npz
+    (test_oracle_golden.py::test_three_pass_guidance_matches_reference; the library needs widths that are multiples
+    of 256, the fixture is D = 64)."""
+    import nova_pointcloud_b200 as nb
+
+    head, x, z, _, pred_ids = make_case(2, 256, 64, 2, 40, 1, n_pred=9)
+    g = torch.Generator().manual_seed(78)
+    z3 = torch.cat([z, torch.randn(z.shape, generator=g), torch.randn(z.shape, generator=g)])
+    p3 = None if mode == "img_all" else torch.cat([pred_ids] * 3)
+    ref = OL.denoise(cpu_sd(head), z3, x, pred_ids=p3, guidance_scale=3.0, **kw)
+    head = head.cuda()
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(25)
+    gs = nb.GuidanceScaler(guidance_scale=3.0, **kw)
+    for _ in range(3):  # eager, graph capture, replay
+        out = nb.denoise(head, sched, z3.cuda(), x.cuda(), gs.clone(), None, None if p3 is None else p3.cuda())
+    assert relmax(out, ref) < 5e-5  # 25 compounded steps, fp32
+    hb = head.to(torch.bfloat16)  # the tcgen05 path: [cond; uncond; third] = 3 x rows through the same kernels
+    refb = OL.denoise(cpu_sd(hb, torch.float32), z3.bfloat16().float(), x, pred_ids=p3, guidance_scale=3.0, **kw)
+    outb = nb.denoise(hb, sched, z3.cuda().bfloat16(), x.cuda(), gs.clone(), None, None if p3 is None else p3.cuda())
+    assert relmax(outb, refb) < 5e-2
 
 
 @pytest.mark.parametrize("shift,steps", [(3.0, 10), (1.0, 1)])
@@ -164,14 +225,22 @@ def test_sample_bf16_teacher_forced_and_chamfer(monkeypatch, wide_rows):
         x_t, v_ref, x_next_ref = traj[i]
         v = head(OH.unpatchify(x_t, 1, 3, N, 1).cuda().bfloat16(), torch.full((B,), float(ts[i])).cuda(), zb.cuda())
         one = head.sample_tokens(x_t.cuda(), zb.cuda(), ts[i : i + 1], sig[i : i + 2])
-        worst_v, worst_x = max(worst_v, relmax(one, x_next_ref)), max(worst_x, relmax(one, x_next_ref))
-        # velocity through the module surface sees a bf16-rounded latent like the reference's bf16 run
-        assert relmax(v.float(), v_ref) < 2 * BF16_TOL, i
+        worst_v, worst_x = max(worst_v, relmax(v.float(), v_ref)), max(worst_x, relmax(one, x_next_ref))
+        # Both per-step quantities meet the north-star bf16 tolerance.  The velocity through the module surface sees a
+        # bf16-ROUNDED latent (as the reference's own bf16 run does) and is returned in bf16; the fused loop keeps the
+        # latent in fp32.
+        assert relmax(v.float(), v_ref) < BF16_TOL, i
         assert relmax(one, x_next_ref) < BF16_TOL, i
+    record(f"bf16 per-step velocity (module surface), wide_rows={wide_rows}", worst_v)
+    record(f"bf16 per-step x_next (fused loop), wide_rows={wide_rows}", worst_x)
     sched = nb.FlowMatchEulerDiscreteScheduler()
     sched.set_timesteps(25)
     out = nb.denoise(head, sched, zb.cuda(), x.cuda())
-    assert relmax(out, ref_final) < 5e-2
+    # 25 compounded bf16 steps against the fp32 oracle: the tolerance north_star states is per step (above); the
+    # end-to-end figure is recorded (profiles/) and bounded by 2.5 x the per-step tolerance
+    e2e = relmax(out, ref_final)
+    record(f"bf16 end-to-end 25 steps, 2 x 256 tokens, D=768, wide_rows={wide_rows}", e2e)
+    assert e2e < BF16_TOL  # measured 6e-4 .. 7e-4 (profiles/r2_parity_errors.jsonl)
     # matching Chamfer on the final clouds (variant A), against each other and against a common target
     target = np.random.default_rng(12).uniform(-1, 1, size=(N, 3)).astype(np.float32)
     for b in range(B):
@@ -230,7 +299,7 @@ def test_graph_replay_of_the_denoise_loop_is_bit_identical(monkeypatch, mode, dt
     runs = [nb.denoise(head, sched, zz, x1, gs, None, pid) for _ in range(3)]  # eager, capture + launch, replay
     ops.launch_count_reset()
     replay_new_data = nb.denoise(head, sched, zz, x2, gs, None, pid)
-    assert ops.launch_count() > 5 * 8  # the replayed kernels are still counted
+    assert ops.launch_count() >= 5 * 3  # the replayed kernels are still counted (>= prep + statistics GEMM + chain kernel per step)
     other_schedule = nb.denoise(head, sched3, zz, x1, gs, None, pid)
     for r in runs:
         assert torch.equal(r, eager1)

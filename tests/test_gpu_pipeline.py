@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import cpu_sd, make_case, relmax
+from gpu_util import record, cpu_sd, make_case, relmax
 from oracle import head as OH
 from oracle import loop as OL
 
@@ -112,9 +112,13 @@ def test_full_size_batch_invariance_and_ragged_batches():
     assert torch.equal(half[0], alone[0, :1024])
     ragged = nb.denoise(head, sched, z[5:12], noise[5:12])  # 7 clouds = 14 336 rows: not a multiple of the 256-row tile pair
     assert torch.equal(ragged, full[5:12])
-    # one oracle cloud pins the full-size run to the reference arithmetic (bf16 tolerance, fp32 oracle on rounded weights)
-    ref = OL.denoise(cpu_sd(head, torch.float32), z[3:4].float().cpu(), noise[3:4].cpu(), num_steps=25)
-    assert relmax(full[3:4], ref) < 5e-2
+    # four oracle clouds spread over the batch pin the full-size run to the reference arithmetic (fp32 oracle on the
+    # bf16-rounded weights; 25 compounded bf16 steps, measured value recorded under profiles/)
+    pick = [3, 12, 21, 30]
+    ref = OL.denoise(cpu_sd(head, torch.float32), z[pick].float().cpu(), noise[pick].cpu(), num_steps=25)
+    err = relmax(full[pick], ref)
+    record("cfg2 full size, 4 oracle clouds, bf16 end-to-end", err)
+    assert err < 2e-2  # measured 6e-4 (profiles/r2_parity_errors.jsonl)
 
 
 @pytest.mark.parametrize("name,D,N,B", [("cfg3: NOVA-0.6B, 1024 points, batch 64", 1024, 1024, 64),
@@ -135,8 +139,11 @@ def test_full_size_batch_invariance_other_configs(name, D, N, B):
         reps = 4096 // N
         alone = nb.denoise(head, sched, z[b:b + 1].repeat(reps, 1, 1), noise[b:b + 1].repeat(reps, 1, 1, 1))
         assert all(torch.equal(alone[r], full[b]) for r in range(reps)), (name, b)
-    ref = OL.denoise(cpu_sd(head, torch.float32), z[1:2].float().cpu(), noise[1:2].cpu(), num_steps=25)
-    assert relmax(full[1:2], ref) < 5e-2, name
+    pick = [1, B // 3, 2 * B // 3, B - 2]  # four oracle clouds spread over the batch
+    ref = OL.denoise(cpu_sd(head, torch.float32), z[pick].float().cpu(), noise[pick].cpu(), num_steps=25)
+    err = relmax(full[pick], ref)
+    record(f"{name}: 4 oracle clouds, bf16 end-to-end", err)
+    assert err < 2e-2, name  # measured 7e-4 .. 1e-3 (profiles/r2_parity_errors.jsonl)
 
 
 def test_degenerate_shapes():

@@ -99,8 +99,9 @@ def test_guidance_scaler_surface():
     x = torch.arange(6.0).reshape(2, 3)
     assert torch.equal(g.expand(x), torch.cat([x, x]))
     assert nb.GuidanceScaler().expand(x) is x
-    with pytest.raises(nb.NovaError):
-        nb.GuidanceScaler(guidance_scale=2, image_guidance_scale=1.5)
+    g3 = nb.GuidanceScaler(guidance_scale=2, image_guidance_scale=1.5)  # third pass (guidance_scaler.py:32-35,46-50)
+    assert g3.extra_pass and torch.equal(g3.expand(x), torch.cat([x, x, x])) and g3.clone().image_guidance_scale == 1.5
+    assert not g.extra_pass and nb.GuidanceScaler(guidance_scale=2, spatiotemporal_guidance_scale=0.5).extra_pass
 
 
 def test_shard_range_covers_everything():
@@ -156,3 +157,38 @@ def test_standard_point_cloud_generation_contract():
     same = nb.standard_point_cloud_generation(pc, 50, generator=torch.Generator().manual_seed(4))
     assert same.shape == (50, 3) and float(same.abs().max()) <= 1.0
     assert 0.05 < float((same - torch.tanh(pc)).std()) < 0.2  # 0.1-sigma noise, clipped at the box
+
+
+def test_module_copies_and_pickles_without_its_handle():
+    """copy.deepcopy (the reference's ModelEMA), pickle and torch.save of a head that has been used: the packed-weights
+    handle (a ctypes pointer into device memory) is never copied; load_state_dict / .to() / invalidate() drop it."""
+    import copy
+    import ctypes
+    import io
+    import pickle
+
+    import nova_pointcloud_b200 as nb
+
+    class FakeHandle:  # what a used head holds; a bare c_void_p cannot be pickled or deep-copied
+        def __init__(self):
+            self.ptr, self.closed = ctypes.c_void_p(1234), False
+
+        def close(self):
+            self.closed = True
+
+    head = nb.DiffusionMLP(1, 256, 256, patch_size=1, image_dim=3)
+    head._handle, head._handle_key = FakeHandle(), ("key",)
+    clone = copy.deepcopy(head)
+    assert clone._handle is None and clone._handle_key is None and head._handle is not None
+    assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), head.state_dict().values()))
+    pickle.loads(pickle.dumps(head))
+    torch.save(head, io.BytesIO())
+    fake = head._handle
+    head.load_state_dict(clone.state_dict())
+    assert head._handle is None and fake.closed  # stale packed weights can never be served after a load
+    head._handle, head._handle_key = FakeHandle(), ("key",)
+    head.to(torch.bfloat16)
+    assert head._handle is None
+    head._handle, head._handle_key = FakeHandle(), ("key",)
+    head.invalidate()  # explicit hook for in-place updates through .data (EMA code), which no version counter sees
+    assert head._handle is None

@@ -124,6 +124,26 @@ def test_denoise_loop_matches_reference(golden_dir, name):
     assert relmax(out, d["out_cfg_trunc"]) < 5e-6
 
 
+GUIDANCE3 = {
+    "img": dict(image_guidance_scale=1.5),
+    "img_all": dict(image_guidance_scale=1.5),
+    "img_renorm": dict(image_guidance_scale=1.5, guidance_renorm=0.6),
+    "st": dict(spatiotemporal_guidance_scale=0.8),
+    "st_renorm_trunc": dict(spatiotemporal_guidance_scale=0.8, guidance_renorm=0.7, guidance_trunc=400.0),
+}
+
+
+@pytest.mark.parametrize("mode", sorted(GUIDANCE3))
+def test_three_pass_guidance_matches_reference(golden_dir, mode):
+    """image_guidance_scale / spatiotemporal_guidance_scale (guidance_scaler.py:78-85) against the reference's own denoise."""
+    d, sd = load(golden_dir, "denoise_guidance3")
+    noise, z3 = torch.from_numpy(d["noise"]), torch.from_numpy(d["z3"])
+    p3 = None if mode == "img_all" else torch.cat([torch.from_numpy(d["pred_ids"])] * 3)
+    out = OL.denoise(sd, z3, noise, num_steps=int(d["cfg"][3]), shift=float(d["shift"]), pred_ids=p3, guidance_scale=3.0,
+                     **GUIDANCE3[mode])
+    assert relmax(out, d["out_" + mode]) < 5e-6
+
+
 def test_denoise_unpredicted_rows_closed_form(golden_dir):
     """Rows outside pred_ids follow x <- x + dt x: noise * prod(1 + dt_i)."""
     d, sd = load(golden_dir, "denoise_small")
