@@ -141,6 +141,29 @@ NOVA_API int nova_head_sample(const nova_head_t* h, const float* noise_tok, cons
                      const double* sigmas_host, int32_t num_steps, const nova_guidance* guidance,
                      float* x_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Set-by-set generation for a fixed condition, scheduled on the device: the accumulation loop of
+ * Transformer3DModel.generate_frame (diffnext/models/transformers/transformer_3d.py:123-133) with the mask bookkeeping
+ * of MaskEmbed.get_pred_mask (diffnext/models/embeddings.py:262-270) as device-side gathers / scatters.
+ *   order          [Bx, N] int64  generation order of every cloud (a permutation of 0..N-1: argsort of uniforms)
+ *   set_sizes_host [num_sets] host int32: set i predicts the tokens order[:, first_i : first_i + n_i], first_i = sum of
+ *                  the sizes before it; empty sets are skipped (transformer_3d.py:120)
+ *   noise_tok      [Bx, N, T] fp32: the initial latent of every token (a set reads only its own positions, so one
+ *                  N(0,1) draw per token has the distribution of the reference's fresh tensor per set)
+ *   guidance_scales_host [live sets] host fp32 or NULL: the decayed guidance scale of every non-empty set
+ *                  (GuidanceScaler.decay_guidance_scale, transformer_3d.py:124); NULL = guidance->scale for all.
+ *                  guidance->renorm must be >= 1 here (its norms need every set's full noise tensor).
+ *   x_out          [Bx, N, T] fp32: tokens of every set written at their positions (x += sample * pred_mask, :133);
+ *                  positions no set covers are left untouched.
+ * One host call per pass: the launches of all sets are captured into ONE CUDA graph on the second call with the same
+ * workspace, buffers, shapes, schedule, set sizes and guidance, and replayed afterwards.
+ */
+NOVA_API int nova_head_generate_sets(const nova_head_t* h, const float* noise_tok, const void* z, const int64_t* order,
+                                     int64_t B, int64_t Bx, int64_t N, const int32_t* set_sizes_host, int32_t num_sets,
+                                     const float* timesteps_host, const double* sigmas_host, int32_t num_steps,
+                                     const nova_guidance* guidance, const float* guidance_scales_host, float* x_out,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* prev = model_output * dt + sample, elementwise, two roundings in `dtype` (nova_dtype). */
 NOVA_API int nova_euler_step(const void* model_output, const void* sample, double dt, void* prev, int64_t numel,
                     int32_t dtype, void* stream);

@@ -417,15 +417,16 @@ int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_p
   const AT* z_rows = z;
   if (pred_ids) {
     const int64_t nvec = M * (Dc / 8);
-    rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, pred_ids, static_cast<AT*>(w.zsel), B, N,
-                                                                           n, Dc, bad_ids_word());
+    rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, rw::IdsView{pred_ids, n, B},
+                                                                           static_cast<AT*>(w.zsel), B, N, n, Dc,
+                                                                           bad_ids_word());
     NOVA_CHECK_LAUNCH();
     z_rows = static_cast<const AT*>(w.zsel);
   }
   const float* x_rows = x_tok;
   if (pred_ids || Bx != B) {
-    rw::gather_tok_kernel<<<(unsigned)ceil_div(M * T, 256), 256, 0, s>>>(x_tok, pred_ids, w.xsel, B, Bx, N, n, T,
-                                                                         bad_ids_word());
+    rw::gather_tok_kernel<<<(unsigned)ceil_div(M * T, 256), 256, 0, s>>>(x_tok, rw::IdsView{pred_ids, n, B}, w.xsel, B, Bx,
+                                                                         N, n, T, bad_ids_word());
     NOVA_CHECK_LAUNCH();
     x_rows = w.xsel;
   }
@@ -435,10 +436,14 @@ int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_p
   return head_step<AT>(h, w, io, s);
 }
 
+// One set of tokens through the S-step loop.  `ids` selects the n tokens per cloud (ids.ptr == nullptr: all N);
+// write_unpredicted: also write the tokens OUTSIDE the set (the reference's x <- x + dt x recurrence) -- the plain
+// denoise call does, the set scheduler (nova_head_generate_sets) does not: there every token belongs to one set.
 template <typename AT>
-int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const int64_t* pred_ids, int64_t B, int64_t Bx,
+int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const rw::IdsView ids, int64_t B, int64_t Bx,
                 int64_t N, int64_t n, const float* timesteps, const double* sigmas, int S, const nova_guidance* g,
-                float* x_out, void* ws, cudaStream_t s) {
+                float* x_out, void* ws, cudaStream_t s, bool write_unpredicted = true) {
+  const int64_t* pred_ids = ids.ptr;
   const int T = h->T(), Dc = h->Dc();
   const int64_t M = B * n, Mx = Bx * n;
   const bool guided = g != nullptr && g->scale > 1.0f;
@@ -447,7 +452,7 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   const float gscale3 = gmode == 1 ? g->image_scale : gmode == 2 ? g->spatiotemporal_scale : 0.f;
   TimeList dts{};
   for (int i = 0; i < S; ++i) dts.v[i] = static_cast<float>(sigmas[i + 1] - sigmas[i]);
-  const bool has_unpred = pred_ids != nullptr && n < N;
+  const bool has_unpred = pred_ids != nullptr && n < N && write_unpredicted;
   auto unpredicted = [&](const float* ratios) -> int {
     // tokens outside the set: x <- (ratio*x)*dt + x per step (ratio == 1 without guidance renorm); the step sizes
     // travel by value, so the empty-set call (M == 0, no workspace required) touches no scratch memory
@@ -465,13 +470,13 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
   const AT* z_rows = z;
   if (pred_ids) {
     const int64_t nvec = M * (Dc / 8);
-    rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, pred_ids, static_cast<AT*>(w.zsel), B, N,
-                                                                           n, Dc, bad_ids_word());
+    rw::gather_rows_kernel<AT><<<(unsigned)ceil_div(nvec, 256), 256, 0, s>>>(z, ids, static_cast<AT*>(w.zsel), B, N, n, Dc,
+                                                                           bad_ids_word());
     NOVA_CHECK_LAUNCH();
     z_rows = static_cast<const AT*>(w.zsel);
   }
   // latent of the selected tokens, fp32, resident in the workspace for all S steps
-  rw::gather_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(noise_tok, pred_ids, w.xsel, Bx, Bx, N, n, T,
+  rw::gather_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(noise_tok, ids, w.xsel, Bx, Bx, N, n, T,
                                                                         bad_ids_word());
   NOVA_CHECK_LAUNCH();
   TimeList tl{};
@@ -556,6 +561,8 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
     const float gparams[5] = {guided ? g->scale : 0.f, guided ? g->trunc : 0.f, guided ? g->renorm : 1.f,
                               static_cast<float>(gmode), gscale3};
     mix(gparams, sizeof(gparams));
+    // the ids pointer, stride and batch are baked into the captured gather-free loop only through shapes: the gather /
+    // scatter launches sit OUTSIDE the captured loop, so a new window of the generation order replays the same graph
     const int64_t shape[6] = {B, Bx, N, n, (int64_t)renorm_extra, (int64_t)T};
     mix(shape, sizeof(shape));
     std::lock_guard<std::mutex> lock(h->graph_mutex);
@@ -611,8 +618,7 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const i
     }
   }
   if (has_unpred) NOVA_PROPAGATE(unpredicted(renorm_extra ? ratios : nullptr));
-  rw::scatter_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(w.xsel, pred_ids, x_out, Bx, N, n, T,
-                                                                         bad_ids_word());
+  rw::scatter_tok_kernel<<<(unsigned)ceil_div(Mx * T, 256), 256, 0, s>>>(w.xsel, ids, x_out, Bx, N, n, T, bad_ids_word());
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
@@ -918,9 +924,151 @@ extern "C" int nova_head_sample(const nova_head_t* h, const float* noise_tok, co
   NOVA_REQUIRE(noise_tok && z && x_out && (num_steps == 0 || (timesteps_host && sigmas_host)),
                "nova_head_sample: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const rw::IdsView ids{pred_ids, n, B};
   if (h->cfg.dtype == NOVA_F32)
-    return sample_impl<float>(h, noise_tok, static_cast<const float*>(z), pred_ids, B, Bx, N, n, timesteps_host,
+    return sample_impl<float>(h, noise_tok, static_cast<const float*>(z), ids, B, Bx, N, n, timesteps_host,
                               sigmas_host, num_steps, guidance, x_out, workspace, s);
-  return sample_impl<bf16>(h, noise_tok, static_cast<const bf16*>(z), pred_ids, B, Bx, N, n, timesteps_host, sigmas_host,
+  return sample_impl<bf16>(h, noise_tok, static_cast<const bf16*>(z), ids, B, Bx, N, n, timesteps_host, sigmas_host,
                            num_steps, guidance, x_out, workspace, s);
+}
+
+// The set-by-set accumulation of generate_frame (transformer_3d.py:123-133) for a fixed condition, scheduled on the
+// device: set i denoises the tokens order[:, first_i : first_i + n_i] of every cloud from noise_tok at those positions
+// and writes them into x_out at those positions (x += sample * pred_mask with disjoint masks, :133; the mask is the
+// window of the order, embeddings.py:262-270).  One host call per pass; the launches of all sets are captured into ONE
+// CUDA graph the second time the same (workspace, shapes, schedule, set sizes, guidance) come back.
+extern "C" int nova_head_generate_sets(const nova_head_t* h, const float* noise_tok, const void* z, const int64_t* order,
+                                       int64_t B, int64_t Bx, int64_t N, const int32_t* set_sizes_host, int32_t num_sets,
+                                       const float* timesteps_host, const double* sigmas_host, int32_t num_steps,
+                                       const nova_guidance* guidance, const float* guidance_scales_host, float* x_out,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  NOVA_REQUIRE(num_steps >= 0 && num_steps <= MAX_STEPS, "nova_head_generate_sets: num_steps %d out of range [0, %d]",
+               num_steps, MAX_STEPS);
+  NOVA_REQUIRE(num_sets >= 0 && (num_sets == 0 || set_sizes_host != nullptr), "nova_head_generate_sets: bad set list");
+  int64_t covered = 0, n_max = 0;
+  for (int i = 0; i < num_sets; ++i) {
+    NOVA_REQUIRE(set_sizes_host[i] >= 0, "nova_head_generate_sets: negative set size");
+    covered += set_sizes_host[i];
+    n_max = set_sizes_host[i] > n_max ? set_sizes_host[i] : n_max;
+  }
+  NOVA_REQUIRE(covered <= N, "nova_head_generate_sets: the sets cover %lld tokens of %lld", (long long)covered, (long long)N);
+  NOVA_PROPAGATE(check_call(h, B, Bx, N, n_max, workspace, workspace_bytes, num_steps, "nova_head_generate_sets"));
+  const bool guided = guidance != nullptr && (guidance->scale > 1.0f || guidance_scales_host != nullptr);
+  const bool third = guided && (guidance->image_scale > 0.f || guidance->spatiotemporal_scale > 0.f);
+  NOVA_REQUIRE(B == (guided ? (third ? 3 : 2) : 1) * Bx,
+               "nova_head_generate_sets: z batch %lld does not match guidance (x batch %lld)", (long long)B, (long long)Bx);
+  NOVA_REQUIRE(!guided || guidance->renorm >= 1.0f,
+               "nova_head_generate_sets: guidance_renorm < 1 needs every set's full noise tensor (its norms run over the "
+               "unpredicted rows too, guidance_scaler.py:67-72): call nova_head_sample per set");
+  if (Bx * N == 0 || covered == 0) return NOVA_OK;
+  NOVA_REQUIRE(noise_tok && z && order && x_out && (num_steps == 0 || (timesteps_host && sigmas_host)),
+               "nova_head_generate_sets: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  auto run_sets = [&](cudaStream_t st) -> int {
+    int64_t first = 0;
+    int live = 0;
+    for (int i = 0; i < num_sets; ++i) live += set_sizes_host[i] > 0;
+    int k = 0;
+    for (int i = 0; i < num_sets; ++i) {
+      const int64_t n = set_sizes_host[i];
+      if (n == 0) continue;  // the reference drops empty sets before counting (transformer_3d.py:120)
+      ++k;
+      nova_guidance gi{};
+      if (guidance) gi = *guidance;
+      if (guided && guidance_scales_host) gi.scale = guidance_scales_host[k - 1];  // decay_guidance_scale, per live set
+      const bool on = guided && gi.scale > 1.0f;
+      const int64_t Bi = on ? B : Bx;  // a set whose decayed scale is <= 1 runs the conditional rows only
+      const rw::IdsView ids{order + first, N, Bx};
+      int rc;
+      if (h->cfg.dtype == NOVA_F32)
+        rc = sample_impl<float>(h, noise_tok, static_cast<const float*>(z), ids, Bi, Bx, N, n, timesteps_host, sigmas_host,
+                                num_steps, on ? &gi : nullptr, x_out, workspace, st, /*write_unpredicted=*/false);
+      else
+        rc = sample_impl<bf16>(h, noise_tok, static_cast<const bf16*>(z), ids, Bi, Bx, N, n, timesteps_host, sigmas_host,
+                               num_steps, on ? &gi : nullptr, x_out, workspace, st, /*write_unpredicted=*/false);
+      NOVA_PROPAGATE(rc);
+      first += n;
+    }
+    (void)live;
+    return NOVA_OK;
+  };
+
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool graphable = h->use_graphs && h->capture_stream != nullptr && num_steps > 0 && !profile_enabled() &&
+                         cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+  if (!graphable) return run_sets(s);
+  uint64_t hash = 0x9E3779B97F4A7C15ull;  // FNV-1a over everything the captured launches depend on
+  auto mix = [&](const void* p, size_t nbytes) {
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    for (size_t k = 0; k < nbytes; ++k) hash = (hash ^ b[k]) * 1099511628211ull;
+  };
+  mix(timesteps_host, sizeof(float) * num_steps);
+  mix(sigmas_host, sizeof(double) * (num_steps + 1));
+  mix(set_sizes_host, sizeof(int32_t) * num_sets);
+  if (guidance) mix(guidance, sizeof(*guidance));
+  if (guided && guidance_scales_host) {
+    int live = 0;
+    for (int i = 0; i < num_sets; ++i) live += set_sizes_host[i] > 0;
+    mix(guidance_scales_host, sizeof(float) * live);
+  }
+  const void* ptrs[4] = {noise_tok, z, order, x_out};  // baked into the gather / scatter nodes of the pass graph
+  mix(ptrs, sizeof(ptrs));
+  const int64_t shape[4] = {B, Bx, N, (int64_t)num_sets};
+  mix(shape, sizeof(shape));
+  std::unique_lock<std::mutex> lock(h->graph_mutex);
+  LoopGraph* e = nullptr;
+  for (LoopGraph& c : h->graphs)
+    if (c.key_hash == hash && c.ws == workspace && c.M == -1 && c.S == num_steps) e = &c;
+  if (e != nullptr && e->exec != nullptr) {
+    NOVA_CHECK_CUDA(cudaGraphLaunch(e->exec, s));
+    count_launch((int)e->launches);
+    e->last_use = ++h->graph_clock;
+    return NOVA_OK;
+  }
+  if (e == nullptr) {  // first sight: remember the key, run the sets eagerly (each may replay its own loop graph)
+    LoopGraph c{};
+    c.key_hash = hash; c.ws = workspace; c.M = -1; c.Mx = Bx; c.n = N; c.S = num_steps; c.last_use = ++h->graph_clock;
+    h->graphs.push_back(c);
+    lock.unlock();
+    return run_sets(s);
+  }
+  // second sight: capture every launch of every set into one graph (inside a capture sample_impl enqueues eagerly)
+  const uint64_t key = e->key_hash;
+  lock.unlock();
+  const int64_t before = nova_launch_count();
+  NOVA_CHECK_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = run_sets(h->capture_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
+  const int64_t captured = nova_launch_count() - before;
+  count_launch(-(int)captured);  // nothing ran yet
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t ie = cudaSuccess;
+  if (rc == NOVA_OK && ce == cudaSuccess && graph != nullptr) ie = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  lock.lock();
+  e = nullptr;
+  for (LoopGraph& c : h->graphs)
+    if (c.key_hash == key && c.ws == workspace && c.M == -1 && c.S == num_steps) e = &c;
+  if (rc != NOVA_OK || ce != cudaSuccess || ie != cudaSuccess || exec == nullptr) {
+    if (rc == NOVA_OK) set_error("nova_head_generate_sets: graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ie));
+    cudaGetLastError();
+    if (e) h->graphs.erase(h->graphs.begin() + (e - h->graphs.data()));
+    if (exec) cudaGraphExecDestroy(exec);
+    return rc != NOVA_OK ? rc : NOVA_ERR_CUDA;
+  }
+  if (e == nullptr) {  // evicted meanwhile: run once without caching
+    NOVA_CHECK_CUDA(cudaGraphLaunch(exec, s));
+    count_launch((int)captured);
+    cudaStreamSynchronize(s);
+    cudaGraphExecDestroy(exec);
+    return NOVA_OK;
+  }
+  e->exec = exec;
+  e->launches = captured;
+  e->last_use = ++h->graph_clock;
+  NOVA_CHECK_CUDA(cudaGraphLaunch(exec, s));
+  count_launch((int)captured);
+  return NOVA_OK;
 }

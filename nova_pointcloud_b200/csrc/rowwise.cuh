@@ -67,16 +67,27 @@ temb_fc2_kernel(const float* __restrict__ hidden, int R, const float* __restrict
 }
 
 // ------------------------------------------------------------------ gather rows by pred_ids
+// The ids of cloud b, token slot j: ptr[(b % batch) * ld + j].  A plain (B, n) pred_ids tensor is {ptr, n, B}; the
+// on-device set scheduler passes a window of the (Bx, N) generation order: {order + first, N, Bx}, which also serves
+// the guidance passes (clouds Bx.. repeat the ids of clouds 0..Bx-1).
+struct IdsView {
+  const int64_t* ptr;
+  int64_t ld, batch;
+  __device__ __forceinline__ int64_t at(int64_t b, int64_t j, int64_t fallback) const {
+    return ptr ? ptr[(b % batch) * ld + j] : fallback;
+  }
+};
+
 // dst[b*n + j, :] = src[b*N + ids[b*n + j], :]   (W elements per row, 8 per thread)
 template <typename T>
-__global__ void gather_rows_kernel(const T* __restrict__ src, const int64_t* __restrict__ ids, T* __restrict__ dst,
+__global__ void gather_rows_kernel(const T* __restrict__ src, const IdsView ids, T* __restrict__ dst,
                                    int64_t B, int64_t N, int64_t n, int W, uint32_t* bad_ids) {
   const int64_t vec_per_row = W / 8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n * vec_per_row) return;
   const int64_t row = i / vec_per_row, v = i % vec_per_row;
   const int64_t b = row / n;
-  int64_t tok = ids ? ids[row] : row % n;
+  int64_t tok = ids.at(b, row - b * n, row % n);
   if (tok < 0 || tok >= N) {  // out-of-range id: never index with it (the reference's gather raises); flag and read token 0
     if (bad_ids && v == 0) *bad_ids = 0xBAD1D5u;
     tok = 0;
@@ -87,14 +98,14 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, const int64_t* __r
 }
 // small fp32 rows (token latent, T values): dst[b*n+j, :] = src[(b % Bx)*N + ids[b*n+j], :]
 static __global__ void
-gather_tok_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids,
+gather_tok_kernel(const float* __restrict__ src, const IdsView ids,
                                   float* __restrict__ dst, int64_t B, int64_t Bx, int64_t N, int64_t n, int T,
                                   uint32_t* bad_ids) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n * T) return;
   const int64_t row = i / T, c = i % T;
   const int64_t b = row / n;
-  int64_t tok = ids ? ids[row] : row % n;
+  int64_t tok = ids.at(b, row - b * n, row % n);
   if (tok < 0 || tok >= N) {
     if (bad_ids && c == 0) *bad_ids = 0xBAD1D5u;
     tok = 0;
@@ -870,13 +881,13 @@ unpred_sumsq_kernel(const float* __restrict__ noise, const float* __restrict__ x
 
 // out[b, tok, :] for predicted tokens <- x_sel;  (pred_ids == nullptr: plain copy)
 static __global__ void
-scatter_tok_kernel(const float* __restrict__ x_sel, const int64_t* __restrict__ ids,
+scatter_tok_kernel(const float* __restrict__ x_sel, const IdsView ids,
                                    float* __restrict__ out, int64_t Bx, int64_t N, int64_t n, int T, uint32_t* bad_ids) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bx * n * T) return;
   const int64_t row = i / T, c = i % T;
   const int64_t b = row / n;
-  const int64_t tok = ids ? ids[row] : row % n;
+  const int64_t tok = ids.at(b, row - b * n, row % n);
   if (tok < 0 || tok >= N) {  // never write through an out-of-range id
     if (bad_ids && c == 0) *bad_ids = 0xBAD1D5u;
     return;

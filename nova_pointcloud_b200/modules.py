@@ -188,6 +188,16 @@ class DiffusionMLP(nn.Module):
             return v
         return tok.to(v.dtype).scatter(1, pred_ids.expand(-1, -1, v.size(-1)), v)
 
+    def generate_tokens(self, noise_tok, z, order, set_sizes, timesteps, sigmas, guidance_scales=(), guidance_trunc=0.0,
+                        image_guidance_scale=0.0, spatiotemporal_guidance_scale=0.0) -> torch.Tensor:
+        """The whole set-by-set pass on the device (one library call): every set denoises its window of ``order``."""
+        h = self.handle()
+        return torch.ops.nova_b200.head_generate_sets(noise_tok.float(), z.to(self.dtype), order, h.id,
+                                                      [int(v) for v in set_sizes], [float(t) for t in timesteps],
+                                                      [float(s) for s in sigmas], [float(v) for v in guidance_scales],
+                                                      float(guidance_trunc), float(image_guidance_scale),
+                                                      float(spatiotemporal_guidance_scale))
+
     def sample_tokens(self, noise_tok, z, timesteps, sigmas, pred_ids=None, guidance_scale=1.0, guidance_trunc=0.0,
                       guidance_renorm=1.0, image_guidance_scale=0.0, spatiotemporal_guidance_scale=0.0) -> torch.Tensor:
         """Fused denoise loop on token layout: (Bx,N,T) fp32 noise -> (Bx,N,T) fp32 sample.

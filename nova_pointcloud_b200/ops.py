@@ -51,7 +51,7 @@ class HeadHandle:
         self.dtype = dtype
         self.cfg = HeadConfig(depth, width, cond_width, token_dim, _DTYPES[dtype])
         self._h = C.c_void_p()
-        self._ws: Dict[int, torch.Tensor] = {}
+        self._ws: Dict[object, torch.Tensor] = {}
         with torch.cuda.device(self.device):
             check(_lib.lib().nova_head_create(C.byref(self.cfg), C.byref(self._h)), "nova_head_create")
         self.id = HeadHandle._next_id
@@ -92,6 +92,19 @@ class HeadHandle:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
+
+    def staging(self, name: str, shape, dtype) -> torch.Tensor:
+        """A handle-owned buffer with a stable address per (stream, name): the whole-pass CUDA graph of
+        nova_head_generate_sets bakes its input / output pointers in, so they are staged through these."""
+        key = (torch.cuda.current_stream(self.device).cuda_stream, name)
+        buf = self._ws.get(key)
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        if buf is None or buf.dtype != dtype or buf.numel() < numel:
+            buf = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self._ws[key] = buf
+        return buf[:numel].view(*shape)
 
     def close(self):
         if self._h:
@@ -192,6 +205,59 @@ def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[tor
 
 @head_sample.register_fake
 def _(noise_tok, z, pred_ids, handle, timesteps, sigmas, guidance_scale, guidance_trunc, guidance_renorm,
+      image_guidance_scale=0.0, spatiotemporal_guidance_scale=0.0):
+    return noise_tok.new_empty(noise_tok.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("nova_b200::head_generate_sets", mutates_args=(), device_types="cuda")
+def head_generate_sets(noise_tok: torch.Tensor, z: torch.Tensor, order: torch.Tensor, handle: int, set_sizes: Sequence[int],
+                       timesteps: Sequence[float], sigmas: Sequence[float], guidance_scales: Sequence[float],
+                       guidance_trunc: float, image_guidance_scale: float = 0.0,
+                       spatiotemporal_guidance_scale: float = 0.0) -> torch.Tensor:
+    """The whole set-by-set pass in one library call, (Bx, N, T) fp32.  See nova_head_generate_sets in nova_b200.h.
+
+    ``guidance_scales``: the (decayed) guidance scale of every non-empty set; all <= 1 means no guidance."""
+    h = HeadHandle.get(handle)
+    _check_inputs(h, noise_tok, z, None)
+    S = len(timesteps)
+    if len(sigmas) != S + 1:
+        raise NovaError(f"sigmas must have len(timesteps)+1 = {S + 1} entries; got {len(sigmas)}")
+    noise_tok = noise_tok.contiguous().float()
+    z = z.contiguous()
+    B, N = z.shape[0], z.shape[1]
+    Bx = noise_tok.shape[0]
+    if order.dim() != 2 or tuple(order.shape) != (Bx, N) or order.dtype != torch.int64:
+        raise NovaError(f"order must be int64 (Bx={Bx}, N={N}); got {tuple(order.shape)} {order.dtype}")
+    order = order.contiguous()
+    sizes = [int(v) for v in set_sizes]
+    live = [v for v in sizes if v > 0]
+    scales = [float(v) for v in guidance_scales]
+    guided = any(v > 1 for v in scales)
+    if guided and len(scales) != len(live):
+        raise NovaError(f"guidance_scales needs one entry per non-empty set ({len(live)}); got {len(scales)}")
+    c_sizes = (C.c_int32 * max(len(sizes), 1))(*sizes)
+    c_t = (C.c_float * max(S, 1))(*[float(v) for v in timesteps])
+    c_s = (C.c_double * (S + 1))(*[float(v) for v in sigmas])
+    c_g = (C.c_float * max(len(scales), 1))(*scales) if guided else None
+    g = Guidance(max(scales) if guided else 1.0, float(guidance_trunc), 1.0, float(image_guidance_scale),
+                 float(spatiotemporal_guidance_scale))
+    with torch.cuda.device(z.device):
+        # inputs and output go through handle-owned buffers: stable addresses let the library replay its pass graph
+        n_buf = h.staging("gen_noise", noise_tok.shape, torch.float32)
+        o_buf = h.staging("gen_order", order.shape, torch.int64)
+        x_buf = h.staging("gen_out", (Bx, N, h.cfg.token_dim), torch.float32)
+        n_buf.copy_(noise_tok)
+        o_buf.copy_(order)
+        x_buf.zero_()
+        ws = h.workspace(B * max(live, default=0), S)
+        check(_lib.lib().nova_head_generate_sets(h._h, _ptr(n_buf), _ptr(z), _ptr(o_buf), B, Bx, N, c_sizes, len(sizes),
+                                                 c_t, c_s, S, C.byref(g), c_g, _ptr(x_buf), _ptr(ws), ws.numel(), _stream()),
+              "nova_head_generate_sets")
+        return x_buf.clone()
+
+
+@head_generate_sets.register_fake
+def _(noise_tok, z, order, handle, set_sizes, timesteps, sigmas, guidance_scales, guidance_trunc,
       image_guidance_scale=0.0, spatiotemporal_guidance_scale=0.0):
     return noise_tok.new_empty(noise_tok.shape, dtype=torch.float32)
 

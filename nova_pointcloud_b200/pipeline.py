@@ -91,11 +91,17 @@ def denoise(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler, z: t
 def generate_sets(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler, z: torch.Tensor, shape,
                   num_preds: Sequence[int], guidance_scaler: Optional[GuidanceScaler] = None,
                   generator: Optional[torch.Generator] = None, order: Optional[torch.Tensor] = None,
-                  z_fn: Optional[Callable] = None) -> torch.Tensor:
-    """Set-by-set generation: every set draws fresh noise, denoises its tokens and accumulates.
+                  z_fn: Optional[Callable] = None, noise: str = "per_token") -> torch.Tensor:
+    """Set-by-set generation: every set starts from fresh noise, denoises its tokens and accumulates
+    (``generate_frame``, transformer_3d.py:123-133).  shape = (B,C,H*p,W*p).  Returns tokens (B,N,T).
 
-    shape = (B,C,H*p,W*p).  ``z_fn(x_tokens, set_index)`` may refresh the condition between sets
-    (the reference re-runs its encoder there); by default z is fixed.  Returns tokens (B,N,T).
+    With a fixed condition (``z_fn is None``) the whole pass is ONE library call: set scheduling, the ``pred_mask``
+    windows of the generation order, gathers and scatters all run on the device (``nova_head_generate_sets``, one CUDA
+    graph per pass).  ``noise="per_token"`` (default) draws ONE ``randn(shape)``: a set only ever reads the noise at
+    its own positions, so this has the distribution of the reference's fresh tensor per set; ``noise="per_set"`` keeps
+    the reference's generator call pattern (``states["noise"].normal_()`` once per set) and therefore its exact random
+    stream, at one library call per set.  ``z_fn(x_tokens, set_index)`` refreshes the condition between sets (the
+    reference re-runs its encoder there) -- a host-side break between sets, so that path also runs set by set.
     """
     gs = guidance_scaler or GuidanceScaler()
     B = shape[0]
@@ -103,14 +109,32 @@ def generate_sets(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler
     head.patch_embed.set_hw(torch.empty(shape, device="meta"))
     N = head.patch_embed.height * head.patch_embed.width
     order = partition.random_order(B, N, generator, device) if order is None else order
+    live = [int(n) for n in num_preds if n > 0]
+    if z_fn is None and noise == "per_token" and gs.guidance_renorm >= 1:
+        scales = []
+        for i in range(len(live)):  # decay_guidance_scale per non-empty set (transformer_3d.py:124)
+            gs.decay_guidance_scale((i + 1) / len(live))
+            scales.append(float(gs.guidance_scale))
+        if max(scales, default=1.0) > 1 and min(scales) <= 1:
+            raise NovaError("a guidance scale that decays to <= 1 inside one pass needs noise='per_set'")
+        first = torch.randn(shape, device=device, dtype=torch.float32, generator=generator)
+        tok = head.patch_embed.patchify(first)
+        scheduler._step_index = None
+        out = head.generate_tokens(tok, z, order, list(num_preds), scheduler.timesteps, scheduler.sigmas,
+                                   scales if max(scales, default=1.0) > 1 else (), gs.guidance_trunc,
+                                   gs.image_guidance_scale, gs.spatiotemporal_guidance_scale)
+        scheduler._step_index = len(scheduler.timesteps)
+        return out
+    if noise not in ("per_token", "per_set"):
+        raise NovaError(f"unknown noise mode {noise!r} (per_token | per_set)")
     sets = partition.split_order(order, list(num_preds))
     x_tok = torch.zeros(B, N, head.token_dim, device=device, dtype=torch.float32)
-    noise = torch.empty(shape, device=device, dtype=torch.float32)
+    buf = torch.empty(shape, device=device, dtype=torch.float32)
     for i, ids in enumerate(sets):
         gs.decay_guidance_scale((i + 1) / len(sets))
         zi = z if z_fn is None else z_fn(x_tok, i)
-        noise.normal_(generator=generator)
-        sample = denoise(head, scheduler, zi, noise, gs.clone(), generator, gs.expand(ids))
+        buf.normal_(generator=generator)
+        sample = denoise(head, scheduler, zi, buf, gs.clone(), generator, gs.expand(ids))
         idx = ids.expand(-1, -1, head.token_dim)
         x_tok.scatter_(1, idx, sample.gather(1, idx))  # x += sample * pred_mask (disjoint sets)
     return x_tok

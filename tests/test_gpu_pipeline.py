@@ -27,8 +27,8 @@ def test_pipeline_all_tokens_matches_oracle():
 
 @pytest.mark.parametrize("schedule", ["cosine", "subsets"])
 def test_set_by_set_generation_matches_oracle(schedule):
-    """Every set: fresh noise, denoise(pred_ids), accumulate -- replayed on the CPU oracle with the
-    same order and the same noise."""
+    """noise="per_set" (the reference's generator call pattern): every set fresh noise, denoise(pred_ids), accumulate
+    -- replayed on the CPU oracle with the same order and the same noise."""
     import nova_pointcloud_b200 as nb
 
     B, N = 2, 60
@@ -41,7 +41,7 @@ def test_set_by_set_generation_matches_oracle(schedule):
     gen = torch.Generator(device="cuda").manual_seed(3)
     order = nb.partition.random_order(B, N, gen)
     gen_state = gen.get_state()
-    tokens = nb.generate_sets(head, sched, z.cuda(), (B, 3, N, 1), sizes, None, gen, order=order)
+    tokens = nb.generate_sets(head, sched, z.cuda(), (B, 3, N, 1), sizes, None, gen, order=order, noise="per_set")
     # replay
     gen.set_state(gen_state)
     noise = torch.empty(B, 3, N, 1, device="cuda")
@@ -52,6 +52,63 @@ def test_set_by_set_generation_matches_oracle(schedule):
         idx = ids.cpu().expand(-1, -1, 3)
         want.scatter_(1, idx, s.gather(1, idx))
     assert relmax(tokens, want) < 5e-5
+
+
+@pytest.mark.parametrize("mode", ["plain", "cfg_decay", "img3"])
+def test_device_scheduled_sets_match_oracle_at_2048_tokens(mode):
+    """nova_head_generate_sets (one library call, one CUDA graph per pass): 64 cosine sets over 2048 tokens, set
+    windows of the generation order gathered / scattered on the device -- replayed set by set on the CPU oracle
+    (generate_frame's accumulate, transformer_3d.py:123-133) with the same order and the same per-token noise;
+    eager pass, graph capture and replays must agree bit for bit, also with new noise in the staged buffers."""
+    import nova_pointcloud_b200 as nb
+
+    B, N, steps = 2, 2048, 3
+    head, _, z, _, _ = make_case(1, 256, 64, B, N, 1)
+    sd = cpu_sd(head)
+    head = head.cuda()
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(steps)
+    sizes = nb.partition.cosine_num_preds(N, 64)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    order = nb.partition.random_order(B, N, gen)
+    kw, passes = {}, 1
+    if mode == "cfg_decay":
+        kw, passes = dict(guidance_scale=4.0, min_guidance_scale=2.0, guidance_trunc=300.0), 2
+    if mode == "img3":
+        kw, passes = dict(guidance_scale=3.0, image_guidance_scale=1.2), 3
+    g = torch.Generator().manual_seed(6)
+    zz = torch.cat([z] + [torch.randn(z.shape, generator=g) for _ in range(passes - 1)])
+    states, outs = [], []
+    for _ in range(3):  # eager, capture, replay
+        states.append(gen.get_state())
+        outs.append(nb.generate_sets(head, sched, zz.cuda(), (B, 3, N, 1), sizes, nb.GuidanceScaler(**kw), gen, order=order))
+    # the three passes drew different noise: replay each state through the eager per-set path for bit-identity ...
+    gen.set_state(states[0])
+    noise0 = torch.randn(B, 3, N, 1, device="cuda", generator=gen)
+    # ... and pass 0 through the oracle
+    live = [n for n in sizes if n > 0]
+    want = torch.zeros(B, N, 3)
+    gs = nb.GuidanceScaler(**kw)
+    for i, ids in enumerate(nb.partition.split_order(order, sizes)):
+        gs.decay_guidance_scale((i + 1) / len(live))
+        pid = torch.cat([ids.cpu()] * passes) if gs.guidance_scale > 1 else ids.cpu()
+        s = OL.denoise(sd, zz if gs.guidance_scale > 1 else z, noise0.cpu(), num_steps=steps, pred_ids=pid,
+                       guidance_scale=float(gs.guidance_scale), guidance_trunc=float(gs.guidance_trunc),
+                       image_guidance_scale=float(gs.image_guidance_scale))
+        idx = ids.cpu().expand(-1, -1, 3)
+        want.scatter_(1, idx, s.gather(1, idx))
+    assert relmax(outs[0], want) < 5e-5
+    for k in (1, 2):  # captured / replayed passes against the eager pass on the same noise
+        gen.set_state(states[k])
+        import os
+        os.environ["NOVA_B200_GRAPH"] = "0"
+        try:
+            h2 = nb.DiffusionMLP(1, 256, 64, patch_size=1, image_dim=3).eval().cuda()
+            h2.load_state_dict(head.state_dict())
+            eager = nb.generate_sets(h2, sched, zz.cuda(), (B, 3, N, 1), sizes, nb.GuidanceScaler(**kw), gen, order=order)
+        finally:
+            del os.environ["NOVA_B200_GRAPH"]
+        assert torch.equal(outs[k], eager), k
 
 
 def test_pipeline_autoregressive_call_and_train_pipeline_surface():
