@@ -549,7 +549,10 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const r
   const bool graphable = h->use_graphs && h->capture_stream != nullptr && S > 0 && !profile_enabled() &&
                          cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
   if (!graphable) {
-    NOVA_PROPAGATE(run_loop(s, false));
+    // inside the pass capture of nova_head_generate_sets (our own capture stream) the forked statistics branch is
+    // available exactly as in this function's own capture; for any other caller the loop stays serial
+    const bool ours = h->capture_stream != nullptr && s == h->capture_stream && cap == cudaStreamCaptureStatusActive;
+    NOVA_PROPAGATE(run_loop(s, ours));
   } else {
     uint64_t hash = 1469598103934665603ull;  // FNV-1a over everything the captured launches depend on
     auto mix = [&](const void* p, size_t nbytes) {
