@@ -33,13 +33,36 @@ struct AdaLNArgs {
   bf16* gate = nullptr;      // [M, ldg], columns N - 2 * features
   int64_t ldg = 0;
   int features = 0;          // D: mod tiles cover 2 D weight rows
+  // x came out of an EPI_TAIL epilogue: its LayerNorm statistics are `n_parts` partials [n_parts][M] of (mean_t, M2_t)
+  // (one per 256-column tile) instead of rowstats
+  const float2* parts = nullptr;
+  int n_parts = 0;
+};
+
+// The block tail fused into the gate GEMM (diffusion_mlp.py:53):  x <- x + (LN(u; eps 1e-5) * gamma + beta) * g,
+// g = a Wg^T + bg.  u's statistics arrive as partials from the fc2 epilogue, the new x's leave as partials.
+struct TailArgs {
+  const bf16* u = nullptr;    // [M, ldu] fc2 output
+  int64_t ldu = 0;
+  bf16* x = nullptr;          // [M, ldx] residual stream, updated in place
+  int64_t ldx = 0;
+  const float* gamma = nullptr;  // [N]
+  const float* beta = nullptr;   // [N]
+  const float2* u_parts = nullptr;  // [n_parts][M]: one per 256-column tile of fc2
+  float2* x_parts = nullptr;        // [2 n_parts][M]: one per 128-column half tile (two epilogue warp sets)
+  int n_parts = 0;                  // N / 256
 };
 
 // C[M,N] = epi(A[M,K] W[N,K]^T + bias), bf16 in / bf16 out, epi = EPI_BIAS | EPI_BIAS_SILU.
 // cta_group: 0 = automatic (CTA pairs once there are at least 2 x 128 rows), 1, 2.
 // reverse_m: walk the row blocks in descending order (see EpiParams::reverse_m).
+// part_out (EPI_BIAS, N a multiple of 256): also emit [N / 256][M] partial LayerNorm statistics of the rounded outputs.
 int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,
-           int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false);
+           int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false, float2* part_out = nullptr);
+
+// gate GEMM with the block tail in its epilogue (CTA pairs, 256-column tiles; M > 128, N a multiple of 256)
+int launch_tail(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, const TailArgs& tail, int M, int N,
+                int K, cudaStream_t stream, bool reverse_m = false);
 
 // AdaLN statistics GEMM with the modulation fused into the epilogue:
 //   W [2 features + gate_cols, K] packed per 128 features as [scale | shift], then gate rows;

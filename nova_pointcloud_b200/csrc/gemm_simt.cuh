@@ -9,8 +9,9 @@
 
 namespace nova {
 
-// EPI_ADALN exists on the tcgen05 kernel only (AdaLN statistics GEMM with the modulation fused in).
-enum Epilogue : int { EPI_BIAS = 0, EPI_BIAS_SILU = 1, EPI_ADALN = 2 };
+// EPI_ADALN and EPI_TAIL exist on the tcgen05 kernel only (AdaLN statistics GEMM with the modulation fused in; gate
+// GEMM with the block tail x += LN_aff(u) * gate fused in).
+enum Epilogue : int { EPI_BIAS = 0, EPI_BIAS_SILU = 1, EPI_ADALN = 2, EPI_TAIL = 3 };
 
 namespace simt {
 

@@ -35,28 +35,42 @@ constexpr int UMMA_K = 16;  // BM, BK, BN_FULL: gemm_api.cuh; tile columns BN ar
 constexpr int A_STAGE_BYTES = BM * BK * 2;                // 16 KB
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+// EPI_TAIL runs 8 epilogue warps (two per TMEM lane quarter, each set taking one half of the tile's columns): its
+// epilogue costs ~13 instructions per element.  The epilogue code below is written for either count; for EPI_ADALN
+// 8 warps measured 11 % SLOWER (38.6 vs 34.7 ms of AdaLN GEMMs per cfg2 pass), so it stays at 4.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_TAIL ? 8 : 4; }
+__host__ __device__ constexpr int num_threads(int epi) { return 128 + 32 * epi_warps(epi); }
 constexpr int TMEM_COLS = 512;
 constexpr int C_CHUNK = 64;                               // output columns per TMA store (128 B rows)
 constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;             // one warp's 32 x 64 bf16 sub-tile: 4 KB
 
 // Per-CTA shared-memory plan for cta_group CG (1: one CTA per 128x256 tile, 2: a CTA pair per
 // 256x256 tile, each CTA holding its 128 rows of A and HALF of the W tile).
-template <int CG, int BN>
+template <int CG, int BN, bool TAIL = false>
 struct Plan {
   static_assert(BN == 64 || BN == 128 || BN == 256, "tile columns: 64 / 128 (small M: more, shorter tiles) or 256");
   static constexpr int B_ROWS = BN / CG;                         // W rows this CTA loads per stage
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;          // BN = 256: 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // BN = 256: 48 KB / 32 KB
   static constexpr int RING = 192 * 1024 / STAGE_BYTES;          // up to 192 KB of operand ring ...
-  static constexpr int STAGES = RING > 8 ? 8 : RING;             // ... in at most 8 stages (4 / 6 at BN = 256)
-  static constexpr int OFF_CSTAGE = STAGES * STAGE_BYTES;        // 4 warps x 2 buffers x 4 KB
+  // ... in at most 8 stages (4 / 6 at BN = 256).  EPI_TAIL gives 64 KB of the ring to the staged u / x chunks.
+  static constexpr int STAGES = TAIL ? (128 * 1024 / STAGE_BYTES) : (RING > 8 ? 8 : RING);
+  // EPI_TAIL: 2 buffers x {u chunk, x chunk} of 128 rows x 64 columns (16 KB each), filled by TMA, in front of the
+  // C staging; a warp copies its rows of a chunk into registers and hands the buffer straight back to the producer
+  static constexpr int T_CHUNK_BYTES = BM * C_CHUNK * 2;         // 16 KB
+  static constexpr int T_BUF_BYTES = 2 * T_CHUNK_BYTES;          // u + x
+  static constexpr int OFF_TAIL = STAGES * STAGE_BYTES;
+  static constexpr int OFF_CSTAGE = OFF_TAIL + (TAIL ? 2 * T_BUF_BYTES : 0);  // 4 warps x 2 buffers x 4 KB
   static constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;  // one BN fp32 bias tile
-  static constexpr int OFF_BAR = OFF_BIAS + BN_FULL * 4;
+  // EPI_TAIL: + one tile of (gamma, beta) as bf16 pairs (exact for a bf16 head: its norm2 parameters ARE bf16); with
+  // 225 KB of shared memory in use there is next to no L1 left, so per-column constants must not come through it
+  static constexpr int OFF_BAR = OFF_BIAS + BN_FULL * 4 * (TAIL ? 2 : 1);
   // 230 656 B: with the 1 KB the hardware reserves per CTA this leaves >= 1 KB of the SM's 228 KB, so a
   // CTA of a shared-memory-free kernel (the HBM-bound row kernels, launched on a second stream) can be
   // co-resident with a persistent GEMM CTA and its memory traffic overlaps the MMAs.
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static constexpr int UMMA_M = BM * CG;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory plan exceeds 227 KB");
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -147,7 +161,8 @@ __device__ __forceinline__ void tma_store_wait_read() {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int THREADS = 128>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -277,7 +292,44 @@ struct EpiParams {
   // Row-block order: consecutive kernels of a step alternate between ascending and descending row blocks, so a
   // kernel starts on the rows its producer wrote LAST -- the part of a 100 MB activation still in the 126 MB L2.
   int reverse_m;
+  // ---- deferred LayerNorm statistics (the block tail fused into the gate GEMM, EPI_TAIL):
+  // a row's statistics travel as `parts` partials [parts][M] of (mean_t, M2_t), one per 256-column tile of the
+  // producer; the consumer merges them (Chan) -- no kernel ever needs a full row.
+  //   EPI_BIAS  : part_out != nullptr: also emit the partials of the (bf16-rounded) outputs      (fc2 -> u statistics)
+  //   EPI_ADALN : stats_parts > 0: rowstats holds `stats_parts` partials of x instead of (mean, rstd)
+  //   EPI_TAIL  : g = a Wg^T + bg (rounded to bf16 like the stored gate it replaces);
+  //               x <- x + (LN(u; part_in, eps 1e-5) * gamma + beta) * g   (diffusion_mlp.py:53), u and x staged by TMA
+  //               through tmap_c2 / tmap_c3, x stored through tmap_c; part_out = partials of the new (rounded) x
+  const float2* part_in;
+  int stats_parts;
+  float2* part_out;
+  const float* gamma;  // [N] norm2 weight / bias (EPI_TAIL)
+  const float* beta;
 };
+
+// merge `parts` equal-sized partials (mean_t, M2_t over n_t values each) of one row -> (mean, rstd)
+__device__ __forceinline__ void merge_partials(const float2* part, int parts, int64_t M, int64_t row, float n_t, float eps,
+                                               float& mean, float& rstd) {
+  float ms[16], m2 = 0.f, msum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < parts) {
+      const float2 v = part[static_cast<int64_t>(t) * M + row];
+      ms[t] = v.x;
+      msum += v.x;
+      m2 += v.y;
+    }
+  }
+  mean = msum / static_cast<float>(parts);
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < parts) {
+      const float d = ms[t] - mean;
+      m2 = fmaf(n_t * d, d, m2);
+    }
+  }
+  rstd = rsqrtf(m2 / (n_t * static_cast<float>(parts)) + eps);
+}
 
 __device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
   uint4 r;
@@ -288,12 +340,13 @@ __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w 
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 template <int EPI, int CG, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
-            const EpiParams p, uint32_t* dbg) {
-  using P = Plan<CG, BN>;
+            const __grid_constant__ CUtensorMap tmap_c3, const EpiParams p, uint32_t* dbg) {
+  using P = Plan<CG, BN, EPI == EPI_TAIL>;
   static_assert(EPI != EPI_ADALN || BN == BN_FULL, "the AdaLN epilogue pairs 128 scale + 128 shift columns per tile");
+  static_assert(EPI != EPI_TAIL || BN == BN_FULL, "the tail epilogue works on 256-column tiles");
   constexpr int STAGES = P::STAGES, STAGE_BYTES = P::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = smem_raw;
@@ -309,6 +362,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P::OFF_BAR + 8 * (2 * STAGES + 4));
+  // EPI_TAIL: full / empty barriers of the two staged {u, x} chunk buffers
+  auto tail_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };
+  auto tail_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };
 
   pdl_trigger();  // the next kernel may be scheduled as soon as resources free up; it waits for our completion itself
 #ifdef NOVA_GEMM_TIMELINE  // diagnostic build (scripts/profile_gemm_timeline.py): SM-clock stamps of CTA 0 in the debug words
@@ -328,7 +384,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
-    if (EPI == EPI_ADALN) prefetch_tmap(&tmap_c2);
+    if (EPI == EPI_ADALN || EPI == EPI_TAIL) prefetch_tmap(&tmap_c2);
+    if (EPI == EPI_TAIL) prefetch_tmap(&tmap_c3);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -337,7 +394,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), CG * 4 * 32);  // every epilogue thread of every CTA of the group arrives
+      mbar_init(tempty_bar(b), CG * epi_warps(EPI) * 32);  // every epilogue thread of every CTA of the group arrives
+      if (EPI == EPI_TAIL) {
+        mbar_init(tail_full(b), 1);   // the tail producer's arrive.expect_tx
+        mbar_init(tail_empty(b), 4);  // one arrival per epilogue warp once it has copied its rows out
+      }
     }
     fence_barrier_init();
   }
@@ -407,39 +468,75 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
       }
     }
+  } else if (EPI == EPI_TAIL && warp == 3) {
+    if (lane == 0) {  // ------------------------------------------------ tail producer: {u, x} chunks of my 128 rows
+      int tb = 0;
+      uint32_t tphase = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
+        const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
+        // chunk order 0, 2, 1, 3: buffer 0 feeds the epilogue warps of the left column half (chunks 0, 1), buffer 1
+        // those of the right half (chunks 2, 3)
+        for (int k = 0; k < BN / C_CHUNK; ++k) {
+          const int cc = (k & 1) * 2 + (k >> 1);
+          mbar_wait(tail_empty(tb), tphase ^ 1u, dbg, 0x700u | tb);
+          const uint32_t dst = base + P::OFF_TAIL + static_cast<uint32_t>(tb) * P::T_BUF_BYTES;
+          mbar_expect_tx(tail_full(tb), P::T_BUF_BYTES);
+          tma_load_2d(&tmap_c2, tail_full(tb), dst, n_idx + cc * C_CHUNK, m_idx);                     // u chunk
+          tma_load_2d(&tmap_c3, tail_full(tb), dst + P::T_CHUNK_BYTES, n_idx + cc * C_CHUNK, m_idx);  // x chunk
+          if (++tb == 2) { tb = 0; tphase ^= 1u; }
+        }
+      }
+    }
   } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue (every CTA: its 128 rows)
     const int q = warp & 3;  // TMEM lane quarter this warp may access == its 32-row slice of the tile
     const int tid_e = threadIdx.x - EPI_WARP0 * 32;
-    const uint32_t cbuf = base + P::OFF_CSTAGE + static_cast<uint32_t>(q) * 2u * C_BUF_BYTES;
+    // C staging: 4 warps x 2 buffers of 4 KB; EPI_TAIL: 8 warps x 1 buffer
+    constexpr bool WIDE_EPI = epi_warps(EPI) == 8;
+    const int half = WIDE_EPI ? (warp - EPI_WARP0) >> 2 : 0;  // which half of the tile's columns this warp set takes
+    const uint32_t cbuf = base + P::OFF_CSTAGE + (WIDE_EPI ? static_cast<uint32_t>(warp - EPI_WARP0) * C_BUF_BYTES
+                                                           : static_cast<uint32_t>(q) * 2u * C_BUF_BYTES);
     float* bias_all = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     int buf = 0, cpar = 0;
     uint32_t buf_phase = 0;
+    int tb = 0;           // EPI_TAIL: staged {u, x} buffer in use
+    uint32_t tphase = 0;
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
       const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
       float* bias_s = bias_all;
-      epi_bar_sync();  // every epilogue warp has finished reading the previous tile's bias
-      for (int j = tid_e; j < BN; j += 128)
+      epi_bar_sync<32 * epi_warps(EPI)>();  // every epilogue warp has finished reading the previous tile's bias
+      for (int j = tid_e; j < BN; j += 32 * epi_warps(EPI)) {
         bias_s[j] = (p.bias != nullptr && n_idx + j < p.N) ? __ldg(p.bias + n_idx + j) : 0.f;
-      epi_bar_sync();  // bias tile visible to the 4 epilogue warps
+        if (EPI == EPI_TAIL)
+          reinterpret_cast<uint32_t*>(bias_s + BN_FULL)[j] =
+              n_idx + j < p.N ? pack_bf16x2(__ldg(p.gamma + n_idx + j), __ldg(p.beta + n_idx + j)) : 0u;
+      }
+      epi_bar_sync<32 * epi_warps(EPI)>();  // bias tile visible to the epilogue warps
       const int tile_n = tile % num_n;
       const int m0 = m_idx + q * 32;
       const bool mod_tile = EPI == EPI_ADALN && tile_n < p.n_mod_tiles;
       // AdaLN modulation tile: this thread's 128 features of x and its row statistics do not depend on the
       // MMA, so they are requested BEFORE waiting for the accumulator and land while the tile is computed.
-      uint4 xv[EPI == EPI_ADALN ? 16 : 1];
+      constexpr int KPW = WIDE_EPI ? 1 : 2;  // 64-feature groups of a modulation tile per warp (set)
+      uint4 xv[EPI == EPI_ADALN ? 8 * KPW : 1];  // my features of x: [64 half KPW, .. + 64 KPW) of the tile's 128
       float mean = 0.f, rstd = 0.f;
       if (mod_tile) {
         const int row = m0 + lane;
         const bool valid = row < p.M;
-        const bf16* xrow = p.x + static_cast<int64_t>(valid ? row : 0) * p.ldx + tile_n * 128;
+        const bf16* xrow = p.x + static_cast<int64_t>(valid ? row : 0) * p.ldx + tile_n * 128 + half * 64 * KPW;
 #pragma unroll
-        for (int c = 0; c < (EPI == EPI_ADALN ? 16 : 1); ++c)
+        for (int c = 0; c < (EPI == EPI_ADALN ? 8 * KPW : 1); ++c)
           xv[c] = p.x != nullptr ? ld_global_nc_v4(xrow + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
-          const float2 st2 = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(row));
-          mean = st2.x;
-          rstd = st2.y;
+          if (p.stats_parts > 0) {  // x was produced by an EPI_TAIL epilogue: merge its per-tile partials
+            merge_partials(p.part_in, p.stats_parts, p.M, row, static_cast<float>(p.n_mod_tiles * 128 / p.stats_parts), 1e-6f,
+                           mean, rstd);
+          } else {
+            const float2 st2 = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(row));
+            mean = st2.x;
+            rstd = st2.y;
+          }
         }
       }
       mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf);
@@ -450,61 +547,146 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // ---- TMEM columns [0,128) = scale, [128,256) = shift of features f0..f0+127
         const int f0 = tile_n * 128;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {  // 64 features -> one staging buffer -> one TMA store
-          if (m0 >= p.M) break;
-          if (lane == 0) tma_store_wait_read<1>();
+        for (int kk = 0; kk < KPW; ++kk) {  // 64 features -> one staging buffer -> one TMA store
+          const int k = half * KPW + kk;
+          if (m0 < p.M) {
+            if (lane == 0) {  // the store that last used this staging buffer has read it
+              if (WIDE_EPI) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            const uint32_t cb = cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES;
+            const uint32_t dst = cb + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+            for (int sc = 0; sc < 2; ++sc) {  // 32-feature sub-chunks keep the register footprint bounded
+              const int fo = 64 * k + 32 * sc;  // feature offset inside the tile
+              uint32_t rs[32], rh[32];
+              tmem_ld_32x32(t_row + fo, rs);
+              tmem_ld_32x32(t_row + 128 + fo, rh);
+              tmem_ld_wait();
+              const float* bsc = bias_s + fo;
+              const float* bsh = bias_s + 128 + fo;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 xq = xv[EPI == EPI_ADALN ? (kk * 2 + sc) * 4 + c : 0];
+                const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+                uint32_t w[4];
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                  const int e = c * 8 + 2 * hh;
+                  const float s0 = __uint_as_float(rs[e]) + bsc[e], s1 = __uint_as_float(rs[e + 1]) + bsc[e + 1];
+                  const float h0 = __uint_as_float(rh[e]) + bsh[e], h1 = __uint_as_float(rh[e + 1]) + bsh[e + 1];
+                  const float y0 = fmaf((bf16_lo(xw[hh]) - mean) * rstd, 1.0f + s0, h0);
+                  const float y1 = fmaf((bf16_hi(xw[hh]) - mean) * rstd, 1.0f + s1, h1);
+                  w[hh] = pack_bf16x2(y0, y1);
+                }
+                st_shared_v4(dst + (static_cast<uint32_t>((sc * 4 + c) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, cb, f0 + 64 * k, m0);
+              tma_store_commit();
+            }
+            cpar ^= 1;
+          }
+        }
+      } else if (EPI == EPI_TAIL) {
+        // ---- gate tile with the block tail fused in: x <- x + (LN(u) * gamma + beta) * g   (diffusion_mlp.py:53)
+        // warps 4-7 take columns [0, 128) of the tile (chunks 0, 1; staged buffer 0), warps 8-11 columns [128, 256)
+        const int row = m0 + lane;
+        const bool valid = row < p.M;
+        float mu = 0.f, ru = 0.f;
+        if (valid) merge_partials(p.part_in, p.stats_parts, p.M, row, static_cast<float>(p.N / p.stats_parts), 1e-5f, mu, ru);
+        float c0 = 0.f, s1 = 0.f, s2 = 0.f;  // statistics of the new (rounded) x over my half tile, about its first value
+        const uint32_t* gb_s = reinterpret_cast<const uint32_t*>(bias_s + BN_FULL);
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+          const int cc = half * 2 + k;
+          const int n0 = n_idx + cc * C_CHUNK;
+          // my rows of the staged {u, x} chunk -> registers, then the buffer goes straight back to the producer
+          mbar_wait(tail_full(half), tphase, dbg, 0x800u | half);
+          tphase ^= 1u;  // each buffer serves one chunk per half tile: its phase flips every use
+          const uint32_t ub = base + P::OFF_TAIL + static_cast<uint32_t>(half) * P::T_BUF_BYTES +
+                              static_cast<uint32_t>(q * 32 + lane) * 128u;
+          uint4 uq[8], xq[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t off = static_cast<uint32_t>(c ^ (lane & 7)) << 4;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(uq[c].x), "=r"(uq[c].y), "=r"(uq[c].z), "=r"(uq[c].w) : "r"(ub + off));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xq[c].x), "=r"(xq[c].y), "=r"(xq[c].z), "=r"(xq[c].w) : "r"(ub + P::T_CHUNK_BYTES + off));
+          }
           __syncwarp();
-          const uint32_t dst = cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
+          if (lane == 0) mbar_arrive(tail_empty(half));
+          if (m0 >= p.M || n0 >= p.N) continue;  // warp-uniform: nothing of this sub-tile is in bounds
+          if (lane == 0) tma_store_wait_read<0>();  // my single staging buffer: its last store (a chunk ago) has read it
+          __syncwarp();
+          const uint32_t dst = cbuf + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
-          for (int sc = 0; sc < 2; ++sc) {  // 32-feature sub-chunks keep the register footprint bounded
-            const int fo = 64 * k + 32 * sc;  // feature offset inside the tile
-            uint32_t rs[32], rh[32];
-            tmem_ld_32x32(t_row + fo, rs);
-            tmem_ld_32x32(t_row + 128 + fo, rh);
+          for (int hc = 0; hc < 2; ++hc) {  // 32 accumulator columns at a time keeps the register footprint bounded
+            uint32_t ra[32];
+            tmem_ld_32x32(t_row + cc * C_CHUNK + hc * 32, ra);
             tmem_ld_wait();
-            const float* bsc = bias_s + fo;
-            const float* bsh = bias_s + 128 + fo;
+            const float* bs = bias_s + cc * C_CHUNK + hc * 32;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 xq = xv[EPI == EPI_ADALN ? (k * 2 + sc) * 4 + c : 0];
-              const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int c = hc * 4 + c4;
+              const uint4 gb0 = *reinterpret_cast<const uint4*>(gb_s + cc * C_CHUNK + c * 8);      // (gamma, beta) pairs
+              const uint4 gb1 = *reinterpret_cast<const uint4*>(gb_s + cc * C_CHUNK + c * 8 + 4);
+              const uint32_t gbw[8] = {gb0.x, gb0.y, gb0.z, gb0.w, gb1.x, gb1.y, gb1.z, gb1.w};
+              const uint32_t uw[4] = {uq[c].x, uq[c].y, uq[c].z, uq[c].w};
+              const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
               uint32_t w[4];
 #pragma unroll
-              for (int hh = 0; hh < 4; ++hh) {
-                const int e = c * 8 + 2 * hh;
-                const float s0 = __uint_as_float(rs[e]) + bsc[e], s1 = __uint_as_float(rs[e + 1]) + bsc[e + 1];
-                const float h0 = __uint_as_float(rh[e]) + bsh[e], h1 = __uint_as_float(rh[e + 1]) + bsh[e + 1];
-                const float y0 = fmaf((bf16_lo(xw[hh]) - mean) * rstd, 1.0f + s0, h0);
-                const float y1 = fmaf((bf16_hi(xw[hh]) - mean) * rstd, 1.0f + s1, h1);
-                w[hh] = pack_bf16x2(y0, y1);
+              for (int h = 0; h < 4; ++h) {
+                const int e = c4 * 8 + 2 * h;
+                // every instruction counts here (the SM's four schedulers run this next to the MMAs): the gate stays in
+                // fp32 (it is no longer a stored bf16 tensor) and the statistics take the values before rounding
+                const float g0 = __uint_as_float(ra[e]) + bs[e], g1 = __uint_as_float(ra[e + 1]) + bs[e + 1];
+                const float l0 = fmaf((bf16_lo(uw[h]) - mu) * ru, bf16_lo(gbw[2 * h]), bf16_hi(gbw[2 * h]));
+                const float l1 = fmaf((bf16_hi(uw[h]) - mu) * ru, bf16_lo(gbw[2 * h + 1]), bf16_hi(gbw[2 * h + 1]));
+                const float y0 = fmaf(l0, g0, bf16_lo(xw[h])), y1 = fmaf(l1, g1, bf16_hi(xw[h]));
+                w[h] = pack_bf16x2(y0, y1);
+                if (k == 0 && c == 0 && h == 0) c0 = y0;
+                const float d0 = y0 - c0, d1 = y1 - c0;
+                s1 += d0 + d1;
+                s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
               }
-              st_shared_v4(dst + (static_cast<uint32_t>((sc * 4 + c) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+              st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
             }
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_c, cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES, f0 + 64 * k, m0);
+            tma_store_2d(&tmap_c, cbuf, n0, m0);
             tma_store_commit();
           }
-          cpar ^= 1;
+        }
+        if (valid && p.part_out != nullptr) {  // one partial per 128-column half tile
+          const float nt = static_cast<float>(BN / 2);
+          p.part_out[static_cast<int64_t>(tile_n * 2 + half) * p.M + row] = make_float2(c0 + s1 / nt, s2 - s1 * s1 / nt);
         }
       } else {
         // ---- plain tile: bias (+SiLU); for EPI_ADALN these are the gate tiles, written through tmap_c2
         const CUtensorMap* out_map = EPI == EPI_ADALN ? &tmap_c2 : &tmap_c;
         const int out_n = EPI == EPI_ADALN ? (tile_n - p.n_mod_tiles) * BN : n_idx;
         const int out_cols = EPI == EPI_ADALN ? p.N - p.n_mod_tiles * BN : p.N;
+        const bool want_parts = EPI == EPI_BIAS && p.part_out != nullptr;  // fc2: partial LayerNorm statistics of u
+        float c0 = 0.f, s1 = 0.f, s2 = 0.f;
+        constexpr int CPW = (BN / C_CHUNK) / (WIDE_EPI ? 2 : 1);  // chunks per warp set
 #pragma unroll 1
-        for (int cc = 0; cc < BN / C_CHUNK; ++cc) {
+        for (int cc = half * CPW; cc < (half + 1) * CPW; ++cc) {
           const int n0 = out_n + cc * C_CHUNK;
           if (m0 >= p.M || n0 >= out_cols) break;  // warp-uniform: nothing of this sub-tile is in bounds
           uint32_t ra[32], rb[32];
           tmem_ld_32x32(t_row + cc * C_CHUNK, ra);
           tmem_ld_32x32(t_row + cc * C_CHUNK + 32, rb);
-          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this staging buffer has read it
+          if (lane == 0) {  // the store that last used this staging buffer has read it
+            if (WIDE_EPI) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
           __syncwarp();
           tmem_ld_wait();
-          const uint32_t dst = cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
+          const uint32_t dst = cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
           const float* bs = bias_s + cc * C_CHUNK;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks of this thread's 128 B row, XOR-swizzled
@@ -516,16 +698,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               float x1 = __uint_as_float(e < 32 ? ra[(e + 1) & 31] : rb[(e + 1) & 31]) + bs[e + 1];
               if (EPI == EPI_BIAS_SILU) { x0 = silu(x0); x1 = silu(x1); }
               w[h] = pack_bf16x2(x0, x1);
+              if (want_parts) {  // statistics of what is stored (rounded), about the tile's first value
+                const float y0 = bf16_lo(w[h]), y1 = bf16_hi(w[h]);
+                if (cc == 0 && c == 0 && h == 0) c0 = y0;
+                const float d0 = y0 - c0, d1 = y1 - c0;
+                s1 += d0 + d1;
+                s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+              }
             }
             st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(out_map, cbuf + static_cast<uint32_t>(cpar) * C_BUF_BYTES, n0, m0);
+            tma_store_2d(out_map, cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES, n0, m0);
             tma_store_commit();
           }
           cpar ^= 1;
+        }
+        if (want_parts && m0 + lane < p.M) {
+          const float nt = static_cast<float>(BN);
+          p.part_out[static_cast<int64_t>(tile_n) * p.M + (m0 + lane)] = make_float2(c0 + s1 / nt, s2 - s1 * s1 / nt);
         }
       }
       tcgen05_fence_before();
@@ -549,31 +742,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ---------------------------------------------------------------- host side (declarations: gemm_api.cuh)
 template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
-               int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false) {
-  using P = Plan<CG, BN>;
+               int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false,
+               float2* part_out = nullptr, const TailArgs* tail = nullptr) {
+  using P = Plan<CG, BN, EPI == EPI_TAIL>;
   static std::atomic<unsigned long long> attr_done{0ull};  // one bit per device
   NOVA_PROPAGATE(ensure_smem_attr(reinterpret_cast<const void*>(gemm_kernel<EPI, CG, BN>), P::SMEM_BYTES, &attr_done));
-  CUtensorMap ta, tb, tc_, tc2;
+  CUtensorMap ta, tb, tc_, tc2, tc3;
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
   NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, P::B_ROWS));
   EpiParams p{};
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.reverse_m = reverse_m ? 1 : 0;
+  p.part_out = part_out;
   if (EPI == EPI_ADALN) {
     // C = h [M, features] fed by the mod tiles; gate [M, N - 2 features] fed by the remaining tiles
     NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, ada->features, ldc, 32));
     const int gate_cols = N - 2 * ada->features;
     if (gate_cols > 0) NOVA_PROPAGATE(make_tmap_kmajor(&tc2, ada->gate, M, gate_cols, ada->ldg, 32));
     else tc2 = tc_;
+    tc3 = tc_;
     p.x = ada->x; p.ldx = ada->ldx; p.rowstats = ada->rowstats; p.n_mod_tiles = 2 * ada->features / BN;
+    p.part_in = ada->parts; p.stats_parts = ada->n_parts;
+  } else if (EPI == EPI_TAIL) {
+    NOVA_PROPAGATE(make_tmap_kmajor(&tc_, tail->x, M, N, tail->ldx, 32));    // new x: stores of 32 x 64 sub-tiles
+    NOVA_PROPAGATE(make_tmap_kmajor(&tc2, tail->u, M, N, tail->ldu, BM));    // staged u chunks: 128 x 64
+    NOVA_PROPAGATE(make_tmap_kmajor(&tc3, tail->x, M, N, tail->ldx, BM));    // staged x chunks
+    p.part_in = tail->u_parts; p.stats_parts = tail->n_parts; p.part_out = tail->x_parts;
+    p.gamma = tail->gamma; p.beta = tail->beta;
   } else {
     NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, N, ldc, 32));
     tc2 = tc_;
+    tc3 = tc_;
   }
   const int tiles = static_cast<int>(ceil_div(M, BM * CG) * ceil_div(N, BN));
   const int groups = tiles < num_sms() / CG ? tiles : num_sms() / CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(num_threads(EPI));
   cfg.dynamicSmemBytes = P::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -585,7 +789,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG, BN>, ta, tb, tc_, tc2, p, debug_word()));
+  NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG, BN>, ta, tb, tc_, tc2, tc3, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
@@ -596,10 +800,10 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
 //   gemm_silu.cu (NOVA_GEMM_TU == 1): EPI_BIAS_SILU kernels,   gemm_adaln.cu (NOVA_GEMM_TU == 2): EPI_ADALN kernels.
 template <int EPI>
 int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
-                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m) {
+                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out = nullptr) {
 #define NOVA_GEMM_CASE(G, B) \
   if (cta_group == G && bn == B) \
-    return launch_epi<EPI, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m);
+    return launch_epi<EPI, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m, part_out);
   NOVA_GEMM_CASE(2, 256) NOVA_GEMM_CASE(1, 256) NOVA_GEMM_CASE(2, 128) NOVA_GEMM_CASE(1, 128) NOVA_GEMM_CASE(2, 64)
   NOVA_GEMM_CASE(1, 64)
 #undef NOVA_GEMM_CASE
@@ -607,7 +811,7 @@ int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const f
   return NOVA_ERR_INVALID;
 }
 int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
-                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m);
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out);
 int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m);
 
@@ -620,13 +824,15 @@ int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const fl
 
 #if NOVA_GEMM_TU == 0
 int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
-                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m) {
-  return launch_plain<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m);
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out) {
+  return launch_plain<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m, part_out);
 }
 
 int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,
-           int K, int epi, cudaStream_t stream, int cta_group, bool reverse_m) {
+           int K, int epi, cudaStream_t stream, int cta_group, bool reverse_m, float2* part_out) {
   if (M <= 0 || N <= 0) return NOVA_OK;
+  NOVA_REQUIRE(part_out == nullptr || (epi == EPI_BIAS && N % BN_FULL == 0),
+               "tcgen05 gemm: partial statistics need the bias epilogue and N a multiple of %d", BN_FULL);
   NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tcgen05 gemm: K, lda, ldw must be multiples of 8");
   NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0,
@@ -638,9 +844,10 @@ int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* 
   const int units = num_sms() / cta_group;
   const int64_t row_blocks = ceil_div(M, BM * cta_group);
   int bn = BN_FULL;
-  if (tile_columns_override() > 0) bn = tile_columns_override();
+  if (part_out != nullptr) bn = BN_FULL;  // one partial per 256-column tile
+  else if (tile_columns_override() > 0) bn = tile_columns_override();
   else if (row_blocks * ceil_div(N, 256) * 2 <= units) bn = row_blocks * ceil_div(N, 128) * 2 <= units ? 64 : 128;
-  return epi == EPI_BIAS ? launch_bias(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m)
+  return epi == EPI_BIAS ? launch_bias(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m, part_out)
                          : launch_silu(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m);
 }
 #endif
@@ -665,6 +872,19 @@ int launch_adaln(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const f
 }
 
 #endif  // NOVA_GEMM_TU == 2
+
+#if NOVA_GEMM_TU == 3
+int launch_tail(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, const TailArgs& tail, int M, int N,
+                int K, cudaStream_t stream, bool reverse_m) {
+  if (M <= 0 || N <= 0) return NOVA_OK;
+  NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && tail.ldu % 8 == 0 && tail.ldx % 8 == 0,
+               "tcgen05 tail gemm: K and leading dimensions must be multiples of 8");
+  NOVA_REQUIRE(N % BN_FULL == 0 && tail.n_parts == N / BN_FULL && tail.n_parts <= 8,
+               "tcgen05 tail gemm: N must be a multiple of %d (<= 2048) with one u partial per tile", BN_FULL);
+  NOVA_REQUIRE(tail.u && tail.x && tail.gamma && tail.beta && tail.u_parts && tail.x_parts, "tcgen05 tail gemm: null operand");
+  return launch_epi<EPI_TAIL, 2>(A, lda, W, ldw, bias, nullptr, 0, M, N, K, stream, nullptr, reverse_m, nullptr, &tail);
+}
+#endif  // NOVA_GEMM_TU == 3
 
 }  // namespace tc
 }  // namespace nova

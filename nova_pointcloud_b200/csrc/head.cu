@@ -120,6 +120,11 @@ struct nova_head {
   // Wide dataflow, bf16: everything after the statistics GEMM (patch embed, 6 x (fc1, fc2, block tail + next
   // modulation), head + Euler: 19 dependent launches) runs as ONE cluster kernel (chain_tcgen05.cu) in which a
   // cluster of 8 CTAs owns 128 rows for the whole chain.  NOVA_B200_CHAIN=0 restores the launch chain (bit-identical).
+  // Fused dataflow: the block tail x += LN_aff(u2) * gate runs in the epilogue of the gate GEMM (the AdaLN GEMM of a
+  // block is split into its modulation part, N = 2 D, and its gate part, N = D, which moves behind fc2); LayerNorm
+  // statistics travel between kernels as per-tile partials.  No separate HBM-bound row kernel per block, and the gate
+  // tensor never exists.  NOVA_B200_FUSE_TAIL=0 restores the resid kernel.
+  bool fuse_tail = true;
   bool use_chain = true;
   bool chained(int64_t rows) const {
     return use_chain && cfg.dtype == NOVA_BF16 && !use_simt_gemm && !fused(rows) && rows <= chain::profitable_rows(cfg.width);
@@ -149,6 +154,7 @@ struct Carver {
 struct Workspace {
   void *c, *a, *x, *h, *u1, *u2, *st, *zsel, *gate;
   float *v, *xsel, *thid, *temb, *tdev, *rstat;
+  float2 *uparts, *xparts;  // fused dataflow: per-tile partial LayerNorm statistics of u2 / of the residual stream
   size_t bytes;
 };
 
@@ -168,6 +174,9 @@ Workspace carve(const nova_head* h, void* base, int64_t rows, int steps) {
     w.st = nullptr;
     w.gate = cv.take(M * D * es);
     w.rstat = static_cast<float*>(cv.take(M * 2 * sizeof(float)));
+    const size_t parts = D / 256;
+    w.uparts = static_cast<float2*>(cv.take(parts * M * sizeof(float2)));
+    w.xparts = static_cast<float2*>(cv.take(2 * parts * M * sizeof(float2)));
   } else {
     w.st = cv.take(AB * M * h->n_ada() * es);
     w.gate = nullptr;
@@ -281,11 +290,20 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
   // Row-block direction alternates from launch to launch: each kernel starts on the rows its producer wrote last.
   bool rev = h->alternate_rows;  // embed wrote x ascending
   auto flip = [&]() { const bool r = rev; if (h->alternate_rows) rev = !rev; return r; };
+  const int parts = D / 256;
+  const bool tail = h->fuse_tail && M > tc::BM && depth > 0;  // the tail epilogue runs on CTA pairs
   for (int i = 0; i < depth; ++i) {
-    {
+    const bf16* w_blk = w_il + (size_t)3 * i * D * D;
+    const float* b_blk = h->b_ada_il + (size_t)3 * i * D;
+    if (tail) {  // modulation part only (N = 2 D); x's statistics: embed's (mean, rstd) for block 0, partials afterwards
       ProfileScope ps(KC_GEMM_ADA, s);
-      NOVA_PROPAGATE(tc::launch_adaln(a, D, w_il + (size_t)3 * i * D * D, D, h->b_ada_il + (size_t)3 * i * D, hh, D, ada,
-                                      (int)M, 3 * D, D, s, 0, flip()));
+      tc::AdaLNArgs mod = ada;
+      mod.gate = nullptr;
+      if (i > 0) { mod.parts = w.xparts; mod.n_parts = 2 * parts; }
+      NOVA_PROPAGATE(tc::launch_adaln(a, D, w_blk, D, b_blk, hh, D, mod, (int)M, 2 * D, D, s, 0, flip()));
+    } else {
+      ProfileScope ps(KC_GEMM_ADA, s);
+      NOVA_PROPAGATE(tc::launch_adaln(a, D, w_blk, D, b_blk, hh, D, ada, (int)M, 3 * D, D, s, 0, flip()));
     }
     {
       ProfileScope ps(KC_GEMM_FC, s);
@@ -295,15 +313,24 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
     {
       ProfileScope ps(KC_GEMM_FC, s);
       NOVA_PROPAGATE(tc::launch(u1, D, static_cast<const bf16*>(h->w_fc2[i]), D, h->b_fc2[i], u2, D, (int)M, D, D,
-                                EPI_BIAS, s, 0, flip()));
+                                EPI_BIAS, s, 0, flip(), tail ? w.uparts : nullptr));
     }
-    ProfileScope ps(KC_ROW, s);
-    NOVA_PROPAGATE(rw::resid_bf16(u2, x, gate, h->gamma[i], h->beta[i], x, w.rstat, M, D, (int)flip(), s));
+    if (tail) {  // gate part (N = D) + block tail in its epilogue
+      ProfileScope ps(KC_GEMM_ADA, s);
+      tc::TailArgs ta{};
+      ta.u = u2; ta.ldu = D; ta.x = x; ta.ldx = D; ta.gamma = h->gamma[i]; ta.beta = h->beta[i];
+      ta.u_parts = w.uparts; ta.x_parts = w.xparts; ta.n_parts = parts;
+      NOVA_PROPAGATE(tc::launch_tail(a, D, w_blk + (size_t)2 * D * D, D, b_blk + 2 * D, ta, (int)M, D, D, s, flip()));
+    } else {
+      ProfileScope ps(KC_ROW, s);
+      NOVA_PROPAGATE(rw::resid_bf16(u2, x, gate, h->gamma[i], h->beta[i], x, w.rstat, M, D, (int)flip(), s));
+    }
   }
   {
     ProfileScope ps(KC_GEMM_ADA, s);
     tc::AdaLNArgs fin = ada;
     fin.gate = nullptr;
+    if (tail) { fin.parts = w.xparts; fin.n_parts = 2 * parts; }
     NOVA_PROPAGATE(tc::launch_adaln(a, D, w_il + (size_t)3 * depth * D * D, D, h->b_ada_il + (size_t)3 * depth * D, hh,
                                     D, fin, (int)M, 2 * D, D, s, 0, flip()));
   }
@@ -690,6 +717,7 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   if (const char* env_wide = std::getenv("NOVA_B200_WIDE_ADA_ROWS")) h->wide_ada_rows = std::atoll(env_wide);
   if (const char* env_alt = std::getenv("NOVA_B200_ALTERNATE")) h->alternate_rows = std::atoi(env_alt) != 0;
   if (const char* env_chain = std::getenv("NOVA_B200_CHAIN")) h->use_chain = std::atoi(env_chain) != 0;
+  if (const char* env_tail = std::getenv("NOVA_B200_FUSE_TAIL")) h->fuse_tail = std::atoi(env_tail) != 0;
   const char* env_graph = std::getenv("NOVA_B200_GRAPH");
   h->use_graphs = env_graph == nullptr || std::atoi(env_graph) != 0;
   if (h->use_graphs && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
