@@ -53,7 +53,9 @@ struct Plan {
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;          // BN = 256: 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // BN = 256: 48 KB / 32 KB
   static constexpr int RING = 192 * 1024 / STAGE_BYTES;          // up to 192 KB of operand ring ...
-  // ... in at most 8 stages (4 / 6 at BN = 256).  EPI_TAIL gives 64 KB of the ring to the staged u / x chunks.
+  // ... in at most 8 stages (4 / 6 at BN = 256).  EPI_TAIL gives 64 KB of the ring to the staged u / x chunks
+  // (measured at cfg2: 4 stages instead of 6 for EVERY GEMM change nothing -- 34.1 / 23.8 ms of AdaLN / fc GEMMs per
+  // pass against 35.4 / 23.3; a 3-stage ring with 3 staged chunk buffers was 3 % slower than 4 + 2).
   static constexpr int STAGES = TAIL ? (128 * 1024 / STAGE_BYTES) : (RING > 8 ? 8 : RING);
   // EPI_TAIL: 2 buffers x {u chunk, x chunk} of 128 rows x 64 columns (16 KB each), filled by TMA, in front of the
   // C staging; a warp copies its rows of a chunk into registers and hands the buffer straight back to the producer
