@@ -200,6 +200,16 @@ NOVA_API int nova_local_density(const float* points, int64_t B, int64_t N, int32
                                 void* stream);
 NOVA_API int nova_softmax_interp(const float* targets, const float* points, int64_t B, int64_t S, int64_t N,
                                  float* out, void* stream);
+/*
+ * nova_farthest_point_sampling: points [B, N, 3], start_idx [B] int64 or NULL (= point 0) -> picked [B, num_samples]
+ *   int64: picked[0] = start, picked[i] = the point farthest (squared distance, lowest index on ties) from the
+ *   points picked so far.  This is the textbook algorithm farthest_point_sampling
+ *   (transformer_pointcloud_nova.py:100-125) is named after; the reference's own loop takes `min` over a distance
+ *   matrix that still holds its zero diagonal and therefore returns [start, 0, 0, ...] in exact arithmetic -- that
+ *   form needs no kernel (the Python mirror offers it as mode="reference").  N <= 14000.
+ */
+NOVA_API int nova_farthest_point_sampling(const float* points, const int64_t* start_idx, int64_t B, int64_t N,
+                                          int32_t num_samples, int64_t* picked, void* stream);
 
 /*
  * Training-mode arithmetic either side of the head, forward only.

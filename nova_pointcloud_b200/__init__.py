@@ -35,6 +35,7 @@ from .geometry import (  # noqa: F401
     compute_local_density,
     density_target_size,
     dynamic_partition,
+    farthest_point_sampling,
     feature_aware_interpolation,
     knn,
 )

@@ -22,7 +22,7 @@ EXPORTS = [
     "nova_head_sample", "nova_head_generate_sets", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
     "nova_debug_chain_timeline", "nova_debug_words_clear", "nova_comm_unique_id", "nova_comm_init_rank",
-    "nova_comm_destroy", "nova_allgather", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_add_noise", "nova_flow_loss",
+    "nova_comm_destroy", "nova_allgather", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_farthest_point_sampling", "nova_add_noise", "nova_flow_loss",
 ]
 
 
@@ -79,6 +79,8 @@ def _declare(lib):
     lib.nova_local_density.argtypes = [vp, i64, i64, i32, vp, vp]
     lib.nova_softmax_interp.restype = C.c_int
     lib.nova_softmax_interp.argtypes = [vp, vp, i64, i64, i64, vp, vp]
+    lib.nova_farthest_point_sampling.restype = C.c_int
+    lib.nova_farthest_point_sampling.argtypes = [vp, vp, i64, i64, i32, vp, vp]
     lib.nova_add_noise.restype = C.c_int
     lib.nova_add_noise.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.nova_flow_loss.restype = C.c_int

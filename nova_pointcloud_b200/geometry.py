@@ -12,10 +12,12 @@ The callers on the far side of the sampling path (SURVEY.md 8(f) #4,
 Distances come from ``torch.ops.nova_b200.{knn, local_density, softmax_interp}`` (exact difference form in
 fp32; the reference's ``torch.cdist`` uses the matrix form above 25 points, ~1e-5 absolute off).  CUDA only.
 
-``farthest_point_sampling`` (:100-125) is deliberately absent: the reference takes ``min`` over a distance
-matrix that still contains its zero diagonal, so in exact arithmetic every pick after the random start is
-index 0, and in fp32 the picks follow the rounding noise of ``torch.cdist``'s diagonal -- there is no
-behaviour to be identical to.
+* ``farthest_point_sampling(points, num_samples, start_indices=None, generator=None, mode="intended")`` -- :100-125.
+  The reference's loop takes ``min`` over a distance matrix that still contains its zero diagonal, so in exact
+  arithmetic every pick after the random start is index 0 (in fp32 the picks follow the rounding noise of
+  ``torch.cdist``'s diagonal).  ``mode="intended"`` runs the textbook algorithm the function is named after (CUDA
+  kernel ``nova_farthest_point_sampling``: arg-max of the running minimum squared distance, lowest index on ties);
+  ``mode="reference"`` returns the reference's exact-arithmetic result, ``[start, 0, 0, ...]``.
 """
 
 from __future__ import annotations
@@ -66,6 +68,34 @@ def feature_aware_interpolation(points, target_size: int, indices: Optional[torc
             raise NovaError("feature_aware_interpolation: indices must be target_size positions inside the cloud")
         out = torch.ops.nova_b200.softmax_interp(p[:, indices, :].contiguous(), p)
     return out[0] if single else out
+
+
+def farthest_point_sampling(points, num_samples: int, start_indices: Optional[torch.Tensor] = None,
+                            generator: Optional[torch.Generator] = None, mode: str = "intended",
+                            return_indices: bool = False):
+    """(B,N,3) -> (B,num_samples,3) (and the picked indices (B,num_samples) with ``return_indices``).
+
+    ``start_indices`` (B,) int64: the first pick of every cloud; drawn with ``torch.randint`` from ``generator`` when
+    absent, as the reference does (:106)."""
+    p, single = _as_cuda_batch(points)
+    B, N, _ = p.shape
+    if num_samples < 1:
+        raise NovaError(f"farthest_point_sampling: num_samples must be positive; got {num_samples}")
+    if start_indices is None:
+        gdev = generator.device if generator is not None else p.device
+        start_indices = torch.randint(0, N, (B,), generator=generator, device=gdev)
+    start = torch.as_tensor(start_indices, device=p.device, dtype=torch.int64).reshape(B)
+    if mode == "intended":
+        idx = torch.ops.nova_b200.farthest_point_sampling(p, start, int(num_samples))
+    elif mode == "reference":
+        idx = torch.zeros(B, num_samples, dtype=torch.int64, device=p.device)
+        idx[:, 0] = start
+    else:
+        raise NovaError(f"farthest_point_sampling: unknown mode {mode!r} (intended | reference)")
+    out = torch.gather(p, 1, idx.unsqueeze(-1).expand(-1, -1, 3))
+    if single:
+        out, idx = out[0], idx[0]
+    return (out, idx) if return_indices else out
 
 
 def dynamic_partition(points: torch.Tensor, k: int = 20, generator: Optional[torch.Generator] = None

@@ -370,6 +370,26 @@ def _(targets, points):
     return targets.new_empty(targets.shape, dtype=torch.float32)
 
 
+@torch.library.custom_op("nova_b200::farthest_point_sampling", mutates_args=(), device_types="cuda")
+def farthest_point_sampling(points: torch.Tensor, start: Optional[torch.Tensor], num_samples: int) -> torch.Tensor:
+    """(B,N,3), start (B,) int64 or None -> picked indices (B, num_samples) int64 (textbook FPS, see nova_b200.h)."""
+    points = _cloud3(points, "farthest_point_sampling")
+    B, N = points.shape[0], points.shape[1]
+    if start is not None and (start.dim() != 1 or start.shape[0] != B or start.dtype != torch.int64):
+        raise NovaError(f"farthest_point_sampling: start must be int64 (B={B},); got {tuple(start.shape)} {start.dtype}")
+    st = None if start is None else start.contiguous()
+    out = torch.empty(B, max(int(num_samples), 0), dtype=torch.int64, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().nova_farthest_point_sampling(_ptr(points), _ptr(st), B, N, int(num_samples), _ptr(out), _stream()),
+              "nova_farthest_point_sampling")
+    return out
+
+
+@farthest_point_sampling.register_fake
+def _(points, start, num_samples):
+    return points.new_empty((points.shape[0], num_samples), dtype=torch.int64)
+
+
 @torch.library.custom_op("nova_b200::add_noise", mutates_args=(), device_types="cuda")
 def add_noise(x: torch.Tensor, noise: torch.Tensor, sigma_table: torch.Tensor, t_table: torch.Tensor,
               t_idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

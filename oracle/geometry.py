@@ -59,6 +59,24 @@ def interpolate(points: np.ndarray, target_size: int, indices: np.ndarray) -> np
     return softmax_interp(points[:, np.asarray(indices)[:target_size], :], points)
 
 
+def farthest_point_sampling(points: np.ndarray, num_samples: int, start: int) -> np.ndarray:
+    """Textbook FPS on one cloud (N,3) float32 -> picked indices (num_samples,).
+
+    The algorithm transformer_pointcloud_nova.py:100-125 is named after (its own loop degenerates: see
+    nova_pointcloud_b200/geometry.py).  float32 arithmetic in the kernel's order -- exact differences, squares summed
+    left to right -- and ``np.argmax`` (first maximum), so the picks match the CUDA kernel bit for bit."""
+    p = np.asarray(points, dtype=np.float32)
+    d = np.full(p.shape[0], np.inf, dtype=np.float32)
+    picked = np.empty(num_samples, dtype=np.int64)
+    picked[0] = cur = int(start)
+    for i in range(1, num_samples):
+        diff = p - p[cur]
+        sq = diff * diff
+        d = np.minimum(d, (sq[:, 0] + sq[:, 1]) + sq[:, 2])
+        picked[i] = cur = int(np.argmax(d))
+    return picked
+
+
 def target_size(density_mean: float, num_points: int, num_subsets: int, density_factor: float = 0.5) -> int:
     base = num_points // num_subsets
     size = int(base * (1 + density_factor * (density_mean - 0.5)))

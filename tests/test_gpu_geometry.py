@@ -134,3 +134,43 @@ def test_dynamic_partition_and_target_size():
     dens = nb.compute_local_density(subsets[int(order[0])])
     size = nb.density_target_size(dens, 15000, 20)
     assert size == OG.target_size(float(dens.mean()), 15000, 20) and 100 <= size <= 1500
+
+
+@pytest.mark.parametrize("B,N,S", [(3, 200, 50), (2, 2048, 512), (1, 5, 5), (4, 1000, 1)])
+def test_farthest_point_sampling_matches_oracle_bit_for_bit(B, N, S):
+    """Textbook FPS (the algorithm transformer_pointcloud_nova.py:100-125 is named after): same picks as the numpy
+    float32 oracle, index for index; duplicated points exercise the lowest-index tie-break."""
+    import nova_pointcloud_b200 as nb
+    from oracle import geometry as OG
+
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    pts = torch.rand(B, N, 3, generator=g) * 2 - 1
+    if N >= 200:
+        pts[:, 150] = pts[:, 7]  # exact duplicates: equal distances everywhere
+        pts[:, 151] = pts[:, 7]
+    start = torch.randint(0, N, (B,), generator=g)
+    out, idx = nb.farthest_point_sampling(pts.cuda(), S, start_indices=start, return_indices=True)
+    assert out.shape == (B, S, 3) and idx.shape == (B, S)
+    for b in range(B):
+        want = OG.farthest_point_sampling(pts[b].numpy(), S, int(start[b]))
+        assert np.array_equal(idx[b].cpu().numpy(), want), b
+        assert torch.equal(out[b].cpu(), pts[b][torch.from_numpy(want)])
+    if S > 1 and N > S:  # property: picks are distinct points and the running minimum distance never grows
+        for b in range(B):
+            sel = pts[b][idx[b].cpu()]
+            assert len(set(idx[b].tolist())) == S or N >= 200  # duplicates may be picked last only
+            d = torch.cdist(sel, sel)
+            gaps = [float(d[i, :i].min()) for i in range(1, S)]
+            assert all(gaps[i] >= gaps[i + 1] - 1e-6 for i in range(len(gaps) - 1))
+
+
+def test_farthest_point_sampling_reference_mode_is_the_exact_arithmetic_result():
+    """mode="reference": the reference's loop in exact arithmetic picks [start, 0, 0, ...] (the zero diagonal wins every
+    min; tests/test_oracle_vs_reference.py::test_geometry_live shows it on the live function for exact distances)."""
+    import nova_pointcloud_b200 as nb
+
+    pts = torch.rand(2, 30, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    start = torch.tensor([5, 11])
+    out, idx = nb.farthest_point_sampling(pts, 4, start_indices=start, mode="reference", return_indices=True)
+    assert idx.cpu().tolist() == [[5, 0, 0, 0], [11, 0, 0, 0]]
+    assert torch.equal(out[:, 1:], pts[:, :1].expand(-1, 3, -1))
