@@ -153,6 +153,11 @@ int default_cta_group(int M) {
   return M > BM ? 2 : 1;  // a CTA pair needs more than one 128-row slab to be worth it
 }
 
+int pdl_epi_mask() {
+  static const int m = [] { const char* e = std::getenv("NOVA_B200_PDL_EPI_MASK"); return e ? std::atoi(e) : 7; }();  // default: bias, SiLU, AdaLN kinds; not the tail
+  return m;
+}
+
 int tile_columns_override() {
   const char* env = std::getenv("NOVA_B200_TILE_N");  // read per call: tests switch it between launches
   const int v = env ? std::atoi(env) : 0;
