@@ -231,6 +231,28 @@ NOVA_API int nova_flow_loss(const float* pred, const float* noise, const float* 
                             int64_t tokens, int32_t T, float* loss_tok, float* scratch2, void* stream);
 
 /*
+ * Training step of the head: forward with saved activations, then the full backward pass --
+ * what autograd does for the reference between Transformer3DModel.get_losses and loss.backward()
+ * (diffnext/models/transformers/transformer_3d.py:79-100) through DiffusionMLP.forward with per-token timesteps
+ * (diffnext/models/diffusion_mlp.py:56-99).  Rows are tokens: rows = batch x tokens, every row has its own timestep.
+ *
+ * nova_head_train_bytes:   bytes of the workspace both calls carve identically (saved activations + backward scratch).
+ * nova_head_train_forward: x_tok [rows, T] fp32 noisy latent (token layout), t [rows] fp32, z [rows, Dc] (handle
+ *                          dtype) -> v_out [rows, T] fp32; the activations the backward needs stay in `workspace`.
+ * nova_head_backward:      dv [rows, T] fp32 = dLoss/dv, with the SAME x_tok, z and workspace as the forward call ->
+ *                          grads[k] (fp32, reference state_dict shape of names[k], WRITTEN not accumulated; any subset
+ *                          of the 14 + 8*depth keys, NULL entries skipped) and dz_out [rows, Dc] (handle dtype) or NULL.
+ * Width must be a multiple of 256.  Matrix products run on the tcgen05 GEMM (bf16 handle) or the SIMT fp32 GEMM
+ * (fp32 parity handle); weight gradients split their reduction over the rows into one batched launch.
+ */
+NOVA_API size_t nova_head_train_bytes(const nova_head_t* h, int64_t rows);
+NOVA_API int nova_head_train_forward(const nova_head_t* h, const float* x_tok, const float* t, const void* z, int64_t rows,
+                                     float* v_out, void* workspace, size_t workspace_bytes, void* stream);
+NOVA_API int nova_head_backward(const nova_head_t* h, const float* dv, const float* x_tok, const void* z, int64_t rows,
+                                int32_t n_grads, const char* const* names, float* const* grads, void* dz_out,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Multi-GPU: clouds are sharded data-parallel over one process per GPU, weights replicated, no collective inside the
  * denoise loop; the ONE collective of the path is an all-gather of the generated points after the last Euler step.
  * NCCL is resolved at first use (dlopen of libnccl.so.2; inside a PyTorch process the already-loaded NCCL is used).

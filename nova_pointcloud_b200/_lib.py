@@ -85,6 +85,12 @@ def _declare(lib):
     lib.nova_add_noise.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.nova_flow_loss.restype = C.c_int
     lib.nova_flow_loss.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
+    lib.nova_head_train_bytes.restype = sz
+    lib.nova_head_train_bytes.argtypes = [vp, i64]
+    lib.nova_head_train_forward.restype = C.c_int
+    lib.nova_head_train_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, sz, vp]
+    lib.nova_head_backward.restype = C.c_int
+    lib.nova_head_backward.argtypes = [vp, vp, vp, vp, i64, i32, C.POINTER(C.c_char_p), C.POINTER(vp), vp, vp, sz, vp]
     lib.nova_launch_count.restype = i64
     lib.nova_launch_count.argtypes = []
     lib.nova_launch_count_reset.restype = None

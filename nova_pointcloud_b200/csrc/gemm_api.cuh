@@ -61,6 +61,11 @@ struct TailArgs {
 int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,
            int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false, float2* part_out = nullptr);
 
+// S = M / batch_m_rows independent GEMMs in one launch (the split-M weight gradients of train_bwd.cu):
+//   C[b] [batch_m_rows, N] = A[b] [batch_m_rows, K] W[b] [N, K]^T, all three stacked along their rows.
+int launch_batched(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, bf16* C, int64_t ldc, int M, int N, int K,
+                   int batch_m_rows, cudaStream_t stream);
+
 // gate GEMM with the block tail in its epilogue (CTA pairs, 256-column tiles; M > 128, N a multiple of 256)
 int launch_tail(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, const TailArgs& tail, int M, int N,
                 int K, cudaStream_t stream, bool reverse_m = false);

@@ -310,6 +310,10 @@ struct EpiParams {
   float2* part_out;
   const float* gamma;  // [N] norm2 weight / bias (EPI_TAIL)
   const float* beta;
+  // Batched form (weight gradients with the M-reduction split S ways, train_bwd.cu): A is S stacked [batch_m_rows, K]
+  // operands, W is S stacked [batch_w_rows, K] operands, and row block m of the stacked output multiplies the W slab
+  // of ITS batch.  batch_m_rows = 0: one ordinary GEMM.
+  int batch_m_rows, batch_w_rows;
 };
 
 // merge `parts` equal-sized partials (mean_t, M2_t over n_t values each) of one row -> (mean, rstd)
@@ -462,7 +466,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
         const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM;
-        const int n_idx = (tile % num_n) * BN + static_cast<int>(rank) * P::B_ROWS;  // CG == 2: my half of W
+        const int w_batch = p.batch_m_rows > 0 ? (m_tile * (BM * CG) / p.batch_m_rows) * p.batch_w_rows : 0;
+        const int n_idx = (tile % num_n) * BN + static_cast<int>(rank) * P::B_ROWS + w_batch;  // CG == 2: my half of W
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, dbg, 0x100u | stage);
           const uint32_t sa = base + stage * STAGE_BYTES;
@@ -819,14 +824,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false,
-               float2* part_out = nullptr, const TailArgs* tail = nullptr) {
+               float2* part_out = nullptr, const TailArgs* tail = nullptr, int batch_m_rows = 0, int batch_w_rows = 0) {
   using P = Plan<CG, BN, EPI == EPI_TAIL>;
   static std::atomic<unsigned long long> attr_done{0ull};  // one bit per device
   NOVA_PROPAGATE(ensure_smem_attr(reinterpret_cast<const void*>(gemm_kernel<EPI, CG, BN>), P::SMEM_BYTES, &attr_done));
   CUtensorMap ta, tb, tc_, tc2, tc3;
   NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
-  NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, N, K, ldw, P::B_ROWS));
+  // batched: W holds one [batch_w_rows, K] slab per batch (M / batch_m_rows of them)
+  NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, batch_m_rows > 0 ? static_cast<int64_t>(M / batch_m_rows) * batch_w_rows : N, K, ldw,
+                                  P::B_ROWS));
   EpiParams p{};
+  p.batch_m_rows = batch_m_rows; p.batch_w_rows = batch_w_rows;
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.reverse_m = reverse_m ? 1 : 0;
   p.part_out = part_out;
   if (EPI == EPI_ADALN) {
@@ -882,10 +890,12 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
 //   gemm_silu.cu (NOVA_GEMM_TU == 1): EPI_BIAS_SILU kernels,   gemm_adaln.cu (NOVA_GEMM_TU == 2): EPI_ADALN kernels.
 template <int EPI>
 int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
-                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out = nullptr) {
+                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out = nullptr,
+                 int batch_m_rows = 0, int batch_w_rows = 0) {
 #define NOVA_GEMM_CASE(G, B) \
   if (cta_group == G && bn == B) \
-    return launch_epi<EPI, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m, part_out);
+    return launch_epi<EPI, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m, part_out, nullptr, \
+                                 batch_m_rows, batch_w_rows);
   NOVA_GEMM_CASE(2, 256) NOVA_GEMM_CASE(1, 256) NOVA_GEMM_CASE(2, 128) NOVA_GEMM_CASE(1, 128) NOVA_GEMM_CASE(2, 64)
   NOVA_GEMM_CASE(1, 64)
 #undef NOVA_GEMM_CASE
@@ -893,7 +903,8 @@ int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const f
   return NOVA_ERR_INVALID;
 }
 int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
-                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out);
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out,
+                int batch_m_rows = 0, int batch_w_rows = 0);
 int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m);
 
@@ -906,8 +917,24 @@ int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const fl
 
 #if NOVA_GEMM_TU == 0
 int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
-                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out) {
-  return launch_plain<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m, part_out);
+                int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out,
+                int batch_m_rows, int batch_w_rows) {
+  return launch_plain<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m, part_out,
+                                batch_m_rows, batch_w_rows);
+}
+
+// S = M / batch_m_rows GEMMs in one launch: C[b] [batch_m_rows, N] = A[b] [batch_m_rows, K] W[b] [batch_w_rows = N, K]^T,
+// operands and outputs stacked along their rows (CTA pairs, 256-column tiles).
+int launch_batched(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, bf16* C, int64_t ldc, int M, int N, int K,
+                   int batch_m_rows, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return NOVA_OK;
+  NOVA_REQUIRE(batch_m_rows > 0 && batch_m_rows % (2 * BM) == 0 && M % batch_m_rows == 0,
+               "tcgen05 batched gemm: rows per batch must be a multiple of %d and divide M", 2 * BM);
+  NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "tcgen05 batched gemm: K and leading dimensions must be multiples of 8");
+  NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "tcgen05 batched gemm: operands must be 16-byte aligned");
+  return launch_bias(A, lda, W, ldw, nullptr, C, ldc, M, N, K, stream, 2, BN_FULL, false, nullptr, batch_m_rows, N);
 }
 
 int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,

@@ -30,6 +30,7 @@
 #include "gemm_api.cuh"
 #include "chain_api.cuh"
 #include "rowwise.cuh"
+#include "head_weights.cuh"
 
 using namespace nova;
 
@@ -915,6 +916,27 @@ extern "C" int nova_head_load(nova_head_t* h, int32_t n, const char* const* name
   NOVA_REQUIRE(seen == expected, "nova_head_load: got %d keys, the reference state_dict has %d", seen, expected);
   h->channels = channels;
   h->loaded = true;
+  return NOVA_OK;
+}
+
+int head_weights_view(const nova_head* h, nova::HeadWeightsView* out, const char* who) {
+  NOVA_REQUIRE(h != nullptr && out != nullptr, "%s: null handle", who);
+  if (!h->loaded) {
+    set_error("%s: weights not loaded", who);
+    return NOVA_ERR_NOT_LOADED;
+  }
+  nova::HeadWeightsView v{};
+  v.D = h->D(); v.Dc = h->Dc(); v.T = h->T(); v.depth = h->cfg.depth; v.channels = h->channels; v.dtype = h->cfg.dtype;
+  v.use_simt_gemm = h->use_simt_gemm;
+  v.w_c1 = h->w_c1; v.w_c2 = h->w_c2; v.w_ada = h->w_ada;
+  v.b_c1 = h->b_c1; v.b_c2 = h->b_c2; v.b_ada = h->b_ada;
+  for (int i = 0; i < h->cfg.depth; ++i) {
+    v.w_fc1[i] = h->w_fc1[i]; v.w_fc2[i] = h->w_fc2[i];
+    v.b_fc1[i] = h->b_fc1[i]; v.b_fc2[i] = h->b_fc2[i]; v.gamma[i] = h->gamma[i]; v.beta[i] = h->beta[i];
+  }
+  v.w_t1 = h->w_t1; v.b_t1 = h->b_t1; v.w_t2 = h->w_t2; v.b_t2 = h->b_t2;
+  v.w_patch = h->w_patch; v.b_patch = h->b_patch; v.w_head = h->w_head; v.b_head = h->b_head;
+  *out = v;
   return NOVA_OK;
 }
 

@@ -441,6 +441,51 @@ def _(pred, noise, x, weight):
     return pred.new_empty(pred.shape[:-1], dtype=torch.float32), pred.new_empty((2,), dtype=torch.float32)
 
 
+def head_train_forward(h: HeadHandle, x_tok: torch.Tensor, t: torch.Tensor, z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Training-mode forward over rows = tokens: x_tok (M, T) fp32, t (M,) fp32, z (M, Dc) in the head dtype ->
+    (v (M, T) fp32, workspace).  The workspace holds the saved activations; hand it to :func:`head_backward`.
+    See nova_head_train_forward in nova_b200.h."""
+    T, Dc = h.cfg.token_dim, h.cfg.cond_width
+    if x_tok.dim() != 2 or x_tok.shape[1] != T or z.dim() != 2 or z.shape[1] != Dc or z.shape[0] != x_tok.shape[0]:
+        raise NovaError(f"head_train_forward expects x_tok (M, {T}) and z (M, {Dc}); got {tuple(x_tok.shape)}, {tuple(z.shape)}")
+    if t.numel() != x_tok.shape[0]:
+        raise NovaError(f"head_train_forward expects one timestep per row; got {tuple(t.shape)} for {x_tok.shape[0]} rows")
+    if z.dtype != h.dtype or not z.is_cuda:
+        raise NovaError(f"z must be a CUDA tensor of the head's dtype {h.dtype}; got {z.dtype} on {z.device}")
+    x_tok, t, z = x_tok.contiguous().float(), t.contiguous().float().reshape(-1), z.contiguous()
+    M = x_tok.shape[0]
+    v = torch.empty(M, T, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        nbytes = max(int(_lib.lib().nova_head_train_bytes(h._h, M)), 256)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+        check(_lib.lib().nova_head_train_forward(h._h, _ptr(x_tok), _ptr(t), _ptr(z), M, _ptr(v), _ptr(ws), ws.numel(),
+                                                 _stream()), "nova_head_train_forward")
+    return v, ws
+
+
+def head_backward(h: HeadHandle, dv: torch.Tensor, x_tok: torch.Tensor, z: torch.Tensor, ws: torch.Tensor,
+                  shapes: Dict[str, Sequence[int]], want_dz: bool = True) -> Tuple[Dict[str, torch.Tensor], Optional[torch.Tensor]]:
+    """Backward of :func:`head_train_forward`: dv (M, T) fp32 -> ({state_dict key: fp32 gradient in the key's shape},
+    dz (M, Dc) in the head dtype or None).  ``shapes`` names the parameters whose gradients are wanted.
+    See nova_head_backward in nova_b200.h."""
+    x_tok, z, dv = x_tok.contiguous().float(), z.contiguous(), dv.contiguous().float()
+    M = x_tok.shape[0]
+    grads = {k: torch.empty(tuple(shp), dtype=torch.float32, device=z.device) for k, shp in shapes.items()}
+    dz = torch.empty_like(z) if want_dz else None
+    if M == 0:
+        for g in grads.values():
+            g.zero_()
+        return grads, dz
+    names = [k.encode() for k in grads]
+    n = len(names)
+    c_names = (C.c_char_p * n)(*names)
+    c_ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads.values()])
+    with torch.cuda.device(z.device):
+        check(_lib.lib().nova_head_backward(h._h, _ptr(dv), _ptr(x_tok), _ptr(z), M, n, c_names, c_ptrs, _ptr(dz), _ptr(ws),
+                                            ws.numel(), _stream()), "nova_head_backward")
+    return grads, dz
+
+
 def debug_gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: str, epilogue: str) -> torch.Tensor:
     """Test hook over nova_debug_gemm: epi(A W^T + bias) with the named GEMM kernel."""
     impl_id = {"simt": 0, "tcgen05_1cta": 1, "tcgen05_2cta": 2, "tcgen05": 3}[impl]

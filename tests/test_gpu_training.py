@@ -1,5 +1,6 @@
-"""GPU: training-mode forward (add_noise, per-token-timestep head, masked flow-matching loss) against the oracle and
-the committed output of the reference's own get_losses."""
+"""GPU: training mode of the head -- add_noise, the per-token-timestep forward, the masked flow-matching loss and the
+backward pass (nova_head_train_forward / nova_head_backward) -- against the oracle (torch autograd through
+oracle/head.py) and the committed output of the reference's own get_losses."""
 
 import os
 
@@ -7,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import cpu_sd
+from gpu_util import cpu_sd, record, relmax
 from oracle import training as OT
 
 pytestmark = pytest.mark.gpu
@@ -36,9 +37,10 @@ def test_get_losses_matches_reference_golden(golden_dir):
     d, sd = _golden(golden_dir)
     head = _head(sd, d["cfg"])
     sched = nb.FlowMatchEulerDiscreteScheduler(1000, shift=1.0)
-    out = nb.get_losses(head, sched, torch.from_numpy(d["z"]).cuda(), torch.from_numpy(d["x"]).cuda(),
-                        mask=torch.from_numpy(d["mask"]).cuda(), noise=torch.from_numpy(d["noise"]).cuda(),
-                        timesteps=torch.from_numpy(d["t_idx"]).cuda())
+    with torch.no_grad():  # evaluation: nova_head_forward + nova_flow_loss, nothing kept for a backward
+        out = nb.get_losses(head, sched, torch.from_numpy(d["z"]).cuda(), torch.from_numpy(d["x"]).cuda(),
+                            mask=torch.from_numpy(d["mask"]).cuda(), noise=torch.from_numpy(d["noise"]).cuda(),
+                            timesteps=torch.from_numpy(d["t_idx"]).cuda())
     want = float(d["loss"])
     assert abs(float(out["loss"]) - want) <= 1e-5 * abs(want)  # fp32 bar: 1e-5 relative
     ref = OT.get_losses(sd, torch.from_numpy(d["z"]), torch.from_numpy(d["x"]), torch.from_numpy(d["noise"]),
@@ -47,10 +49,127 @@ def test_get_losses_matches_reference_golden(golden_dir):
     assert float((got - ref["loss_per_token"]).abs().max()) <= 1e-5 * float(ref["loss_per_token"].abs().max())
     assert abs(float(out["weight_sum"]) - float(torch.from_numpy(d["mask"]).sum()) * 4) < 1e-3
     # bf16 head: same loss within the bf16 bar
-    out16 = nb.get_losses(_head(sd, d["cfg"], torch.bfloat16), sched, torch.from_numpy(d["z"]).cuda().bfloat16(),
-                          torch.from_numpy(d["x"]).cuda(), mask=torch.from_numpy(d["mask"]).cuda(),
-                          noise=torch.from_numpy(d["noise"]).cuda(), timesteps=torch.from_numpy(d["t_idx"]).cuda())
+    with torch.no_grad():
+        out16 = nb.get_losses(_head(sd, d["cfg"], torch.bfloat16), sched, torch.from_numpy(d["z"]).cuda().bfloat16(),
+                              torch.from_numpy(d["x"]).cuda(), mask=torch.from_numpy(d["mask"]).cuda(),
+                              noise=torch.from_numpy(d["noise"]).cuda(), timesteps=torch.from_numpy(d["t_idx"]).cuda())
     assert abs(float(out16["loss"]) - want) <= 2e-2 * abs(want)
+
+
+def _oracle_loss_and_grads(sd, z, x, noise, t_idx, mask, R):
+    """torch autograd through the oracle's restatement of get_losses (transformer_3d.py:81-95) on the CPU, fp32."""
+    leaves = {k: v.detach().clone().float().requires_grad_(True) for k, v in sd.items()}
+    zl = z.detach().clone().float().requires_grad_(True)
+    out = OT.get_losses(leaves, zl, x.float(), noise.float(), t_idx, mask, loss_repeat=R)
+    out["loss"].backward()
+    return float(out["loss"]), {k: v.grad for k, v in leaves.items()}, zl.grad
+
+
+def _train_case(depth, D, Dc, patch, chan, B, H, W, R, seed, dtype):
+    import nova_pointcloud_b200 as nb
+    from oracle import head as OH
+
+    sd = OH.init_state_dict(depth, D, Dc, patch, chan, seed=seed)
+    if dtype == torch.bfloat16:
+        sd = {k: v.bfloat16().float() for k, v in sd.items()}  # the oracle differentiates the weights the GPU head holds
+    g = torch.Generator().manual_seed(seed + 1)
+    N, T = H * W, patch * patch * chan
+    x = torch.randn(B, chan, H * patch, W * patch, generator=g)
+    z = torch.randn(B, N, Dc, generator=g)
+    if dtype == torch.bfloat16:
+        z = z.bfloat16().float()
+    mask = (torch.rand(B, N, 1, generator=g) < 0.7).float()
+    noise = torch.randn(R * B, N, T, generator=g)
+    t_idx = OT.sample_timesteps((R * B, N), generator=g)
+    head = nb.DiffusionMLP(depth, D, Dc, patch_size=patch, image_dim=chan).train()
+    head.load_state_dict(sd)
+    return sd, head.to("cuda", dtype), x, z, mask, noise, t_idx
+
+
+def _gpu_loss_and_grads(head, x, z, mask, noise, t_idx, R):
+    import nova_pointcloud_b200 as nb
+
+    sched = nb.FlowMatchEulerDiscreteScheduler(1000, shift=1.0)
+    head.zero_grad(set_to_none=True)
+    zc = z.to("cuda", head.dtype).requires_grad_(True)
+    out = nb.get_losses(head, sched, zc, x.cuda(), mask=mask.cuda(), loss_repeat=R, noise=noise.cuda(), timesteps=t_idx.cuda())
+    out["loss"].backward()
+    return float(out["loss"]), {k: p.grad.detach().float().cpu() for k, p in head.named_parameters()}, zc.grad.float().cpu()
+
+
+def test_backward_matches_autograd_fp32_on_the_reference_golden(golden_dir):
+    """The reference's own get_losses case (tests/golden/losses.npz): loss through the training-mode forward, and
+    every gradient of loss.backward() against autograd through the oracle -- fp32 handle, <= 1e-4 of each tensor's max
+    (measured values recorded under profiles/)."""
+    d, sd = _golden(golden_dir)
+    head = _head(sd, d["cfg"]).train()
+    z, x, mask = torch.from_numpy(d["z"]), torch.from_numpy(d["x"]), torch.from_numpy(d["mask"])
+    noise, t_idx = torch.from_numpy(d["noise"]), torch.from_numpy(d["t_idx"])
+    loss, grads, dz = _gpu_loss_and_grads(head, x, z, mask, noise, t_idx, 4)
+    want = float(d["loss"])
+    assert abs(loss - want) <= 1e-5 * abs(want)  # the reference's own number
+    _, ref, ref_dz = _oracle_loss_and_grads(sd, z, x, noise, t_idx, mask, 4)
+    assert set(grads) == set(ref)
+    worst = max(relmax(grads[k], ref[k]) for k in ref)
+    record("training backward fp32 (reference golden case): worst parameter gradient", worst)
+    for k in ref:
+        assert grads[k].shape == ref[k].shape and relmax(grads[k], ref[k]) <= 1e-4, k
+    assert relmax(dz, ref_dz) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 4e-2)])
+def test_backward_matches_autograd_two_blocks_patch2(dtype, tol):
+    """depth 2, patch 2 x 2 x 4 channels (T = 16: the Conv2d-layout weight gradient), Dc = 64, 150 rows (not a multiple
+    of anything), masked loss, loss_repeat 2.  bf16: against the fp32 oracle on the bf16-rounded weights."""
+    sd, head, x, z, mask, noise, t_idx = _train_case(2, 256, 64, 2, 4, 3, 5, 5, 2, 11, dtype)
+    loss, grads, dz = _gpu_loss_and_grads(head, x, z, mask, noise, t_idx, 2)
+    want, ref, ref_dz = _oracle_loss_and_grads(sd, z, x, noise, t_idx, mask, 2)
+    assert abs(loss - want) <= (1e-5 if dtype == torch.float32 else 2e-2) * abs(want)
+    errs = {k: relmax(grads[k], ref[k]) for k in ref}
+    record(f"training backward {str(dtype).split('.')[-1]} (depth 2, T 16, 150 rows): worst parameter gradient", max(errs.values()))
+    record(f"training backward {str(dtype).split('.')[-1]} (depth 2, T 16, 150 rows): dz", relmax(dz, ref_dz))
+    for k, e in errs.items():
+        assert e <= tol, (k, e)
+    assert relmax(dz, ref_dz) <= tol
+
+
+def test_backward_split_reduction_on_tensor_cores_matches_fp32_handle():
+    """4096 rows: the bf16 handle's weight gradients run as ONE batched tcgen05 launch over a split M-reduction
+    (tc::launch_batched); compared with the fp32 handle (SIMT GEMMs, itself pinned to autograd above) on the same
+    bf16-rounded weights.  Also: a repeat is bit-identical (deterministic reductions, no atomics)."""
+    sd, head16, x, z, mask, noise, t_idx = _train_case(2, 256, 64, 1, 3, 4, 32, 32, 1, 5, torch.bfloat16)
+    import nova_pointcloud_b200 as nb
+
+    head32 = nb.DiffusionMLP(2, 256, 64, patch_size=1, image_dim=3).train()
+    head32.load_state_dict(sd)
+    head32 = head32.cuda()
+    l16, g16, dz16 = _gpu_loss_and_grads(head16, x, z, mask, noise, t_idx, 1)
+    l16b, g16b, dz16b = _gpu_loss_and_grads(head16, x, z, mask, noise, t_idx, 1)
+    assert l16 == l16b and all(torch.equal(g16[k], g16b[k]) for k in g16) and torch.equal(dz16, dz16b)
+    l32, g32, dz32 = _gpu_loss_and_grads(head32, x, z, mask, noise, t_idx, 1)
+    assert abs(l16 - l32) <= 2e-2 * abs(l32)
+    errs = {k: relmax(g16[k], g32[k]) for k in g32}
+    record("training backward bf16 vs fp32 handle (4096 rows, split reduction): worst parameter gradient", max(errs.values()))
+    for k, e in errs.items():
+        assert e <= 4e-2, (k, e)
+    assert relmax(dz16, dz32) <= 4e-2
+
+
+def test_backward_only_requested_gradients_and_frozen_parameters():
+    """Frozen parameters get no gradient (and cost no GEMM); z without requires_grad gets none either."""
+    import nova_pointcloud_b200 as nb
+
+    sd, head, x, z, mask, noise, t_idx = _train_case(1, 256, 64, 1, 3, 2, 4, 4, 1, 3, torch.float32)
+    for k, p in head.named_parameters():
+        p.requires_grad_(k.startswith("blocks.0.proj"))
+    sched = nb.FlowMatchEulerDiscreteScheduler(1000, shift=1.0)
+    out = nb.get_losses(head, sched, z.cuda(), x.cuda(), loss_repeat=1, noise=noise.cuda(), timesteps=t_idx.cuda())
+    out["loss"].backward()
+    got = {k for k, p in head.named_parameters() if p.grad is not None}
+    assert got == {k for k, _ in head.named_parameters() if k.startswith("blocks.0.proj")}
+    _, ref, _ = _oracle_loss_and_grads(sd, z, x, noise, t_idx, None, 1)
+    for k in got:
+        assert relmax(dict(head.named_parameters())[k].grad, ref[k]) <= 1e-4
 
 
 def test_add_noise_bit_exact_and_scheduler_state():
