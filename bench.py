@@ -731,6 +731,40 @@ def main():
                                                                 "transformer_pointcloud_nova.py:81-89)"}
         except Exception as e:
             extras["geometry"] = {"error": str(e)[:300]}
+        try:  # training step: forward with saved activations + the full backward, cfg2's rows
+            from nova_pointcloud_b200 import ops as _ops
+
+            hh = head.handle()
+            Mt, Tt, Dct = B * N, hh.cfg.token_dim, hh.cfg.cond_width
+            xt_tr = torch.randn(Mt, Tt, device=dev, generator=gc)
+            tt_tr = torch.rand(Mt, device=dev, generator=gc) * 1000
+            zt_tr = z_d.reshape(Mt, Dct)
+            shapes_tr = {k: tuple(p.shape) for k, p in head.named_parameters()}
+
+            def train_step():
+                v_tr, ws_tr = _ops.head_train_forward(hh, xt_tr, tt_tr, zt_tr)
+                _ops.head_backward(hh, v_tr * 1e-3, xt_tr, zt_tr, ws_tr, shapes_tr, want_dz=True)
+
+            for _ in range(2):
+                train_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                train_step()
+            e1.record()
+            torch.cuda.synchronize()
+            tms = e0.elapsed_time(e1) / 3
+            fwd_flop = 2.0 * Mt * (256 * D + D * D + Dct * D + D * D + (3 * 6 + 2) * D * D + 12 * D * D + 2 * Tt * D)
+            extras["train_step"] = {
+                "value": Mt / (tms * 1e-3), "unit": "tokens/s", "ms": tms, "rows": Mt,
+                "tflops": 3.0 * fwd_flop / (tms * 1e-3) / 1e12,
+                "frac_of_sustained_bf16": 3.0 * fwd_flop / (tms * 1e-3) / 1e12 / peaks()["sustained"],
+                "what": "one training step of the head over %d tokens with per-token timesteps: nova_head_train_forward (saved "
+                        "activations) + nova_head_backward (all 14 + 8*depth parameter gradients and dz), bf16 tcgen05 GEMMs; "
+                        "FLOP = 3 x the forward's GEMM FLOP" % Mt}
+        except Exception as e:
+            extras["train_step"] = {"error": str(e)[:300]}
         try:  # the reference's algorithm as eager PyTorch on this GPU: the library-kernel bar
             with torch.no_grad():
                 ref_out = eager_library_sampler(head, sched, z_d, noise_d)

@@ -322,10 +322,40 @@ tail_bwd_kernel(const float* __restrict__ dxo, const AT* __restrict__ u2, const 
 }
 
 // ------------------------------------------------------------------ reductions over the M rows (deterministic)
-// partial[chunk][n] = sum over the chunk's rows of Y[r, n]
+// partial[chunk][n] = sum over the chunk's rows of Y[r, n].  A warp covers 256 consecutive columns of one row (16-byte
+// loads), the 8 warps of a block take every 8th row of the chunk; N % 8 == 0 and 16-byte aligned rows (vector form),
+// any N otherwise (scalar form, the [M, T] inputs).
 template <typename TI>
 __global__ void __launch_bounds__(THREADS)
 colsum_partial_kernel(const TI* __restrict__ Y, int64_t ld, int64_t M, int N, int64_t rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float sh[WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 256 + lane * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r1 = r0 + rows_per_chunk < M ? r0 + rows_per_chunk : M;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n0 + 8 <= N) {
+    for (int64_t r = r0 + warp; r < r1; r += WARPS) {
+      float v[8];
+      load8(Y + r * ld + n0, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sh[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < WARPS; ++k) s += sh[k][threadIdx.x];
+    partial[(int64_t)blockIdx.y * N + n] = s;
+  }
+}
+template <typename TI>
+__global__ void __launch_bounds__(THREADS)
+colsum_partial_scalar_kernel(const TI* __restrict__ Y, int64_t ld, int64_t M, int N, int64_t rows_per_chunk, float* __restrict__ partial) {
   __shared__ float sh[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -461,6 +491,7 @@ struct Plan {
   AT* partial;             // batched weight-gradient outputs [S][N][K]
   float* colpart;          // first-stage column sums / skinny weight gradients
   float* small;            // fp32 staging for gradients that need a re-layout
+  float* wstage;           // [n_ada, D] fp32: the AdaLN weight gradients of all layers before they are split up
   AT *fc1T[HW_MAX_DEPTH], *fc2T[HW_MAX_DEPTH], *adaT, *t2T, *c2T, *c1T;  // transposed weights for the dgrads
   int64_t Mp;  // padded row count of the transposes: Smax * 64-aligned chunk
   size_t bytes;
@@ -497,11 +528,14 @@ Plan<AT> make_plan(const HeadWeightsView& w, void* base, int64_t M) {
   const size_t wide = n_ada, narrow = D > Dc ? (D > 256 ? D : 256) : (Dc > 256 ? Dc : 256);
   p.yt = cv.take<AT>(wide * p.Mp);
   p.xt = cv.take<AT>(narrow * p.Mp);
-  p.partial = cv.take<AT>(16 * 3 * D * narrow);  // up to S = 16 partial products of the largest gradient, [3 D, narrow]
+  // S partial products of an [n_rows, k_out] gradient with S <= ceil(74 / tiles), tiles = (n_rows / 256) ceil(k_out / 256):
+  // S n_rows k_out <= 74 * 256 * 256 + n_rows k_out for every shape
+  p.partial = cv.take<AT>((size_t)75 * 65536 + n_ada * narrow);
   const size_t chunks = ceil_div(m, COL_CHUNK_ROWS);
   const size_t wideT = (size_t)w.T * D > n_ada ? (size_t)w.T * D : n_ada;
   p.colpart = cv.take<float>(chunks * wideT);
   p.small = cv.take<float>((size_t)w.T * D);
+  p.wstage = cv.take<float>(n_ada * D);
   for (size_t i = 0; i < L; ++i) { p.fc1T[i] = cv.take<AT>(D * D); p.fc2T[i] = cv.take<AT>(D * D); }
   p.adaT = cv.take<AT>(D * n_ada); p.t2T = cv.take<AT>(D * D); p.c2T = cv.take<AT>(D * D); p.c1T = cv.take<AT>(Dc * D);
   p.bytes = cv.off;
@@ -512,7 +546,11 @@ template <typename AT>
 int colsum(const AT* Y, int64_t ld, int64_t M, int N, float* colpart, float* out, cudaStream_t s) {
   if (out == nullptr) return NOVA_OK;
   const int chunks = static_cast<int>(ceil_div(M, COL_CHUNK_ROWS));
-  colsum_partial_kernel<AT><<<dim3(blocks_for(N, 32), (unsigned)chunks), THREADS, 0, s>>>(Y, ld, M, N, COL_CHUNK_ROWS, colpart);
+  const bool vec = N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(Y) & 31) == 0;
+  if (vec)
+    colsum_partial_kernel<AT><<<dim3(blocks_for(N, 256), (unsigned)chunks), THREADS, 0, s>>>(Y, ld, M, N, COL_CHUNK_ROWS, colpart);
+  else
+    colsum_partial_scalar_kernel<AT><<<dim3(blocks_for(N, 32), (unsigned)chunks), THREADS, 0, s>>>(Y, ld, M, N, COL_CHUNK_ROWS, colpart);
   NOVA_CHECK_LAUNCH();
   reduce_chunks_kernel<<<blocks_for(N), 256, 0, s>>>(colpart, chunks, N, out);
   NOVA_CHECK_LAUNCH();
@@ -689,13 +727,27 @@ int train_backward(const HeadWeightsView& w, const float* dv, const float* x_tok
   }
   // ---- the statistics GEMM st = a W_ada^T + b_ada: its output gradient dst is complete now; per layer, because the
   // reference keeps one nn.Linear per AdaLayerNormZero (normalization.py:28-32)
-  for (int i = 0; i <= L; ++i) {
-    const bool fin = i == L;
-    const std::string key = fin ? "norm.proj." : "blocks." + std::to_string(i) + ".norm1.proj.";
-    const int rows = fin ? 2 * D : 3 * D;
-    const int64_t off = (int64_t)3 * i * D;
-    NOVA_PROPAGATE(colsum<AT>(p.dst + off, n_ada, M, rows, p.colpart, g.get(key + "bias"), s));
-    NOVA_PROPAGATE(wgrad<AT>(w, p, p.dst + off, n_ada, rows, p.a, D, D, M, g.get(key + "weight"), s));
+  {
+    // ONE product for all (3L + 2) D statistics rows (dst^T a: 60 x 3 tiles at D = 768), staged in fp32; the rows of
+    // each layer then go to that layer's gradient tensor (the reference keeps one nn.Linear per AdaLayerNormZero,
+    // normalization.py:28-32)
+    bool any_w = false;
+    for (int i = 0; i <= L; ++i) {
+      const bool fin = i == L;
+      const std::string key = fin ? "norm.proj." : "blocks." + std::to_string(i) + ".norm1.proj.";
+      any_w = any_w || g.get(key + "weight") != nullptr;
+      NOVA_PROPAGATE(colsum<AT>(p.dst + (int64_t)3 * i * D, n_ada, M, fin ? 2 * D : 3 * D, p.colpart, g.get(key + "bias"), s));
+    }
+    if (any_w) {
+      NOVA_PROPAGATE(wgrad<AT>(w, p, p.dst, n_ada, n_ada, p.a, D, D, M, p.wstage, s));
+      for (int i = 0; i <= L; ++i) {
+        const bool fin = i == L;
+        float* out = g.get((fin ? std::string("norm.proj.") : "blocks." + std::to_string(i) + ".norm1.proj.") + "weight");
+        if (out == nullptr) continue;
+        NOVA_CHECK_CUDA(cudaMemcpyAsync(out, p.wstage + (size_t)3 * i * D * D, (size_t)(fin ? 2 : 3) * D * D * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s));
+      }
+    }
   }
   AT* da = p.s0;
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.dst, n_ada, p.adaT, n_ada, nullptr, da, D, M, D, n_ada, s));

@@ -62,7 +62,7 @@ def _oracle_loss_and_grads(sd, z, x, noise, t_idx, mask, R):
     zl = z.detach().clone().float().requires_grad_(True)
     out = OT.get_losses(leaves, zl, x.float(), noise.float(), t_idx, mask, loss_repeat=R)
     out["loss"].backward()
-    return float(out["loss"]), {k: v.grad for k, v in leaves.items()}, zl.grad
+    return float(out["loss"].detach()), {k: v.grad for k, v in leaves.items()}, zl.grad
 
 
 def _train_case(depth, D, Dc, patch, chan, B, H, W, R, seed, dtype):
@@ -94,12 +94,12 @@ def _gpu_loss_and_grads(head, x, z, mask, noise, t_idx, R):
     zc = z.to("cuda", head.dtype).requires_grad_(True)
     out = nb.get_losses(head, sched, zc, x.cuda(), mask=mask.cuda(), loss_repeat=R, noise=noise.cuda(), timesteps=t_idx.cuda())
     out["loss"].backward()
-    return float(out["loss"]), {k: p.grad.detach().float().cpu() for k, p in head.named_parameters()}, zc.grad.float().cpu()
+    return float(out["loss"].detach()), {k: p.grad.detach().float().cpu() for k, p in head.named_parameters()}, zc.grad.float().cpu()
 
 
 def test_backward_matches_autograd_fp32_on_the_reference_golden(golden_dir):
     """The reference's own get_losses case (tests/golden/losses.npz): loss through the training-mode forward, and
-    every gradient of loss.backward() against autograd through the oracle -- fp32 handle, <= 1e-4 of each tensor's max
+    every gradient of loss.backward() against autograd through the oracle -- fp32 handle, <= 5e-5 of each tensor's max
     (measured values recorded under profiles/)."""
     d, sd = _golden(golden_dir)
     head = _head(sd, d["cfg"]).train()
@@ -113,11 +113,11 @@ def test_backward_matches_autograd_fp32_on_the_reference_golden(golden_dir):
     worst = max(relmax(grads[k], ref[k]) for k in ref)
     record("training backward fp32 (reference golden case): worst parameter gradient", worst)
     for k in ref:
-        assert grads[k].shape == ref[k].shape and relmax(grads[k], ref[k]) <= 1e-4, k
-    assert relmax(dz, ref_dz) <= 1e-4
+        assert grads[k].shape == ref[k].shape and relmax(grads[k], ref[k]) <= 5e-5, k  # measured 1.2e-5
+    assert relmax(dz, ref_dz) <= 5e-5
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 4e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.bfloat16, 2e-2)])  # measured 2.2e-5 / 6.5e-3
 def test_backward_matches_autograd_two_blocks_patch2(dtype, tol):
     """depth 2, patch 2 x 2 x 4 channels (T = 16: the Conv2d-layout weight gradient), Dc = 64, 150 rows (not a multiple
     of anything), masked loss, loss_repeat 2.  bf16: against the fp32 oracle on the bf16-rounded weights."""
@@ -151,8 +151,8 @@ def test_backward_split_reduction_on_tensor_cores_matches_fp32_handle():
     errs = {k: relmax(g16[k], g32[k]) for k in g32}
     record("training backward bf16 vs fp32 handle (4096 rows, split reduction): worst parameter gradient", max(errs.values()))
     for k, e in errs.items():
-        assert e <= 4e-2, (k, e)
-    assert relmax(dz16, dz32) <= 4e-2
+        assert e <= 2e-2, (k, e)  # measured 5e-3
+    assert relmax(dz16, dz32) <= 2e-2
 
 
 def test_backward_only_requested_gradients_and_frozen_parameters():
