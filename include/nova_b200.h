@@ -212,6 +212,19 @@ NOVA_API int nova_farthest_point_sampling(const float* points, const int64_t* st
                                           int32_t num_samples, int64_t* picked, void* stream);
 
 /*
+ * nova_emd: earth mover's distance of equal-size clouds, a [B, N, 3], b [B, N, 3] fp32 -> emd [B] = mean distance of
+ *   the minimum-cost perfect matching; assign [B, N] int32 or NULL (object of b matched to point i of a);
+ *   status [B] int32 or NULL (bidding rounds used; negative: round budget exhausted, the matching is completed
+ *   greedily and is not optimal).  Replaces dist = cdist(a, b); linear_sum_assignment(dist); mean(dist[rows, cols])
+ *   (emd_approx train_newloss.py:352-377, earth_mover_distance demo.py:57-74, test_optimize.py:395-414).
+ *   The reference solves it with the Hungarian method on the CPU; here it is Bertsekas' auction algorithm with
+ *   epsilon scaling, one CTA per pair: the matching cost is within N * eps_final of the optimum (the mean within
+ *   eps_final; the Python mirror uses 1e-5).  N <= 4096.  Deterministic.
+ */
+NOVA_API int nova_emd(const float* a, const float* b, int64_t B, int64_t N, float eps_final, int32_t max_rounds,
+                      float* emd_out, int32_t* assign_out, int32_t* status_out, void* stream);
+
+/*
  * Training-mode arithmetic either side of the head, forward only.
  *
  * nova_add_noise: x, noise [tokens, T] fp32, t_idx [tokens] int64 into the scheduler's training tables

@@ -28,6 +28,11 @@ from .chamfer import (  # noqa: F401
     chamfer_distance,
     chamfer_nn,
     compute_chamfer_distance,
+    compute_emd,
+    earth_mover_distance,
+    emd_approx,
+    emd_matching,
+    robust_emd,
     dist_chamfer,
     robust_chamfer_distance,
 )

@@ -23,6 +23,7 @@ EXPORTS = [
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
     "nova_debug_chain_timeline", "nova_debug_words_clear", "nova_comm_unique_id", "nova_comm_init_rank",
     "nova_comm_destroy", "nova_allgather", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_farthest_point_sampling", "nova_add_noise", "nova_flow_loss",
+    "nova_head_train_bytes", "nova_head_train_forward", "nova_head_backward", "nova_emd",
 ]
 
 
@@ -85,6 +86,8 @@ def _declare(lib):
     lib.nova_add_noise.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.nova_flow_loss.restype = C.c_int
     lib.nova_flow_loss.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
+    lib.nova_emd.restype = C.c_int
+    lib.nova_emd.argtypes = [vp, vp, i64, i64, C.c_float, i32, vp, vp, vp, vp]
     lib.nova_head_train_bytes.restype = sz
     lib.nova_head_train_bytes.argtypes = [vp, i64]
     lib.nova_head_train_forward.restype = C.c_int

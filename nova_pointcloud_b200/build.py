@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libnova_b200.so")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
 SOURCES = ["rowwise_row_bf16.cu", "rowwise_row_f32.cu", "rowwise_fused.cu", "gemm_adaln.cu", "gemm_bias.cu", "gemm_silu.cu", "gemm_tail.cu",
-           "chain_r64.cu", "chain_r128.cu", "head.cu", "runtime.cu", "comm.cu", "chamfer.cu", "knn.cu", "fps.cu", "train.cu", "train_bwd.cu"]
+           "chain_r64.cu", "chain_r128.cu", "head.cu", "runtime.cu", "comm.cu", "chamfer.cu", "knn.cu", "fps.cu", "train.cu", "train_bwd.cu", "emd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

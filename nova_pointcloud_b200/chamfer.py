@@ -1,4 +1,6 @@
-"""Chamfer distance on the GPU: one CUDA nearest-neighbour primitive, the reference's three reductions.
+"""Chamfer distance and earth mover's distance on the GPU.
+
+Chamfer: one CUDA nearest-neighbour primitive, the reference's three reductions.
 
 * ``chamfer_distance``          -- variant A, /root/reference/demo.py:38-55 (the canonical definition)
 * ``dist_chamfer`` / ``robust_chamfer_distance`` -- variant B, /root/reference/train_newloss.py:316-349,381-384
@@ -6,6 +8,13 @@
 
 All distances come from ``torch.ops.nova_b200.chamfer_nn`` (exact difference form, fp32); the
 per-point transforms and means on top are elementwise glue.
+
+EMD: ``torch.ops.nova_b200.emd`` solves the assignment problem the reference hands to scipy's
+``linear_sum_assignment`` with the auction algorithm on the GPU (``csrc/emd.cu``):
+
+* ``earth_mover_distance``      -- /root/reference/demo.py:57-74
+* ``emd_approx`` / ``robust_emd`` -- /root/reference/train_newloss.py:352-377,386-388 (inputs clamped to [-2, 2])
+* ``compute_emd``               -- /root/reference/test_optimize.py:395-414 (mean over the batch, clamped to [0, 10])
 """
 
 from __future__ import annotations
@@ -76,3 +85,43 @@ def compute_chamfer_distance(pred, target):
     d1 = (m1 * (1.0 / (m1 + 1e-6))).mean(dim=1)
     d2 = (m2 * (1.0 / (m2 + 1e-6))).mean(dim=1)
     return (d1 + d2).mean().clamp(0.0, 10.0)
+
+
+EMD_EPS = 1e-5  # the matching's mean distance is within this of the optimum (auction algorithm, epsilon scaling)
+
+
+def emd_matching(a, b, eps: float = EMD_EPS):
+    """(emd (B,), assign (B, N) int32): the minimum-cost perfect matching of equal-size clouds.  Raises if a pair did
+    not converge within the round budget (never observed; the kernel bounds every loop)."""
+    a, _ = _as_cuda_batch(a)
+    b, _ = _as_cuda_batch(b, a.device)
+    out, assign, status = torch.ops.nova_b200.emd(a, b, float(eps))
+    if bool((status < 0).any()):
+        raise NovaError("EMD: the auction did not converge within its round budget for %d pair(s)" % int((status < 0).sum()))
+    return out, assign
+
+
+def earth_mover_distance(points1, points2):
+    """demo.py:57-74: mean matched distance.  (N,3),(N,3) -> float; batched -> (B,) tensor."""
+    a, single = _as_cuda_batch(points1)
+    out, _ = emd_matching(a, points2)
+    return float(out[0]) if single else out
+
+
+def emd_approx(x, y):
+    """train_newloss.py:352-377: inputs clamped to [-2, 2] -> (B,) tensor (the 1e-8 floor on the distances cannot change
+    a mean of fp32 distances by more than 1e-8)."""
+    a, _ = _as_cuda_batch(x)
+    b, _ = _as_cuda_batch(y, a.device)
+    out, _ = emd_matching(a.clamp(-2.0, 2.0), b.clamp(-2.0, 2.0))
+    return out
+
+
+def robust_emd(pred, gt):
+    return emd_approx(pred, gt).mean()
+
+
+def compute_emd(pred, target):
+    """test_optimize.py:395-414: batch mean of the per-pair EMD, clamped to [0, 10]."""
+    out, _ = emd_matching(pred, target)
+    return out.mean().clamp(0.0, 10.0)

@@ -316,28 +316,40 @@ struct EpiParams {
   int batch_m_rows, batch_w_rows;
 };
 
-// merge `parts` equal-sized partials (mean_t, M2_t over n_t values each) of one row -> (mean, rstd)
-__device__ __forceinline__ void merge_partials(const float2* part, int parts, int64_t M, int64_t row, float n_t, float eps,
-                                               float& mean, float& rstd) {
-  float ms[16], m2 = 0.f, msum = 0.f;
+// merge `parts` equal-sized partials (mean_t, M2_t over n_t values each) of one row -> (mean, rstd).  Two halves so that
+// the loads can be issued at the top of a tile and the arithmetic done after the epilogue warps' barriers.
+struct RowPartials {
+  float2 v[16];
+};
+__device__ __forceinline__ void load_partials(const float2* part, int parts, int64_t M, int64_t row, RowPartials& rp) {
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+    if (t < parts) rp.v[t] = part[static_cast<int64_t>(t) * M + row];
+}
+__device__ __forceinline__ void finish_partials(const RowPartials& rp, int parts, float n_t, float eps, float& mean, float& rstd) {
+  float m2 = 0.f, msum = 0.f;
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     if (t < parts) {
-      const float2 v = part[static_cast<int64_t>(t) * M + row];
-      ms[t] = v.x;
-      msum += v.x;
-      m2 += v.y;
+      msum += rp.v[t].x;
+      m2 += rp.v[t].y;
     }
   }
   mean = msum / static_cast<float>(parts);
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     if (t < parts) {
-      const float d = ms[t] - mean;
+      const float d = rp.v[t].x - mean;
       m2 = fmaf(n_t * d, d, m2);
     }
   }
   rstd = rsqrtf(m2 / (n_t * static_cast<float>(parts)) + eps);
+}
+__device__ __forceinline__ void merge_partials(const float2* part, int parts, int64_t M, int64_t row, float n_t, float eps,
+                                               float& mean, float& rstd) {
+  RowPartials rp;
+  load_partials(part, parts, M, row, rp);
+  finish_partials(rp, parts, n_t, eps, mean, rstd);
 }
 
 __device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
@@ -412,6 +424,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   // EPI_TAIL: full / empty barriers of the two staged {u, x} chunk buffers
   auto tail_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };
   auto tail_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };
+  // EPI_ADALN: epilogue warp q stages its 32 x 64 chunks of x through its two C staging buffers (TMA load, in-place
+  // modulation, TMA store): one "landed" barrier per (warp, buffer)
+  auto xfull = [&](int qq, int b) { return bar_base + 8u * (2 * STAGES + 9 + 2 * qq + b); };
 
   pdl_trigger();  // the next kernel may be scheduled as soon as resources free up; it waits for our completion itself
 #ifdef NOVA_GEMM_TIMELINE  // diagnostic build (scripts/profile_gemm_timeline.py): SM-clock stamps of CTA 0 in the debug words
@@ -431,8 +446,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
-    if (EPI == EPI_ADALN || EPI == EPI_TAIL) prefetch_tmap(&tmap_c2);
-    if (EPI == EPI_TAIL) prefetch_tmap(&tmap_c3);
+    if (EPI == EPI_ADALN || EPI == EPI_TAIL) {
+      prefetch_tmap(&tmap_c2);
+      prefetch_tmap(&tmap_c3);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -446,6 +463,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_init(tail_full(b), 1);   // the tail producer's arrive.expect_tx
         mbar_init(tail_empty(b), 4);  // one arrival per epilogue warp once it has copied its rows out
       }
+      if (EPI == EPI_ADALN)
+        for (int qq = 0; qq < 4; ++qq) mbar_init(xfull(qq, b), 1);
     }
     fence_barrier_init();
   }
@@ -549,6 +568,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t buf_phase = 0;
     int tb = 0;           // EPI_TAIL: staged {u, x} buffer in use
     uint32_t tphase = 0;
+    uint32_t xphase = 0u;  // EPI_ADALN: parities of my two x-staging barriers (bit b = buffer b)
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
       const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
@@ -556,36 +576,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int tile_n = tile % num_n;
       const int m0 = m_idx + q * 32;
       const bool mod_tile = EPI == EPI_ADALN && tile_n < p.n_mod_tiles;
-      epi_bar_sync<32 * epi_warps(EPI)>();  // every epilogue warp has finished reading the previous tile's bias
-      for (int j = tid_e; j < BN; j += 32 * epi_warps(EPI)) {
+      // ---- everything this tile's epilogue needs from memory is requested FIRST; the barriers below then wait under
+      // those round trips instead of in front of them
+      constexpr bool X_STAGED = EPI == EPI_ADALN && !WIDE_EPI;  // x chunks through the C staging buffers (TMA)
+      constexpr int KPW = WIDE_EPI ? 1 : 2;  // 64-feature groups of a modulation tile per warp (set)
+      const int cpar0 = cpar;                // staging buffer of this tile's first chunk
+      if (X_STAGED && mod_tile && m0 < p.M) {
+        if (lane == 0) {
+          tma_store_wait_read<0>();  // both staging buffers: their last stores have read them
+#pragma unroll
+          for (int kk = 0; kk < KPW; ++kk) {
+            const uint32_t cb = cbuf + static_cast<uint32_t>(cpar0 ^ kk) * C_BUF_BYTES;
+            mbar_expect_tx(xfull(q, cpar0 ^ kk), C_BUF_BYTES);
+            tma_load_2d(&tmap_c3, xfull(q, cpar0 ^ kk), cb, tile_n * 128 + 64 * kk, m0);
+          }
+        }
+        __syncwarp();
+      }
+      RowPartials rp;
+      float2 st2 = make_float2(0.f, 0.f);
+      const bool stats_row = (mod_tile || EPI == EPI_TAIL) && m0 + lane < p.M;
+      if (stats_row) {
+        if (EPI == EPI_TAIL || p.stats_parts > 0) load_partials(p.part_in, p.stats_parts, p.M, m0 + lane, rp);
+        else st2 = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(m0 + lane));
+      }
+      constexpr int NB = BN / (32 * epi_warps(EPI)) > 0 ? BN / (32 * epi_warps(EPI)) : 1;  // bias values per thread
+      float bv[NB], gv[NB], btv[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int j = tid_e + i * 32 * epi_warps(EPI);
+        const bool in = j < BN && n_idx + j < p.N;
         // modulation tiles: the scale half carries (1 + bias), so the epilogue forms 1 + scale with one addition
-        bias_s[j] = ((p.bias != nullptr && n_idx + j < p.N) ? __ldg(p.bias + n_idx + j) : 0.f) + ((mod_tile && j < 128) ? 1.0f : 0.f);
+        bv[i] = ((p.bias != nullptr && in) ? __ldg(p.bias + n_idx + j) : 0.f) + ((mod_tile && j < 128) ? 1.0f : 0.f);
         if (EPI == EPI_TAIL) {
-          reinterpret_cast<float*>(smem + P::OFF_GAMMA)[j] = n_idx + j < p.N ? __ldg(p.gamma + n_idx + j) : 0.f;
-          if ((j & 1) == 0)
-            reinterpret_cast<uint32_t*>(smem + P::OFF_BETA)[j >> 1] =
-                n_idx + j + 1 < p.N ? pack_bf16x2(__ldg(p.beta + n_idx + j), __ldg(p.beta + n_idx + j + 1)) : 0u;
+          gv[i] = in ? __ldg(p.gamma + n_idx + j) : 0.f;
+          btv[i] = in ? __ldg(p.beta + n_idx + j) : 0.f;
+        }
+      }
+      epi_bar_sync<32 * epi_warps(EPI)>();  // every epilogue warp has finished reading the previous tile's bias
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int j = tid_e + i * 32 * epi_warps(EPI);
+        if (j < BN) {
+          bias_s[j] = bv[i];
+          if (EPI == EPI_TAIL) {
+            reinterpret_cast<float*>(smem + P::OFF_GAMMA)[j] = gv[i];
+            reinterpret_cast<bf16*>(smem + P::OFF_BETA)[j] = __float2bfloat16_rn(btv[i]);  // column pairs: (beta_e, beta_e+1)
+          }
         }
       }
       epi_bar_sync<32 * epi_warps(EPI)>();  // bias tile visible to the epilogue warps
-      // AdaLN modulation tile: this thread's 128 features of x and its row statistics do not depend on the
-      // MMA, so they are requested BEFORE waiting for the accumulator and land while the tile is computed.
-      constexpr int KPW = WIDE_EPI ? 1 : 2;  // 64-feature groups of a modulation tile per warp (set)
-      uint4 xv[EPI == EPI_ADALN ? 8 * KPW : 1];  // my features of x: [64 half KPW, .. + 64 KPW) of the tile's 128
+      // AdaLN modulation tile: this thread's row statistics (and, when x is not staged, its 128 features of x) do not
+      // depend on the MMA, so they are requested BEFORE waiting for the accumulator and land while the tile is computed.
+      uint4 xv[(EPI == EPI_ADALN && !X_STAGED) ? 8 * KPW : 1];  // my features of x: [64 half KPW, .. + 64 KPW) of the tile's 128
       float mean = 0.f, rstd = 0.f;
       if (mod_tile) {
         const int row = m0 + lane;
         const bool valid = row < p.M;
-        const bf16* xrow = p.x + static_cast<int64_t>(valid ? row : 0) * p.ldx + tile_n * 128 + half * 64 * KPW;
+        if (!X_STAGED) {
+          const bf16* xrow = p.x + static_cast<int64_t>(valid ? row : 0) * p.ldx + tile_n * 128 + half * 64 * KPW;
 #pragma unroll
-        for (int c = 0; c < (EPI == EPI_ADALN ? 8 * KPW : 1); ++c)
-          xv[c] = p.x != nullptr ? ld_global_nc_v4(xrow + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
+          for (int c = 0; c < ((EPI == EPI_ADALN && !X_STAGED) ? 8 * KPW : 1); ++c)
+            xv[c] = p.x != nullptr ? ld_global_nc_v4(xrow + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
+        }
         if (valid) {
           if (p.stats_parts > 0) {  // x was produced by an EPI_TAIL epilogue: merge its per-tile partials
-            merge_partials(p.part_in, p.stats_parts, p.M, row, static_cast<float>(p.n_mod_tiles * 128 / p.stats_parts), 1e-6f,
-                           mean, rstd);
+            finish_partials(rp, p.stats_parts, static_cast<float>(p.n_mod_tiles * 128 / p.stats_parts), 1e-6f, mean, rstd);
           } else {
-            const float2 st2 = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(row));
             mean = st2.x;
             rstd = st2.y;
           }
@@ -602,10 +659,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int kk = 0; kk < KPW; ++kk) {  // 64 features -> one staging buffer -> one TMA store
           const int k = half * KPW + kk;
           if (m0 < p.M) {
-            if (lane == 0) {  // the store that last used this staging buffer has read it
-              if (WIDE_EPI) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            if (X_STAGED) {  // my 32 x 64 chunk of x has landed in this staging buffer; h overwrites it in place
+              mbar_wait(xfull(q, cpar), (xphase >> cpar) & 1u, dbg, 0x900u | (q << 1) | cpar);
+              xphase ^= 1u << cpar;
+            } else {
+              if (lane == 0) {  // the store that last used this staging buffer has read it
+                if (WIDE_EPI) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+              }
+              __syncwarp();
             }
-            __syncwarp();
             const uint32_t cb = cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES;
             const uint32_t dst = cb + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
@@ -620,7 +682,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               const f32x2 nmean2 = pk2(-mean, -mean), rstd2 = pk2(rstd, rstd);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const uint4 xq = xv[EPI == EPI_ADALN ? (kk * 2 + sc) * 4 + c : 0];
+                uint4 xq;
+                if (X_STAGED) {
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xq.x), "=r"(xq.y), "=r"(xq.z), "=r"(xq.w)
+                               : "r"(dst + (static_cast<uint32_t>((sc * 4 + c) ^ (lane & 7)) << 4)));
+                } else {
+                  xq = xv[(EPI == EPI_ADALN && !X_STAGED) ? (kk * 2 + sc) * 4 + c : 0];
+                }
                 const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
                 uint32_t w[4];
 #pragma unroll
@@ -649,7 +717,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int row = m0 + lane;
         const bool valid = row < p.M;
         float mu = 0.f, ru = 0.f;
-        if (valid) merge_partials(p.part_in, p.stats_parts, p.M, row, static_cast<float>(p.N / p.stats_parts), 1e-5f, mu, ru);
+        if (valid) finish_partials(rp, p.stats_parts, static_cast<float>(p.N / p.stats_parts), 1e-5f, mu, ru);
         // statistics of the new x over my half tile, about its first value (packed: even / odd columns)
         float c0 = 0.f;
         f32x2 nc02 = pk2(0.f, 0.f), s1v = pk2(0.f, 0.f), s2v = pk2(0.f, 0.f);
@@ -843,7 +911,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
     const int gate_cols = N - 2 * ada->features;
     if (gate_cols > 0) NOVA_PROPAGATE(make_tmap_kmajor(&tc2, ada->gate, M, gate_cols, ada->ldg, 32));
     else tc2 = tc_;
-    tc3 = tc_;
+    NOVA_PROPAGATE(make_tmap_kmajor(&tc3, ada->x, M, ada->features, ada->ldx, 32));  // x chunks into the C staging buffers
     p.x = ada->x; p.ldx = ada->ldx; p.rowstats = ada->rowstats; p.n_mod_tiles = 2 * ada->features / BN;
     p.part_in = ada->parts; p.stats_parts = ada->n_parts;
   } else if (EPI == EPI_TAIL) {

@@ -390,6 +390,30 @@ def _(points, start, num_samples):
     return points.new_empty((points.shape[0], num_samples), dtype=torch.int64)
 
 
+@torch.library.custom_op("nova_b200::emd", mutates_args=(), device_types="cuda")
+def emd(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-5, max_rounds: int = 400000
+        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(emd (B,) fp32, assign (B, N) int32, status (B,) int32): minimum-cost perfect matching of equal-size clouds by the
+    auction algorithm.  See nova_emd in nova_b200.h."""
+    a, b = _cloud3(a, "a"), _cloud3(b, "b")
+    if a.shape != b.shape:
+        raise NovaError(f"EMD needs clouds of equal size (the reference asserts it); got {tuple(a.shape)} and {tuple(b.shape)}")
+    B, N = a.shape[0], a.shape[1]
+    out = torch.empty(B, dtype=torch.float32, device=a.device)
+    assign = torch.empty(B, N, dtype=torch.int32, device=a.device)
+    status = torch.zeros(B, dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.lib().nova_emd(_ptr(a), _ptr(b), B, N, float(eps), int(max_rounds), _ptr(out), _ptr(assign), _ptr(status),
+                                  _stream()), "nova_emd")
+    return out, assign, status
+
+
+@emd.register_fake
+def _(a, b, eps=1e-5, max_rounds=400000):
+    return (a.new_empty((a.shape[0],), dtype=torch.float32), a.new_empty(a.shape[:2], dtype=torch.int32),
+            a.new_empty((a.shape[0],), dtype=torch.int32))
+
+
 @torch.library.custom_op("nova_b200::add_noise", mutates_args=(), device_types="cuda")
 def add_noise(x: torch.Tensor, noise: torch.Tensor, sigma_table: torch.Tensor, t_table: torch.Tensor,
               t_idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -72,3 +72,21 @@ def chamfer_c(pred: np.ndarray, target: np.ndarray) -> float:
     d1 = (m1 / (m1 + 1e-6)).mean(axis=1)
     d2 = (m2 / (m2 + 1e-6)).mean(axis=1)
     return float(np.clip((d1 + d2).mean(), 0.0, 10.0))
+
+
+def emd(a: np.ndarray, b: np.ndarray) -> float:
+    """Earth mover's distance of two equal-size clouds: mean distance of the minimum-cost perfect matching, solved
+    exactly like the reference does (scipy linear_sum_assignment on the float64 cdist matrix):
+    /root/reference/demo.py:57-74; emd_approx /root/reference/train_newloss.py:352-377 clamps the inputs to [-2, 2]
+    first (``clamp=2.0``); /root/reference/test_optimize.py:395-414 averages over the batch and clamps to [0, 10]."""
+    from scipy.optimize import linear_sum_assignment
+
+    d = cdist(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))
+    r, c = linear_sum_assignment(d)
+    return float(d[r, c].mean())
+
+
+def emd_approx(x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """train_newloss.py:352-377 on (B, N, 3) batches -> (B,)."""
+    x, y = np.clip(np.asarray(x, np.float64), -2.0, 2.0), np.clip(np.asarray(y, np.float64), -2.0, 2.0)
+    return np.array([emd(x[i], y[i]) for i in range(x.shape[0])])

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from gpu_util import record
 from oracle import chamfer as OC
 
 pytestmark = pytest.mark.gpu
@@ -91,3 +92,76 @@ def test_full_size_properties():
     cd = nb.chamfer_distance(a, b)
     assert cd.shape == (256,)
     assert abs(float(cd[255]) - (m1.mean() + m2.mean())) < 1e-6
+
+
+# ---------------------------------------------------------------- earth mover's distance
+def _emd_clouds(B, N, seed, spread=1.0):
+    g = np.random.default_rng(seed)
+    a = g.uniform(-spread, spread, size=(B, N, 3)).astype(np.float32)
+    b = (a[:, g.permutation(N)] * 0.9 + g.normal(0, 0.15, size=(B, N, 3))).astype(np.float32)  # a shuffled, perturbed copy
+    return a, b
+
+
+@pytest.mark.parametrize("N", [1, 2, 7, 33, 256, 700])
+def test_emd_matches_hungarian(N):
+    """nova_emd (auction algorithm) against scipy's linear_sum_assignment on float64 distances (demo.py:57-74): the mean
+    matched distance is within eps = 1e-5 of the optimum (N * eps on the matching cost), the assignment is a permutation
+    and its own cost is what the kernel reports."""
+    import nova_pointcloud_b200 as nb
+
+    a, b = _emd_clouds(3, N, 100 + N)
+    got, assign = nb.emd_matching(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    for i in range(3):
+        want = OC.emd(a[i], b[i])
+        assert abs(float(got[i]) - want) <= 1.5e-5 + 1e-6 * want, (N, i, float(got[i]), want)
+        perm = assign[i].cpu().numpy()
+        assert sorted(perm.tolist()) == list(range(N))
+        own = np.linalg.norm(a[i].astype(np.float64) - b[i][perm].astype(np.float64), axis=1).mean()
+        assert abs(own - float(got[i])) <= 1e-6 * max(own, 1.0) + 1e-7
+        assert float(got[i]) >= want - 1e-6  # never below the optimum (beyond fp32 summation noise)
+    record(f"emd vs Hungarian (N={N}): worst abs error of the mean distance",
+           max(abs(float(got[i]) - OC.emd(a[i], b[i])) for i in range(3)))
+
+
+def test_emd_variants_and_properties():
+    """The three reference surfaces (demo.py:57-74, train_newloss.py:352-377, test_optimize.py:395-414), identical
+    clouds -> 0, a pure permutation -> 0, symmetry, determinism, unequal sizes rejected (the reference asserts)."""
+    import nova_pointcloud_b200 as nb
+
+    a, b = _emd_clouds(4, 512, 9, spread=2.5)  # beyond +-2: emd_approx's clamp matters
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    got = nb.emd_approx(ta, tb).cpu().numpy()
+    want = OC.emd_approx(a, b)
+    assert np.abs(got - want).max() <= 2e-5
+    assert abs(float(nb.robust_emd(ta, tb)) - want.mean()) <= 2e-5
+    full = np.array([OC.emd(a[i], b[i]) for i in range(4)])
+    assert abs(float(nb.compute_emd(ta, tb)) - min(max(full.mean(), 0.0), 10.0)) <= 2e-5
+    assert abs(nb.earth_mover_distance(a[0], b[0]) - full[0]) <= 2e-5  # (N,3) numpy in, float out
+    assert float(nb.emd_matching(ta, ta)[0].abs().max()) == 0.0
+    perm = torch.randperm(512, device="cuda")
+    assert float(nb.emd_matching(ta, ta[:, perm].contiguous())[0].abs().max()) <= 1e-5
+    fwd, bwd = nb.emd_matching(ta, tb)[0], nb.emd_matching(tb, ta)[0]
+    assert float((fwd - bwd).abs().max()) <= 2e-5
+    again = nb.emd_matching(ta, tb)
+    assert torch.equal(again[0], fwd) and torch.equal(again[1], nb.emd_matching(ta, tb)[1])
+    with pytest.raises(nb.NovaError):
+        nb.emd_matching(ta, tb[:, :100].contiguous())
+
+
+def test_emd_full_size_cfg5():
+    """BASELINE configs[4] shapes: 2048 x 2048 points.  One pair against the Hungarian oracle (~1 s of scipy), 16 pairs
+    for the size-independent properties: a valid permutation, cost >= the Chamfer lower bound (every point's matched
+    distance is at least its nearest-neighbour distance), all pairs converged."""
+    import nova_pointcloud_b200 as nb
+
+    a, b = _emd_clouds(16, 2048, 77)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out, assign, status = torch.ops.nova_b200.emd(ta, tb, 1e-5)
+    assert bool((status > 0).all())
+    want = OC.emd(a[0], b[0])
+    record("emd vs Hungarian (N=2048): abs error of the mean distance", abs(float(out[0]) - want))
+    assert abs(float(out[0]) - want) <= 1.5e-5 + 1e-6 * want
+    d1, d2, _, _ = nb.chamfer_nn(ta, tb, with_indices=False)
+    assert bool((out >= torch.maximum(d1.mean(1), d2.mean(1)) - 1e-6).all())
+    srt = assign.sort(dim=1).values.cpu()
+    assert torch.equal(srt, torch.arange(2048, dtype=torch.int32).expand(16, -1))

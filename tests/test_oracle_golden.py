@@ -248,3 +248,19 @@ def test_training_tables_and_timestep_sampling():
     x, n = torch.randn(2, 5, 3), torch.randn(2, 5, 3)
     zero = torch.zeros(2, 5, dtype=torch.int64)
     assert torch.equal(OT.add_noise(x, n, zero, sig), n)  # sigma = 1 at index 0: pure noise
+
+
+def test_emd_oracle_is_the_exact_assignment_optimum():
+    """oracle/chamfer.py::emd restates demo.py:57-74 (scipy linear_sum_assignment on cdist): on clouds small enough to
+    enumerate, it equals the minimum over all permutations; emd_approx clamps to [-2, 2] first (train_newloss.py:363-364)."""
+    import itertools
+
+    from oracle import chamfer as OC
+
+    g = np.random.default_rng(3)
+    a, b = g.normal(size=(6, 3)) * 1.5, g.normal(size=(6, 3)) * 1.5
+    best = min(np.linalg.norm(a - b[list(p)], axis=1).mean() for p in itertools.permutations(range(6)))
+    assert abs(OC.emd(a, b) - best) < 1e-12
+    ac, bc = np.clip(a, -2, 2), np.clip(b, -2, 2)
+    assert abs(OC.emd_approx(a[None], b[None])[0] - OC.emd(ac, bc)) < 1e-12
+    assert OC.emd(a, a) == 0.0
