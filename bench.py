@@ -731,6 +731,32 @@ def main():
                                                                 "transformer_pointcloud_nova.py:81-89)"}
         except Exception as e:
             extras["geometry"] = {"error": str(e)[:300]}
+        try:  # earth mover's distance: the assignment problem of cfg5's pairs, auction algorithm
+            emd_b = pb[:, torch.randperm(Nc, device=dev, generator=gc)] * 0.9 + 0.1 * pa  # a shuffled, perturbed copy
+            emd_b = emd_b.contiguous()
+            torch.ops.nova_b200.emd(pa, emd_b, 1e-5)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            emd_v, _, emd_st = torch.ops.nova_b200.emd(pa, emd_b, 1e-5)
+            e1.record()
+            torch.cuda.synchronize()
+            ems = e0.elapsed_time(e1)
+            extras["emd"] = {"value": Bc / (ems * 1e-3), "unit": "cloud pairs/s", "ms": ems, "pairs": Bc, "points": Nc,
+                             "bidding_rounds_mean": float(emd_st.float().abs().mean()), "converged": bool((emd_st > 0).all()),
+                             "what": "minimum-cost perfect matching of %d x (%d vs %d) points (emd_approx, train_newloss.py:352-377): "
+                                     "auction algorithm with epsilon scaling to 1e-5, one CTA per pair" % (Bc, Nc, Nc)}
+            if not args.no_cpu_baseline:
+                from oracle import chamfer as OCe
+
+                t0 = time.perf_counter()
+                ref_e = OCe.emd(pa[0].cpu().numpy(), emd_b[0].cpu().numpy())
+                cpu_s = time.perf_counter() - t0
+                extras["emd"]["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "cloud pairs/s", "cores": 1, "kind": "port",
+                                                 "sample": "1 pair, scipy cdist float64 + linear_sum_assignment (oracle/chamfer.py, demo.py:57-74)",
+                                                 "abs_diff_of_mean_distance": abs(float(emd_v[0]) - ref_e)}
+        except Exception as e:
+            extras["emd"] = {"error": str(e)[:300]}
         try:  # training step: forward with saved activations + the full backward, cfg2's rows
             from nova_pointcloud_b200 import ops as _ops
 

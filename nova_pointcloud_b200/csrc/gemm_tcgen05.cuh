@@ -569,6 +569,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int tb = 0;           // EPI_TAIL: staged {u, x} buffer in use
     uint32_t tphase = 0;
     uint32_t xphase = 0u;  // EPI_ADALN: parities of my two x-staging barriers (bit b = buffer b)
+#ifdef NOVA_TAIL_TIMELINE  // diagnostic build: where an EPI_TAIL epilogue warp spends its cycles (CTA 0, first warp)
+    long long tt_full = 0, tt_acc = 0, tt_store = 0, tt_bar = 0;
+    const long long tt_begin = clock64();
+#define NOVA_TT(acc, stmt) do { const long long _t = clock64(); stmt; acc += clock64() - _t; } while (0)
+#else
+#define NOVA_TT(acc, stmt) do { stmt; } while (0)
+#endif
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
       const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
@@ -613,7 +620,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           btv[i] = in ? __ldg(p.beta + n_idx + j) : 0.f;
         }
       }
-      epi_bar_sync<32 * epi_warps(EPI)>();  // every epilogue warp has finished reading the previous tile's bias
+      NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // every epilogue warp has finished reading the previous tile's bias
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int j = tid_e + i * 32 * epi_warps(EPI);
@@ -625,7 +632,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       }
-      epi_bar_sync<32 * epi_warps(EPI)>();  // bias tile visible to the epilogue warps
+      NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // bias tile visible to the epilogue warps
       // AdaLN modulation tile: this thread's row statistics (and, when x is not staged, its 128 features of x) do not
       // depend on the MMA, so they are requested BEFORE waiting for the accumulator and land while the tile is computed.
       uint4 xv[(EPI == EPI_ADALN && !X_STAGED) ? 8 * KPW : 1];  // my features of x: [64 half KPW, .. + 64 KPW) of the tile's 128
@@ -648,7 +655,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       }
-      mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf);
+      NOVA_TT(tt_acc, mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf));
       if (tile == group && threadIdx.x == EPI_WARP0 * 32) NOVA_TL_STAMP(2);  // first accumulator complete
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
@@ -729,7 +736,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int cc = half * 2 + k;
           const int n0 = n_idx + cc * C_CHUNK;
           // my rows of the staged {u, x} chunk -> registers, then the buffer goes straight back to the producer
-          mbar_wait(tail_full(half), tphase, dbg, 0x800u | half);
+          NOVA_TT(tt_full, mbar_wait(tail_full(half), tphase, dbg, 0x800u | half));
           tphase ^= 1u;  // each buffer serves one chunk per half tile: its phase flips every use
           const uint32_t ub = base + P::OFF_TAIL + static_cast<uint32_t>(half) * P::T_BUF_BYTES +
                               static_cast<uint32_t>(q * 32 + lane) * 128u;
@@ -743,8 +750,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(tail_empty(half));
           if (m0 >= p.M || n0 >= p.N) continue;  // warp-uniform: nothing of this sub-tile is in bounds
-          if (lane == 0) tma_store_wait_read<0>();  // my single staging buffer: its last store (a chunk ago) has read it
-          __syncwarp();
+          NOVA_TT(tt_store, { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); });  // my single staging buffer: its last store (a chunk ago) has read it
           const uint32_t dst = cbuf + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {  // 32 accumulator columns at a time keeps the register footprint bounded
@@ -877,6 +883,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging memory must outlive the last stores' reads
     if (threadIdx.x == EPI_WARP0 * 32) NOVA_TL_STAMP(3);  // epilogue done
+#ifdef NOVA_TAIL_TIMELINE
+    if (EPI == EPI_TAIL && dbg && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32) {
+      dbg[0] = static_cast<uint32_t>(clock64() - tt_begin);  // whole epilogue loop
+      dbg[1] = static_cast<uint32_t>(tt_full);                // waiting for the staged {u, x} chunks
+      dbg[2] = static_cast<uint32_t>(tt_acc);                 // waiting for accumulators
+      // waiting for my staging buffer's last store (low 16 bits) | at the epilogue warps' barriers (high 16), units of 64 cycles
+      dbg[3] = static_cast<uint32_t>((tt_store >> 6) & 0xffff) | (static_cast<uint32_t>((tt_bar >> 6) & 0xffff) << 16);
+      __threadfence_system();
+    }
+#endif
   }
   __syncwarp();  // lanes of the single-lane roles reconverge before the CTA-wide barrier
   tcgen05_fence_before();
