@@ -10,12 +10,21 @@ int launch_rows128(const ChainParams& p, const bf16* w_stack, cudaStream_t strea
 
 bool supported(int D) { return D > 0 && D % 256 == 0 && D <= 2048; }
 
-// Measured (B200, D = 768, 25-step calls, scripts/profile_sets.py): the chain kernel wins while every cluster owns 64
-// rows and all clusters are resident in one wave (2.42 vs 2.49 ms at 32 rows, 2.58 vs 3.11 ms at 512, 3.01 vs 3.40 ms
-// at 768); with 128 rows per cluster it is level with the launch chain (3.84 vs 3.68 ms at 1024, 4.16 vs 4.25 at 1632).
+// Measured (B200, 25-step calls of 32 clouds x n tokens, scripts/gpu_chain_sweep.sh, ms per call, chain vs launches):
+//   D = 768  (64-row clusters up to 896 rows, 128-row clusters above)
+//     768 rows 2.64 vs 3.46 | 1024: 3.42 vs 3.77 | 1632: 3.47 vs 4.33 | 1792: 3.51 vs 4.41 | 2048: 6.71 vs 4.57 (second wave)
+//   D = 1024   768: 3.32 vs 4.36 | 1024: 4.08 vs 4.62 | 1632: 4.56 vs 5.42 | 1792: 5.09 vs 5.46
+//   D = 1536   768: 5.34 vs 6.15 | 1024 (128-row clusters): 6.95 vs 6.74
+// i.e. the kernel wins while all of its clusters are resident in ONE wave -- with 64 rows per cluster at any width,
+// with 128 rows per cluster up to D = 1024 (at D = 1536 a CTA's 590 KB weight slice per stage costs more than the
+// launches it saves).  An earlier build put 128-row clusters level with the launch chain; the group-wise ring barriers,
+// the whole-warp MMA loop and the packed-fp32 epilogues moved that.
 int64_t profitable_rows(int D) {
   if (const char* env = std::getenv("NOVA_B200_CHAIN_ROWS")) return std::atoll(env);
-  return supported(D) ? static_cast<int64_t>(64) * max_clusters64(D) : 0;
+  if (!supported(D)) return 0;
+  const int64_t r64 = static_cast<int64_t>(64) * max_clusters64(D);
+  const int64_t r128 = D <= 1024 ? static_cast<int64_t>(128) * max_clusters_rows<128>(D) : 0;
+  return r64 > r128 ? r64 : r128;
 }
 
 long long* timeline_buffer(bool create) {
