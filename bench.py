@@ -865,8 +865,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ada_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": ada_tf / pk["sustained"], "traffic": traffic,
-                         "kernel": "nova::tc::gemm_kernel<EPI_ADALN, cta_group 2>: AdaLN statistics GEMM M x 3D x D with the "
-                                   "LayerNorm modulation fused into its epilogue (dominant kernel)",
+                         "kernel": "nova::tc::gemm_kernel<EPI_ADALN | EPI_TAIL, cta_group 2>: the AdaLN statistics GEMMs of the step "
+                                   "(dominant class, 3D of the 5D output columns per block): modulation part M x 2D x D with "
+                                   "LN(x)(1+scale)+shift in its epilogue and gate part M x D x D with the block tail "
+                                   "x += LN(u) gamma gate in its epilogue; FLOP and time averaged over both kinds of launch",
                          "flop_per_launch": ada_flops, "avg_launch_ms": ada_avg_ms, "launches_timed": ada_n,
                          "how": "CUDA events recorded by the library around every launch on the launching stream, "
                                 "inside real sampling steps (nova_profile_*)",
