@@ -39,7 +39,10 @@ constexpr int EPI_WARP0 = 4;
 // epilogue costs ~13 instructions per element.  The epilogue code below is written for either count; for EPI_ADALN
 // 8 warps measured 11 % SLOWER (38.6 vs 34.7 ms of AdaLN GEMMs per cfg2 pass), so it stays at 4.
 __host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_TAIL ? 8 : 4; }
-__host__ __device__ constexpr int num_threads(int epi) { return 128 + 32 * epi_warps(epi); }
+// (EPI_TAIL with 11 warps -- TMEM allocator and chunk producer sharing a warp -- was tried to get past the 168 registers
+// 384 threads allow: warps are allocated in fours, ptxas stays at 168.)
+__host__ __device__ constexpr int epi_warp0(int) { return EPI_WARP0; }
+__host__ __device__ constexpr int num_threads(int epi) { return 32 * (epi_warp0(epi) + epi_warps(epi)); }
 constexpr int TMEM_COLS = 512;
 constexpr int C_CHUNK = 64;                               // output columns per TMA store (128 B rows)
 constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;             // one warp's 32 x 64 bf16 sub-tile: 4 KB
@@ -318,18 +321,21 @@ struct EpiParams {
 
 // merge `parts` equal-sized partials (mean_t, M2_t over n_t values each) of one row -> (mean, rstd).  Two halves so that
 // the loads can be issued at the top of a tile and the arithmetic done after the epilogue warps' barriers.
+template <int MAXP>
 struct RowPartials {
-  float2 v[16];
+  float2 v[MAXP];
 };
-__device__ __forceinline__ void load_partials(const float2* part, int parts, int64_t M, int64_t row, RowPartials& rp) {
+template <int MAXP>
+__device__ __forceinline__ void load_partials(const float2* part, int parts, int64_t M, int64_t row, RowPartials<MAXP>& rp) {
 #pragma unroll
-  for (int t = 0; t < 16; ++t)
+  for (int t = 0; t < MAXP; ++t)
     if (t < parts) rp.v[t] = part[static_cast<int64_t>(t) * M + row];
 }
-__device__ __forceinline__ void finish_partials(const RowPartials& rp, int parts, float n_t, float eps, float& mean, float& rstd) {
+template <int MAXP>
+__device__ __forceinline__ void finish_partials(const RowPartials<MAXP>& rp, int parts, float n_t, float eps, float& mean, float& rstd) {
   float m2 = 0.f, msum = 0.f;
 #pragma unroll
-  for (int t = 0; t < 16; ++t) {
+  for (int t = 0; t < MAXP; ++t) {
     if (t < parts) {
       msum += rp.v[t].x;
       m2 += rp.v[t].y;
@@ -337,7 +343,7 @@ __device__ __forceinline__ void finish_partials(const RowPartials& rp, int parts
   }
   mean = msum / static_cast<float>(parts);
 #pragma unroll
-  for (int t = 0; t < 16; ++t) {
+  for (int t = 0; t < MAXP; ++t) {
     if (t < parts) {
       const float d = rp.v[t].x - mean;
       m2 = fmaf(n_t * d, d, m2);
@@ -347,7 +353,7 @@ __device__ __forceinline__ void finish_partials(const RowPartials& rp, int parts
 }
 __device__ __forceinline__ void merge_partials(const float2* part, int parts, int64_t M, int64_t row, float n_t, float eps,
                                                float& mean, float& rstd) {
-  RowPartials rp;
+  RowPartials<16> rp;
   load_partials(part, parts, M, row, rp);
   finish_partials(rp, parts, n_t, eps, mean, rstd);
 }
@@ -404,6 +410,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
             const __grid_constant__ CUtensorMap tmap_c3, const EpiParams p, uint32_t* dbg) {
   using P = Plan<CG, BN, EPI == EPI_TAIL>;
+  constexpr int EW0 = epi_warp0(EPI);  // first epilogue warp
   static_assert(EPI != EPI_ADALN || BN == BN_FULL, "the AdaLN epilogue pairs 128 scale + 128 shift columns per tile");
   static_assert(EPI != EPI_TAIL || BN == BN_FULL, "the tail epilogue works on 256-column tiles");
   constexpr int STAGES = P::STAGES, STAGE_BYTES = P::STAGE_BYTES;
@@ -555,13 +562,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {  // ------------------------------------ epilogue (every CTA: its 128 rows)
+  } else if (warp >= EW0) {  // ------------------------------------ epilogue (every CTA: its 128 rows)
     const int q = warp & 3;  // TMEM lane quarter this warp may access == its 32-row slice of the tile
-    const int tid_e = threadIdx.x - EPI_WARP0 * 32;
+    const int tid_e = threadIdx.x - EW0 * 32;
     // C staging: 4 warps x 2 buffers of 4 KB; EPI_TAIL: 8 warps x 1 buffer
     constexpr bool WIDE_EPI = epi_warps(EPI) == 8;
-    const int half = WIDE_EPI ? (warp - EPI_WARP0) >> 2 : 0;  // which half of the tile's columns this warp set takes
-    const uint32_t cbuf = base + P::OFF_CSTAGE + (WIDE_EPI ? static_cast<uint32_t>(warp - EPI_WARP0) * C_BUF_BYTES
+    const int half = WIDE_EPI ? (warp - EW0) >> 2 : 0;  // which half of the tile's columns this warp set takes
+    const uint32_t cbuf = base + P::OFF_CSTAGE + (WIDE_EPI ? static_cast<uint32_t>(warp - EW0) * C_BUF_BYTES
                                                            : static_cast<uint32_t>(q) * 2u * C_BUF_BYTES);
     float* bias_all = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     int buf = 0, cpar = 0;
@@ -600,7 +607,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         __syncwarp();
       }
-      RowPartials rp;
+      RowPartials<EPI == EPI_TAIL ? 8 : 16> rp;  // the tail merges <= 8 partials of u (launch_tail), the modulation <= 16 of x
       float2 st2 = make_float2(0.f, 0.f);
       const bool stats_row = (mod_tile || EPI == EPI_TAIL) && m0 + lane < p.M;
       if (stats_row) {
@@ -656,7 +663,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
       NOVA_TT(tt_acc, mbar_wait(tfull_bar(buf), buf_phase, dbg, 0x400u | buf));
-      if (tile == group && threadIdx.x == EPI_WARP0 * 32) NOVA_TL_STAMP(2);  // first accumulator complete
+      if (tile == group && threadIdx.x == EW0 * 32) NOVA_TL_STAMP(2);  // first accumulator complete
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       if (mod_tile) {
@@ -882,9 +889,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging memory must outlive the last stores' reads
-    if (threadIdx.x == EPI_WARP0 * 32) NOVA_TL_STAMP(3);  // epilogue done
+    if (threadIdx.x == EW0 * 32) NOVA_TL_STAMP(3);  // epilogue done
 #ifdef NOVA_TAIL_TIMELINE
-    if (EPI == EPI_TAIL && dbg && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32) {
+    if (dbg && blockIdx.x == 0 && threadIdx.x == EW0 * 32) {
       dbg[0] = static_cast<uint32_t>(clock64() - tt_begin);  // whole epilogue loop
       dbg[1] = static_cast<uint32_t>(tt_full);                // waiting for the staged {u, x} chunks
       dbg[2] = static_cast<uint32_t>(tt_acc);                 // waiting for accumulators
