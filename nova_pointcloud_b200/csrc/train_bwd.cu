@@ -73,27 +73,45 @@ __global__ void embed_fwd_kernel(const float* __restrict__ xt, const float* __re
   x0[i] = from_float<AT>(acc);
 }
 
+// element-wise kernels: 8 elements per thread (16-byte accesses for bf16); n = M * D with D % 256 == 0
 template <typename AT>
 __global__ void silu_fwd_kernel(const AT* __restrict__ p, AT* __restrict__ u, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) u[i] = from_float<AT>(silu_accurate(to_float(p[i])));
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  float v[8];
+  load8(p + i, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = silu_accurate(v[e]);
+  store8(u + i, v);
 }
 
 template <typename AT>
 __global__ void add_silu_kernel(const AT* __restrict__ c, const AT* __restrict__ temb, AT* __restrict__ zt,
                                 AT* __restrict__ a, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  const AT z = from_float<AT>(to_float(c[i]) + to_float(temb[i]));
-  zt[i] = z;
-  a[i] = from_float<AT>(silu_accurate(to_float(z)));  // of the stored (rounded) value: what the backward differentiates
+  float x[8], y[8], z[8];
+  load8(c + i, x);
+  load8(temb + i, y);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) z[e] = to_float(from_float<AT>(x[e] + y[e]));  // the stored (rounded) value is what the
+  store8(zt + i, z);                                                         // backward differentiates
+#pragma unroll
+  for (int e = 0; e < 8; ++e) z[e] = silu_accurate(z[e]);
+  store8(a + i, z);
 }
 
 // dp = du * silu'(p)   (in place allowed: dp == du)
 template <typename AT>
 __global__ void silu_bwd_kernel(const AT* __restrict__ du, const AT* __restrict__ p, AT* __restrict__ dp, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dp[i] = from_float<AT>(to_float(du[i]) * dsilu(to_float(p[i])));
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  float g[8], v[8];
+  load8(du + i, g);
+  load8(p + i, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) g[e] *= dsilu(v[e]);
+  store8(dp + i, g);
 }
 
 template <typename TS, typename TD>
@@ -404,29 +422,52 @@ __global__ void splitk_reduce_kernel(const AT* __restrict__ partial, int S, int6
   for (int k = 0; k < S; ++k) s += to_float(partial[(int64_t)k * n + i]);
   out[i] = s;
 }
-// out [S][N][Mc] <- Y [M, N] (row stride ld): out[s][n][mc] = Y[s Mc + mc][n], zero beyond row M
+// out [S][N][Mc] <- Y [M, N] (row stride ld): out[s][n][mc] = Y[s Mc + mc][n], zero beyond row M.
+// 64 x 64 tiles through shared memory; a thread moves two adjacent elements each way, so a warp reads 64 consecutive
+// columns of a row and writes 64 consecutive rows of an output line (128 B each for bf16).  Mc % 64 == 0: a tile never
+// straddles two splits.
+template <typename T>
+struct Pair {
+  T a, b;
+};
 template <typename TI, typename AT>
 __global__ void __launch_bounds__(256)
 transpose_split_kernel(const TI* __restrict__ Y, int64_t ld, int64_t M, int N, AT* __restrict__ out, int64_t Mc, int S) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][65];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
-  const int n0 = blockIdx.y * 32;
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const bool pair_in = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(Y) & (2 * sizeof(TI) - 1)) == 0);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     const int64_t r = r0 + ty + 8 * j;
-    const int n = n0 + tx;
-    tile[ty + 8 * j][tx] = (r < M && n < N) ? to_float(Y[r * ld + n]) : 0.f;
+    const int n = n0 + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < M) {
+      if (pair_in && n + 1 < N) {
+        const Pair<TI> pr = *reinterpret_cast<const Pair<TI>*>(Y + r * ld + n);
+        v0 = to_float(pr.a);
+        v1 = to_float(pr.b);
+      } else {
+        if (n < N) v0 = to_float(Y[r * ld + n]);
+        if (n + 1 < N) v1 = to_float(Y[r * ld + n + 1]);
+      }
+    }
+    tile[ty + 8 * j][2 * tx] = v0;
+    tile[ty + 8 * j][2 * tx + 1] = v1;
   }
   __syncthreads();
   const int64_t Mp = Mc * S;
+  const int64_t s = r0 / Mc, mc0 = r0 - s * Mc;  // the whole tile lies in split s
+  if (r0 >= Mp) return;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     const int n = n0 + ty + 8 * j;
-    const int64_t r = r0 + tx;
-    if (n < N && r < Mp) {
-      const int64_t s = r / Mc, mc = r - s * Mc;
-      out[(s * N + n) * Mc + mc] = from_float<AT>(tile[tx][ty + 8 * j]);
+    if (n < N) {
+      Pair<AT> pr;
+      pr.a = from_float<AT>(tile[2 * tx][ty + 8 * j]);
+      pr.b = from_float<AT>(tile[2 * tx + 1][ty + 8 * j]);
+      *reinterpret_cast<Pair<AT>*>(out + (s * N + n) * Mc + mc0 + 2 * tx) = pr;
     }
   }
 }
@@ -570,7 +611,7 @@ int skinny_wgrad(const float* S, int T, const WT* Wd, int D, int64_t M, float* c
 
 template <typename TI, typename AT>
 int transpose_split(const TI* Y, int64_t ld, int64_t M, int N, AT* out, int64_t Mc, int S, cudaStream_t s) {
-  transpose_split_kernel<TI, AT><<<dim3(blocks_for(Mc * S, 32), blocks_for(N, 32)), 256, 0, s>>>(Y, ld, M, N, out, Mc, S);
+  transpose_split_kernel<TI, AT><<<dim3(blocks_for(Mc * S, 64), blocks_for(N, 64)), 256, 0, s>>>(Y, ld, M, N, out, Mc, S);
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }
@@ -626,14 +667,14 @@ int train_forward(const HeadWeightsView& w, const float* x_tok, const float* t, 
   freq_kernel<AT><<<blocks_for(M * 128), 256, 0, s>>>(t, M, p.f);
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.f, 256, wt1, 256, w.b_t1, p.t1p, D, M, D, 256, s));
-  silu_fwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(p.t1p, p.t1, MD);
+  silu_fwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.t1p, p.t1, MD);
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.t1, D, wt2, D, w.b_t2, p.s0, D, M, D, D, s));  // temb
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, z, Dc, static_cast<const AT*>(w.w_c1), Dc, w.b_c1, p.c1p, D, M, D, Dc, s));
-  silu_fwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(p.c1p, p.c1, MD);
+  silu_fwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.c1p, p.c1, MD);
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.c1, D, static_cast<const AT*>(w.w_c2), D, w.b_c2, p.s1, D, M, D, D, s));  // c
-  add_silu_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(p.s1, p.s0, p.zt, p.a, MD);
+  add_silu_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.s1, p.s0, p.zt, p.a, MD);
   NOVA_CHECK_LAUNCH();
   // all AdaLN statistics in one GEMM (normalization.py:34)
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.a, D, static_cast<const AT*>(w.w_ada), D, w.b_ada, p.st, n_ada, M, n_ada, D, s));
@@ -643,7 +684,7 @@ int train_forward(const HeadWeightsView& w, const float* x_tok, const float* t, 
     ln_mod_fwd_kernel<AT><<<row_blocks(M), THREADS, 0, s>>>(p.x[i], p.st, n_ada, (int64_t)3 * i * D, p.h[i], p.sx[i], M, D);
     NOVA_CHECK_LAUNCH();
     NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.h[i], D, static_cast<const AT*>(w.w_fc1[i]), D, w.b_fc1[i], p.p1[i], D, M, D, D, s));
-    silu_fwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(p.p1[i], p.u1[i], MD);
+    silu_fwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.p1[i], p.u1[i], MD);
     NOVA_CHECK_LAUNCH();
     NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.u1[i], D, static_cast<const AT*>(w.w_fc2[i]), D, w.b_fc2[i], p.u2[i], D, M, D, D, s));
     tail_fwd_kernel<AT><<<row_blocks(M), THREADS, 0, s>>>(p.u2[i], p.x[i], p.st, n_ada, (int64_t)3 * i * D + 2 * D, w.gamma[i],
@@ -707,7 +748,7 @@ int train_backward(const HeadWeightsView& w, const float* dv, const float* x_tok
     NOVA_PROPAGATE(wgrad<AT>(w, p, du2, D, D, p.u1[i], D, D, M, g.get(blk + "proj.fc2.weight"), s));
     AT* du1 = p.s0;  // dh of the block above has been consumed
     NOVA_PROPAGATE(gemm_nt<AT>(simt_path, du2, D, p.fc2T[i], D, nullptr, du1, D, M, D, D, s));
-    silu_bwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(du1, p.p1[i], du1, MD);  // dp1 in place
+    silu_bwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(du1, p.p1[i], du1, MD);  // dp1 in place
     NOVA_CHECK_LAUNCH();
     // fc1: p1 = h P1^T + b1
     NOVA_PROPAGATE(colsum<AT>(du1, D, M, D, p.colpart, g.get(blk + "proj.fc1.bias"), s));
@@ -751,23 +792,25 @@ int train_backward(const HeadWeightsView& w, const float* dv, const float* x_tok
   }
   AT* da = p.s0;
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.dst, n_ada, p.adaT, n_ada, nullptr, da, D, M, D, n_ada, s));
-  silu_bwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(da, p.zt, da, MD);  // dzt in place: zt = c + temb feeds both branches
+  silu_bwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(da, p.zt, da, MD);  // dzt in place: zt = c + temb feeds both branches
   NOVA_CHECK_LAUNCH();
   AT* dzt = da;
   // ---- timestep_proj (diffusion_mlp.py:59-60,74): temb = t1 Wt2^T + bt2, t1 = silu(f Wt1^T + bt1)
   NOVA_PROPAGATE(colsum<AT>(dzt, D, M, D, p.colpart, g.get("time_cond_embed.timestep_proj.fc2.bias"), s));
   NOVA_PROPAGATE(colsum<AT>(dzt, D, M, D, p.colpart, g.get("time_cond_embed.condition_proj.fc2.bias"), s));
   NOVA_PROPAGATE(wgrad<AT>(w, p, dzt, D, D, p.t1, D, D, M, g.get("time_cond_embed.timestep_proj.fc2.weight"), s));
-  NOVA_PROPAGATE(wgrad<AT>(w, p, dzt, D, D, p.c1, D, D, M, g.get("time_cond_embed.condition_proj.fc2.weight"), s));
+  // same dY and the same split: dzt^T is already in place if the gradient above was computed
+  NOVA_PROPAGATE(wgrad<AT>(w, p, dzt, D, D, p.c1, D, D, M, g.get("time_cond_embed.condition_proj.fc2.weight"), s,
+                           g.get("time_cond_embed.timestep_proj.fc2.weight") != nullptr));
   AT* d1 = p.s1;
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, dzt, D, p.t2T, D, nullptr, d1, D, M, D, D, s));
-  silu_bwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(d1, p.t1p, d1, MD);
+  silu_bwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(d1, p.t1p, d1, MD);
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(colsum<AT>(d1, D, M, D, p.colpart, g.get("time_cond_embed.timestep_proj.fc1.bias"), s));
   NOVA_PROPAGATE(wgrad<AT>(w, p, d1, D, D, p.f, 256, 256, M, g.get("time_cond_embed.timestep_proj.fc1.weight"), s));
   // ---- condition_proj (diffusion_mlp.py:61,75): c = c1 Wc2^T + bc2, c1 = silu(z Wc1^T + bc1)
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, dzt, D, p.c2T, D, nullptr, d1, D, M, D, D, s));
-  silu_bwd_kernel<AT><<<blocks_for(MD), 256, 0, s>>>(d1, p.c1p, d1, MD);
+  silu_bwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(d1, p.c1p, d1, MD);
   NOVA_CHECK_LAUNCH();
   NOVA_PROPAGATE(colsum<AT>(d1, D, M, D, p.colpart, g.get("time_cond_embed.condition_proj.fc1.bias"), s));
   NOVA_PROPAGATE(wgrad<AT>(w, p, d1, D, D, z, Dc, Dc, M, g.get("time_cond_embed.condition_proj.fc1.weight"), s));
