@@ -60,13 +60,17 @@ struct Plan {
   // (measured at cfg2: 4 stages instead of 6 for EVERY GEMM change nothing -- 34.1 / 23.8 ms of AdaLN / fc GEMMs per
   // pass against 35.4 / 23.3; a 3-stage ring with 3 staged chunk buffers was 3 % slower than 4 + 2).
   static constexpr int STAGES = TAIL ? (128 * 1024 / STAGE_BYTES) : (RING > 8 ? 8 : RING);
-  // EPI_TAIL: 2 buffers x {u chunk, x chunk} of 128 rows x 64 columns (16 KB each), filled by TMA, in front of the
-  // C staging; a warp copies its rows of a chunk into registers and hands the buffer straight back to the producer
+  // EPI_TAIL: T_BUFS buffers x {u chunk, x chunk} of 128 rows x 64 columns (16 KB each), filled by TMA.  The epilogue
+  // works IN PLACE: a warp reads u and x of its 32 rows from the buffer, writes the new x over the old one and stores
+  // its 32 x 64 slice from there by TMA -- no copy into registers (64 fewer), no separate C staging (32 KB that pay for
+  // the third buffer).  A buffer returns to the producer when the four warps of its column half have had their stores
+  // read it.
   static constexpr int T_CHUNK_BYTES = BM * C_CHUNK * 2;         // 16 KB
   static constexpr int T_BUF_BYTES = 2 * T_CHUNK_BYTES;          // u + x
+  static constexpr int T_BUFS = 3;
   static constexpr int OFF_TAIL = STAGES * STAGE_BYTES;
-  static constexpr int OFF_CSTAGE = OFF_TAIL + (TAIL ? 2 * T_BUF_BYTES : 0);  // 4 warps x 2 buffers x 4 KB
-  static constexpr int OFF_BIAS = OFF_CSTAGE + 4 * 2 * C_BUF_BYTES;  // one BN fp32 bias tile
+  static constexpr int OFF_CSTAGE = OFF_TAIL + (TAIL ? T_BUFS * T_BUF_BYTES : 0);  // 4 warps x 2 buffers x 4 KB (not EPI_TAIL)
+  static constexpr int OFF_BIAS = OFF_CSTAGE + (TAIL ? 0 : 4 * 2 * C_BUF_BYTES);  // one BN fp32 bias tile
   // EPI_TAIL: + one tile of gamma (fp32) and of beta as bf16 column pairs (exact for a bf16 head: its norm2 parameters
   // ARE bf16; all three tiles in fp32 would exceed the 227 KB by 136 B); with 225 KB of shared memory in use there is
   // next to no L1 left, so per-column constants must not come through it
@@ -429,11 +433,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P::OFF_BAR + 8 * (2 * STAGES + 4));
   // EPI_TAIL: full / empty barriers of the two staged {u, x} chunk buffers
-  auto tail_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };
-  auto tail_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 7 + b); };
+  auto tail_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };   // b < T_BUFS = 3
+  auto tail_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };
   // EPI_ADALN: epilogue warp q stages its 32 x 64 chunks of x through its two C staging buffers (TMA load, in-place
   // modulation, TMA store): one "landed" barrier per (warp, buffer)
-  auto xfull = [&](int qq, int b) { return bar_base + 8u * (2 * STAGES + 9 + 2 * qq + b); };
+  auto xfull = [&](int qq, int b) { return bar_base + 8u * (2 * STAGES + 11 + 2 * qq + b); };
 
   pdl_trigger();  // the next kernel may be scheduled as soon as resources free up; it waits for our completion itself
 #ifdef NOVA_GEMM_TIMELINE  // diagnostic build (scripts/profile_gemm_timeline.py): SM-clock stamps of CTA 0 in the debug words
@@ -467,8 +471,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), CG * epi_warps(EPI) * 32);  // every epilogue thread of every CTA of the group arrives
       if (EPI == EPI_TAIL) {
-        mbar_init(tail_full(b), 1);   // the tail producer's arrive.expect_tx
-        mbar_init(tail_empty(b), 4);  // one arrival per epilogue warp once it has copied its rows out
+        for (int t = b; t < P::T_BUFS; t += 2) {
+          mbar_init(tail_full(t), 1);   // the tail producer's arrive.expect_tx
+          mbar_init(tail_empty(t), 4);  // one arrival per warp of the column half once its store has read the buffer
+        }
       }
       if (EPI == EPI_ADALN)
         for (int qq = 0; qq < 4; ++qq) mbar_init(xfull(qq, b), 1);
@@ -544,21 +550,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (EPI == EPI_TAIL && warp == 3) {
     if (lane == 0) {  // ------------------------------------------------ tail producer: {u, x} chunks of my 128 rows
-      int tb = 0;
-      uint32_t tphase = 0;
+      int g = 0;  // running chunk index: chunk g lives in buffer g % T_BUFS
       for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
         const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
-        // chunk order 0, 2, 1, 3: buffer 0 feeds the epilogue warps of the left column half (chunks 0, 1), buffer 1
-        // those of the right half (chunks 2, 3)
-        for (int k = 0; k < BN / C_CHUNK; ++k) {
+        // chunk order 0, 2, 1, 3: the epilogue warps of the left column half take chunks 0, 1 (k = 0, 2), those of the
+        // right half chunks 2, 3 (k = 1, 3), so consecutive chunks go to alternating halves
+        for (int k = 0; k < BN / C_CHUNK; ++k, ++g) {
           const int cc = (k & 1) * 2 + (k >> 1);
-          mbar_wait(tail_empty(tb), tphase ^ 1u, dbg, 0x700u | tb);
+          const int tb = g % P::T_BUFS;
+          mbar_wait(tail_empty(tb), ((static_cast<uint32_t>(g / P::T_BUFS) & 1u) ^ 1u), dbg, 0x700u | tb);
           const uint32_t dst = base + P::OFF_TAIL + static_cast<uint32_t>(tb) * P::T_BUF_BYTES;
           mbar_expect_tx(tail_full(tb), P::T_BUF_BYTES);
           tma_load_2d(&tmap_c2, tail_full(tb), dst, n_idx + cc * C_CHUNK, m_idx);                     // u chunk
           tma_load_2d(&tmap_c3, tail_full(tb), dst + P::T_CHUNK_BYTES, n_idx + cc * C_CHUNK, m_idx);  // x chunk
-          if (++tb == 2) { tb = 0; tphase ^= 1u; }
         }
       }
     }
@@ -573,8 +578,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     float* bias_all = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     int buf = 0, cpar = 0;
     uint32_t buf_phase = 0;
-    int tb = 0;           // EPI_TAIL: staged {u, x} buffer in use
-    uint32_t tphase = 0;
+    int tile_it = 0;      // EPI_TAIL: tiles done so far (chunk indices follow the producer's order)
+    int prev_tb = -1;     // EPI_TAIL: staged buffer my last store still reads, -1 if none
     uint32_t xphase = 0u;  // EPI_ADALN: parities of my two x-staging barriers (bit b = buffer b)
 #ifdef NOVA_TAIL_TIMELINE  // diagnostic build: where an EPI_TAIL epilogue warp spends its cycles (CTA 0, first warp)
     long long tt_full = 0, tt_acc = 0, tt_store = 0, tt_bar = 0;
@@ -626,6 +631,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           gv[i] = in ? __ldg(p.gamma + n_idx + j) : 0.f;
           btv[i] = in ? __ldg(p.beta + n_idx + j) : 0.f;
         }
+      }
+      if (EPI == EPI_TAIL && prev_tb >= 0) {
+        // the staged buffer of the previous tile's last chunk goes back to the producer (its store has had the time of
+        // the loads above to read it); waiting until my next chunk would hold up the other half's next chunk
+        if (lane == 0) { tma_store_wait_read<0>(); mbar_arrive(tail_empty(prev_tb)); }
+        prev_tb = -1;
       }
       NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // every epilogue warp has finished reading the previous tile's bias
 #pragma unroll
@@ -742,23 +753,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int k = 0; k < 2; ++k) {
           const int cc = half * 2 + k;
           const int n0 = n_idx + cc * C_CHUNK;
-          // my rows of the staged {u, x} chunk -> registers, then the buffer goes straight back to the producer
-          NOVA_TT(tt_full, mbar_wait(tail_full(half), tphase, dbg, 0x800u | half));
-          tphase ^= 1u;  // each buffer serves one chunk per half tile: its phase flips every use
-          const uint32_t ub = base + P::OFF_TAIL + static_cast<uint32_t>(half) * P::T_BUF_BYTES +
-                              static_cast<uint32_t>(q * 32 + lane) * 128u;
-          uint4 uq[8], xq[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t off = static_cast<uint32_t>(c ^ (lane & 7)) << 4;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(uq[c].x), "=r"(uq[c].y), "=r"(uq[c].z), "=r"(uq[c].w) : "r"(ub + off));
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xq[c].x), "=r"(xq[c].y), "=r"(xq[c].z), "=r"(xq[c].w) : "r"(ub + P::T_CHUNK_BYTES + off));
+          // chunk index in the producer's order (0, 2, 1, 3 per tile: halves alternate) -> buffer and barrier phase
+          const int g = tile_it * (BN / C_CHUNK) + half + 2 * k;
+          const int tb = g % P::T_BUFS;
+          // the buffer of my previous chunk goes back to the producer once my store has read it
+          if (prev_tb >= 0) {
+            NOVA_TT(tt_store, { if (lane == 0) { tma_store_wait_read<0>(); mbar_arrive(tail_empty(prev_tb)); } });
+            prev_tb = -1;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tail_empty(half));
+          NOVA_TT(tt_full, mbar_wait(tail_full(tb), static_cast<uint32_t>(g / P::T_BUFS) & 1u, dbg, 0x800u | tb));
+          prev_tb = tb;
           if (m0 >= p.M || n0 >= p.N) continue;  // warp-uniform: nothing of this sub-tile is in bounds
-          NOVA_TT(tt_store, { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); });  // my single staging buffer: its last store (a chunk ago) has read it
-          const uint32_t dst = cbuf + static_cast<uint32_t>(lane) * 128u;
+          // my row of the staged chunk: u at ub, x (overwritten in place by the new x) at xb; 128 B rows, 128 B swizzle
+          const uint32_t ub = base + P::OFF_TAIL + static_cast<uint32_t>(tb) * P::T_BUF_BYTES +
+                              static_cast<uint32_t>(q * 32 + lane) * 128u;
+          const uint32_t xb = ub + P::T_CHUNK_BYTES;
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {  // 32 accumulator columns at a time keeps the register footprint bounded
             uint32_t ra[32];
@@ -768,8 +777,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const int c = hc * 4 + c4;
-              const uint32_t uw[4] = {uq[c].x, uq[c].y, uq[c].z, uq[c].w};
-              const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+              const uint32_t off = static_cast<uint32_t>(c ^ (lane & 7)) << 4;
+              uint32_t uw[4], xw[4];
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(uw[0]), "=r"(uw[1]), "=r"(uw[2]), "=r"(uw[3]) : "r"(ub + off));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xw[0]), "=r"(xw[1]), "=r"(xw[2]), "=r"(xw[3]) : "r"(xb + off));
               const uint4 bq = *reinterpret_cast<const uint4*>(bet_s + (col0 + c4 * 8) / 2);  // beta of 8 columns
               const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
               uint32_t w[4];
@@ -792,13 +803,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 s1v = add2(s1v, d2);
                 s2v = fma2(d2, d2, s2v);
               }
-              st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+              st_shared_v4(xb + off, w[0], w[1], w[2], w[3]);  // over the x it was computed from
             }
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmap_c, cbuf, n0, m0);
+          if (lane == 0) {  // my 32 x 64 slice of the buffer's x chunk
+            tma_store_2d(&tmap_c, base + P::OFF_TAIL + static_cast<uint32_t>(tb) * P::T_BUF_BYTES + P::T_CHUNK_BYTES +
+                                      static_cast<uint32_t>(q) * C_BUF_BYTES, n0, m0);
             tma_store_commit();
           }
         }
@@ -887,6 +899,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // all tcgen05.ld of this accumulator have completed: hand the buffer back to the MMA issuer
       if (CG == 1) mbar_arrive(tempty_bar(buf)); else mbar_arrive_cluster(tempty_bar(buf), 0u);
       if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
+      ++tile_it;
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging memory must outlive the last stores' reads
     if (threadIdx.x == EW0 * 32) NOVA_TL_STAMP(3);  // epilogue done
