@@ -67,6 +67,7 @@ struct Plan {
   // read it.
   static constexpr int T_CHUNK_BYTES = BM * C_CHUNK * 2;         // 16 KB
   static constexpr int T_BUF_BYTES = 2 * T_CHUNK_BYTES;          // u + x
+  // three: with a 3-stage operand ring four would fit (two per column half), measured 6 % slower on the AdaLN class
   static constexpr int T_BUFS = 3;
   static constexpr int OFF_TAIL = STAGES * STAGE_BYTES;
   static constexpr int OFF_CSTAGE = OFF_TAIL + (TAIL ? T_BUFS * T_BUF_BYTES : 0);  // 4 warps x 2 buffers x 4 KB (not EPI_TAIL)
@@ -433,11 +434,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P::OFF_BAR + 8 * (2 * STAGES + 4));
   // EPI_TAIL: full / empty barriers of the two staged {u, x} chunk buffers
-  auto tail_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };   // b < T_BUFS = 3
-  auto tail_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };
+  auto tail_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };   // b < T_BUFS
+  auto tail_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 9 + b); };
   // EPI_ADALN: epilogue warp q stages its 32 x 64 chunks of x through its two C staging buffers (TMA load, in-place
   // modulation, TMA store): one "landed" barrier per (warp, buffer)
-  auto xfull = [&](int qq, int b) { return bar_base + 8u * (2 * STAGES + 11 + 2 * qq + b); };
+  auto xfull = [&](int qq, int b) { return bar_base + 8u * (2 * STAGES + 5 + 2 * qq + b); };  // (never together with the tail barriers)
 
   pdl_trigger();  // the next kernel may be scheduled as soon as resources free up; it waits for our completion itself
 #ifdef NOVA_GEMM_TIMELINE  // diagnostic build (scripts/profile_gemm_timeline.py): SM-clock stamps of CTA 0 in the debug words
@@ -551,13 +552,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (EPI == EPI_TAIL && warp == 3) {
     if (lane == 0) {  // ------------------------------------------------ tail producer: {u, x} chunks of my 128 rows
       int g = 0;  // running chunk index: chunk g lives in buffer g % T_BUFS
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
+      int it = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
         const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
         const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
-        // chunk order 0, 2, 1, 3: the epilogue warps of the left column half take chunks 0, 1 (k = 0, 2), those of the
-        // right half chunks 2, 3 (k = 1, 3), so consecutive chunks go to alternating halves
+        // consecutive chunks go to alternating column halves (left half: tile chunks 0, 1; right half: 2, 3), and the
+        // half that is served first alternates from tile to tile, so neither half is always the one whose first chunk
+        // had the shorter head start
         for (int k = 0; k < BN / C_CHUNK; ++k, ++g) {
-          const int cc = (k & 1) * 2 + (k >> 1);
+          const int cc = (((k ^ it) & 1) * 2) + (k >> 1);
           const int tb = g % P::T_BUFS;
           mbar_wait(tail_empty(tb), ((static_cast<uint32_t>(g / P::T_BUFS) & 1u) ^ 1u), dbg, 0x700u | tb);
           const uint32_t dst = base + P::OFF_TAIL + static_cast<uint32_t>(tb) * P::T_BUF_BYTES;
@@ -754,7 +757,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int cc = half * 2 + k;
           const int n0 = n_idx + cc * C_CHUNK;
           // chunk index in the producer's order (0, 2, 1, 3 per tile: halves alternate) -> buffer and barrier phase
-          const int g = tile_it * (BN / C_CHUNK) + half + 2 * k;
+          const int g = tile_it * (BN / C_CHUNK) + ((half ^ tile_it) & 1) + 2 * k;
           const int tb = g % P::T_BUFS;
           // the buffer of my previous chunk goes back to the producer once my store has read it
           if (prev_tb >= 0) {
