@@ -591,6 +591,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #else
 #define NOVA_TT(acc, stmt) do { stmt; } while (0)
 #endif
+    // What an epilogue needs from global memory per tile -- its slice of the bias (gamma, beta) tile and its row's
+    // LayerNorm statistics -- is fetched ONE TILE AHEAD into registers: the round trips run under the previous tile's
+    // arithmetic instead of in front of this tile's barriers (ncu: a quarter of the tail epilogue's samples sat there).
+    using RP = RowPartials<EPI == EPI_TAIL ? 8 : 16>;  // the tail merges <= 8 partials of u (launch_tail), the modulation <= 16 of x
+    constexpr int NB = BN / (32 * epi_warps(EPI)) > 0 ? BN / (32 * epi_warps(EPI)) : 1;  // bias values per thread
+    RP rp_n;
+    float2 st2_n = make_float2(0.f, 0.f);
+    float bv_n[NB], gv_n[NB], btv_n[NB];
+    auto fetch = [&](int t) {
+      const int t_n = t % num_n;
+      const int t_m0 = (p.reverse_m ? num_m - 1 - t / num_n : t / num_n) * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
+      const bool t_mod = EPI == EPI_ADALN && t_n < p.n_mod_tiles;
+      if ((t_mod || EPI == EPI_TAIL) && t_m0 + lane < p.M) {
+        if (EPI == EPI_TAIL || p.stats_parts > 0) load_partials(p.part_in, p.stats_parts, p.M, t_m0 + lane, rp_n);
+        else st2_n = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(t_m0 + lane));
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int j = tid_e + i * 32 * epi_warps(EPI);
+        const bool in = j < BN && t_n * BN + j < p.N;
+        // modulation tiles: the scale half carries (1 + bias), so the epilogue forms 1 + scale with one addition
+        bv_n[i] = ((p.bias != nullptr && in) ? __ldg(p.bias + t_n * BN + j) : 0.f) + ((t_mod && j < 128) ? 1.0f : 0.f);
+        if (EPI == EPI_TAIL) {
+          gv_n[i] = in ? __ldg(p.gamma + t_n * BN + j) : 0.f;
+          btv_n[i] = in ? __ldg(p.beta + t_n * BN + j) : 0.f;
+        }
+      }
+    };
+    if (group < num_tiles) fetch(group);
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
       const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
@@ -615,26 +644,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         __syncwarp();
       }
-      RowPartials<EPI == EPI_TAIL ? 8 : 16> rp;  // the tail merges <= 8 partials of u (launch_tail), the modulation <= 16 of x
-      float2 st2 = make_float2(0.f, 0.f);
-      const bool stats_row = (mod_tile || EPI == EPI_TAIL) && m0 + lane < p.M;
-      if (stats_row) {
-        if (EPI == EPI_TAIL || p.stats_parts > 0) load_partials(p.part_in, p.stats_parts, p.M, m0 + lane, rp);
-        else st2 = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(m0 + lane));
-      }
-      constexpr int NB = BN / (32 * epi_warps(EPI)) > 0 ? BN / (32 * epi_warps(EPI)) : 1;  // bias values per thread
+      const RP rp = rp_n;  // this tile's values, requested a tile ago
+      const float2 st2 = st2_n;
       float bv[NB], gv[NB], btv[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
-        const int j = tid_e + i * 32 * epi_warps(EPI);
-        const bool in = j < BN && n_idx + j < p.N;
-        // modulation tiles: the scale half carries (1 + bias), so the epilogue forms 1 + scale with one addition
-        bv[i] = ((p.bias != nullptr && in) ? __ldg(p.bias + n_idx + j) : 0.f) + ((mod_tile && j < 128) ? 1.0f : 0.f);
-        if (EPI == EPI_TAIL) {
-          gv[i] = in ? __ldg(p.gamma + n_idx + j) : 0.f;
-          btv[i] = in ? __ldg(p.beta + n_idx + j) : 0.f;
-        }
+        bv[i] = bv_n[i];
+        gv[i] = EPI == EPI_TAIL ? gv_n[i] : 0.f;
+        btv[i] = EPI == EPI_TAIL ? btv_n[i] : 0.f;
       }
+      if (tile + num_groups < num_tiles) fetch(tile + num_groups);
       if (EPI == EPI_TAIL && prev_tb >= 0) {
         // the staged buffer of the previous tile's last chunk goes back to the producer (its store has had the time of
         // the loads above to read it); waiting until my next chunk would hold up the other half's next chunk
