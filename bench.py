@@ -424,7 +424,34 @@ def main():
         return ms, launches, clocks
 
     ms, launches, clocks = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    # e2e: HOST buffers through the public API.  Every step's H2D (pinned noise + z) and D2H (the points) is inside the
+    # timed region; nb.HostSampler issues the copy of step k+1 on a copy stream under the denoise of step k, so only the
+    # first copy of the region is exposed.  (step_e2e above is the same path without the overlap, kept for warm-up.)
+    def timed_e2e(steps):
+        pipe = nb.HostSampler(head, sched, total)
+        pipe.submit(z_h, noise_h)
+        pipe.collect(out_h)  # warm-up: staging slots allocated, loop graph captured for slot 0
+        pipe.submit(z_h, noise_h)
+        pipe.collect(out_h)  # ... and for slot 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe.submit(z_h, noise_h)
+        for k in range(steps):
+            if k + 1 < steps:
+                pipe.submit(z_h, noise_h)
+            pipe.collect(out_h)
+        e1.record()
+        barrier()
+        t_ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
+    timed(step_e2e, 1, 1)
+    ms_e2e = timed_e2e(args.steps)
     value = total / (ms * 1e-3)
     e2e_value = total / (ms_e2e * 1e-3)
 

@@ -17,6 +17,7 @@ from .pipeline import (  # noqa: F401
     NOVAPointCloudGenerationPipeline,
     NOVAPointCloudPipelineOutput,
     NOVATrainPointCloudPipeline,
+    HostSampler,
     denoise,
     gather_shards,
     generate_sets,

@@ -322,3 +322,58 @@ def sample_sharded(head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteSchedule
     """Data-parallel all-token sampling: this rank denoises its shard; one all-gather returns all clouds."""
     local = denoise(head, scheduler, z_local, noise_local, guidance_scaler)
     return gather_shards(local, total, group)
+
+
+class HostSampler:
+    """Sampling service for HOST-resident requests: the host->device copy of request k+1 runs on a copy stream under the
+    denoise of request k (two device staging slots), the device->host copy of the result is queued behind the gather.
+
+        sampler = HostSampler(head, scheduler, total)
+        sampler.submit(z_host, noise_host)                # pinned host tensors of this rank's shard
+        for k in range(K):
+            if k + 1 < K: sampler.submit(z_next, noise_next)
+            full = sampler.collect(out_host)             # (total, N, T) on the device; out_host filled asynchronously
+
+    Nothing here is arithmetic: CUDA streams and events around :func:`sample_sharded`.  A slot's staging tensors keep
+    their addresses, so the captured denoise loop is replayed for every request of a slot.
+    """
+
+    def __init__(self, head: DiffusionMLP, scheduler: FlowMatchEulerDiscreteScheduler, total: int,
+                 guidance_scaler: Optional[GuidanceScaler] = None, group=None, depth: int = 2):
+        if head.device.type != "cuda":
+            raise NovaError("HostSampler needs the head on a CUDA device; there is no CPU path")
+        self.head, self.scheduler, self.total, self.gs, self.group = head, scheduler, int(total), guidance_scaler, group
+        self.copy_stream = torch.cuda.Stream(device=head.device)
+        self.slots = [dict(z=None, noise=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(max(int(depth), 1))]
+        self.n_submitted = self.n_collected = 0
+
+    def submit(self, z_host: torch.Tensor, noise_host: torch.Tensor) -> int:
+        if self.n_submitted - self.n_collected >= len(self.slots):
+            raise NovaError("HostSampler: every staging slot holds a request that has not been collected")
+        slot = self.slots[self.n_submitted % len(self.slots)]
+        dev = self.head.device
+        with torch.cuda.stream(self.copy_stream):
+            if self.n_submitted >= len(self.slots):
+                self.copy_stream.wait_event(slot["free"])  # the denoise that last read this slot has consumed it
+            for key, src in (("z", z_host), ("noise", noise_host)):
+                if slot[key] is None or slot[key].shape != src.shape or slot[key].dtype != src.dtype:
+                    slot[key] = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                slot[key].copy_(src, non_blocking=True)
+            slot["ready"].record(self.copy_stream)
+        self.n_submitted += 1
+        return self.n_submitted - 1
+
+    @torch.no_grad()
+    def collect(self, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.n_collected >= self.n_submitted:
+            raise NovaError("HostSampler: nothing submitted")
+        slot = self.slots[self.n_collected % len(self.slots)]
+        cur = torch.cuda.current_stream(self.head.device)
+        cur.wait_event(slot["ready"])
+        local = denoise(self.head, self.scheduler, slot["z"], slot["noise"], self.gs)
+        slot["free"].record(cur)
+        full = gather_shards(local, self.total, self.group)
+        if out_host is not None:
+            out_host.copy_(full, non_blocking=True)
+        self.n_collected += 1
+        return full
