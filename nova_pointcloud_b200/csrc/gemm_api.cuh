@@ -66,6 +66,11 @@ int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* 
 int launch_batched(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, bf16* C, int64_t ldc, int M, int N, int K,
                    int batch_m_rows, cudaStream_t stream);
 
+// The same products from MN-major operands (no transposed copies): C[b] [n_rows, N] = Y[b]^T X[b], Y = source
+// [src_rows, n_rows], X = source [src_rows, N], batch b reducing over source rows [b k_len, (b + 1) k_len).
+int launch_batched_mn(const bf16* Y, int64_t ldy, const bf16* X, int64_t ldx, bf16* C, int64_t ldc, int src_rows, int n_rows,
+                      int N, int k_len, int batches, cudaStream_t stream);
+
 // gate GEMM with the block tail in its epilogue (CTA pairs, 256-column tiles; M > 128, N a multiple of 256)
 int launch_tail(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, const TailArgs& tail, int M, int N,
                 int K, cudaStream_t stream, bool reverse_m = false);

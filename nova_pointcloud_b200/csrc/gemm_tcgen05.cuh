@@ -284,12 +284,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major operand tile (the reduction index runs over the ROWS of the source matrix, as in a weight gradient
+// dW = dY^T X read straight from dY [M, N] and X [M, K]): TMA boxes of {64 MN elements = 128 B, 64 reduction rows} with
+// 128 B swizzle, one 8 KB box per 64 MN elements.  Canonical form (cute/atom/mma_traits_sm100.hpp, Major::MN, B128), in
+// 16-byte units: ((8, n), (8, k)) : ((1, LBO), (8, SBO)) -- 8 reduction rows of 128 B are one 1024 B swizzle atom
+// (SBO = 1024 B to the next 8 rows), the next 64 MN elements start LBO bytes on (8192 B: the next box).
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1,
 // b=BF16 [10,13)=1, both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+constexpr uint32_t IDESC_A_MN_MAJOR = 1u << 15, IDESC_B_MN_MAJOR = 1u << 16;
 
 struct EpiParams {
   const float* bias;  // [N] or nullptr
@@ -322,6 +337,10 @@ struct EpiParams {
   // operands, W is S stacked [batch_w_rows, K] operands, and row block m of the stacked output multiplies the W slab
   // of ITS batch.  batch_m_rows = 0: one ordinary GEMM.
   int batch_m_rows, batch_w_rows;
+  // MN-major form of the batched GEMM (no transposed copies): C[b] [batch_m_rows, N] = A[b]^T W[b], where A is the source
+  // matrix [rows, batch_m_rows] and W the source matrix [rows, N], both row-major, and batch b reduces over source rows
+  // [b K, (b + 1) K) (rows beyond the matrices read as zero).  CTA pairs, 256-column tiles.
+  int mn_major;
 };
 
 // merge `parts` equal-sized partials (mean_t, M2_t over n_t values each) of one row -> (mean, rstd).  Two halves so that
@@ -501,10 +520,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM;
         const int w_batch = p.batch_m_rows > 0 ? (m_tile * (BM * CG) / p.batch_m_rows) * p.batch_w_rows : 0;
         const int n_idx = (tile % num_n) * BN + static_cast<int>(rank) * P::B_ROWS + w_batch;  // CG == 2: my half of W
+        // MN-major batched form: batch b = m_tile / (tiles per batch); operand columns instead of operand rows
+        const int mn_tiles = (CG == 2 && p.mn_major) ? p.batch_m_rows / (BM * CG) : 1;
+        const int mn_b = m_tile / mn_tiles;
+        const int mn_a_col = (m_tile - mn_b * mn_tiles) * (BM * CG) + static_cast<int>(rank) * BM;
+        const int mn_w_col = (tile % num_n) * BN + static_cast<int>(rank) * P::B_ROWS;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, dbg, 0x100u | stage);
           const uint32_t sa = base + stage * STAGE_BYTES;
-          if (CG == 1) {
+          if (CG == 2 && p.mn_major) {
+            const int row = mn_b * p.K + kb * BK;  // source rows of this k-block
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+#pragma unroll
+            for (int at = 0; at < BM / 64; ++at)  // one 64 x 64 box (8 KB) per 64 MN elements
+              tma_load_2d_2sm(&tmap_a, full_bar(stage), sa + at * 8192, mn_a_col + at * 64, row);
+#pragma unroll
+            for (int at = 0; at < P::B_ROWS / 64; ++at)
+              tma_load_2d_2sm(&tmap_b, full_bar(stage), sa + A_STAGE_BYTES + at * 8192, mn_w_col + at * 64, row);
+          } else if (CG == 1) {
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(&tmap_a, full_bar(stage), sa, kb * BK, m_idx);
             tma_load_2d(&tmap_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_idx);
@@ -533,6 +566,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (tile == group && kb == 0) NOVA_TL_STAMP(1);  // first operands landed
           tcgen05_fence_after();
           const uint32_t sa = base + stage * STAGE_BYTES;
+          if (CG == 2 && p.mn_major) {
+            const uint64_t a_desc = make_smem_desc_mn_sw128(sa, 8192u);
+            const uint64_t b_desc = make_smem_desc_mn_sw128(sa + A_STAGE_BYTES, 8192u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // 16 reduction rows = two 1024 B swizzle atoms: +2048 B = +128 in 16 B units
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              umma_f16_2sm(d_tmem, a_desc + 128u * k, b_desc + 128u * k, idesc | IDESC_A_MN_MAJOR | IDESC_B_MN_MAJOR, acc);
+            }
+          } else {
           const uint64_t a_desc = make_smem_desc_sw128(sa);
           const uint64_t b_desc = make_smem_desc_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
@@ -541,6 +584,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             if (CG == 1) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
             else umma_f16_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
+          }
           }
           if (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_2sm(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -950,17 +994,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false,
-               float2* part_out = nullptr, const TailArgs* tail = nullptr, int batch_m_rows = 0, int batch_w_rows = 0) {
+               float2* part_out = nullptr, const TailArgs* tail = nullptr, int batch_m_rows = 0, int batch_w_rows = 0,
+               int mn_rows = 0) {
   using P = Plan<CG, BN, EPI == EPI_TAIL>;
   static std::atomic<unsigned long long> attr_done{0ull};  // one bit per device
   NOVA_PROPAGATE(ensure_smem_attr(reinterpret_cast<const void*>(gemm_kernel<EPI, CG, BN>), P::SMEM_BYTES, &attr_done));
   CUtensorMap ta, tb, tc_, tc2, tc3;
-  NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
-  // batched: W holds one [batch_w_rows, K] slab per batch (M / batch_m_rows of them)
-  NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, batch_m_rows > 0 ? static_cast<int64_t>(M / batch_m_rows) * batch_w_rows : N, K, ldw,
-                                  P::B_ROWS));
+  if (mn_rows > 0) {
+    // MN-major batched form: A = source [mn_rows, batch_m_rows] (row stride lda), W = source [mn_rows, N] (row stride ldw);
+    // boxes of {64 columns, 64 source rows}
+    NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, mn_rows, batch_m_rows, lda, 64));
+    NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, mn_rows, N, ldw, 64));
+  } else {
+    NOVA_PROPAGATE(make_tmap_kmajor(&ta, A, M, K, lda, BM));
+    // batched: W holds one [batch_w_rows, K] slab per batch (M / batch_m_rows of them)
+    NOVA_PROPAGATE(make_tmap_kmajor(&tb, W, batch_m_rows > 0 ? static_cast<int64_t>(M / batch_m_rows) * batch_w_rows : N, K, ldw,
+                                    P::B_ROWS));
+  }
   EpiParams p{};
-  p.batch_m_rows = batch_m_rows; p.batch_w_rows = batch_w_rows;
+  p.batch_m_rows = batch_m_rows; p.batch_w_rows = batch_w_rows; p.mn_major = mn_rows > 0 ? 1 : 0;
   p.bias = bias; p.M = M; p.N = N; p.K = K; p.reverse_m = reverse_m ? 1 : 0;
   p.part_out = part_out;
   if (EPI == EPI_ADALN) {
@@ -1017,11 +1069,11 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
 template <int EPI>
 int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                  int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out = nullptr,
-                 int batch_m_rows = 0, int batch_w_rows = 0) {
+                 int batch_m_rows = 0, int batch_w_rows = 0, int mn_rows = 0) {
 #define NOVA_GEMM_CASE(G, B) \
   if (cta_group == G && bn == B) \
     return launch_epi<EPI, G, B>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, nullptr, reverse_m, part_out, nullptr, \
-                                 batch_m_rows, batch_w_rows);
+                                 batch_m_rows, batch_w_rows, mn_rows);
   NOVA_GEMM_CASE(2, 256) NOVA_GEMM_CASE(1, 256) NOVA_GEMM_CASE(2, 128) NOVA_GEMM_CASE(1, 128) NOVA_GEMM_CASE(2, 64)
   NOVA_GEMM_CASE(1, 64)
 #undef NOVA_GEMM_CASE
@@ -1030,7 +1082,7 @@ int launch_plain(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const f
 }
 int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out,
-                int batch_m_rows = 0, int batch_w_rows = 0);
+                int batch_m_rows = 0, int batch_w_rows = 0, int mn_rows = 0);
 int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m);
 
@@ -1044,9 +1096,25 @@ int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const fl
 #if NOVA_GEMM_TU == 0
 int launch_bias(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m, float2* part_out,
-                int batch_m_rows, int batch_w_rows) {
+                int batch_m_rows, int batch_w_rows, int mn_rows) {
   return launch_plain<EPI_BIAS>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m, part_out,
-                                batch_m_rows, batch_w_rows);
+                                batch_m_rows, batch_w_rows, mn_rows);
+}
+
+// The same S products WITHOUT transposed copies (MN-major operands): C[b] [n_rows, N] = Y[b]^T X[b], where Y is the
+// source matrix [src_rows, n_rows] (row stride ldy), X the source matrix [src_rows, N] (row stride ldx), both row-major,
+// and batch b reduces over source rows [b k_len, (b + 1) k_len) (rows >= src_rows read as zero).  Outputs stacked.
+int launch_batched_mn(const bf16* Y, int64_t ldy, const bf16* X, int64_t ldx, bf16* C, int64_t ldc, int src_rows, int n_rows,
+                      int N, int k_len, int batches, cudaStream_t stream) {
+  if (n_rows <= 0 || N <= 0 || batches <= 0) return NOVA_OK;
+  NOVA_REQUIRE(n_rows % (2 * BM) == 0, "tcgen05 MN-major gemm: output rows per batch must be a multiple of %d", 2 * BM);
+  NOVA_REQUIRE(k_len > 0 && k_len % BK == 0 && ldy % 8 == 0 && ldx % 8 == 0 && ldc % 8 == 0 && N % 8 == 0,
+               "tcgen05 MN-major gemm: reduction length must be a multiple of %d, leading dimensions of 8", BK);
+  NOVA_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "tcgen05 MN-major gemm: operands must be 16-byte aligned");
+  return launch_bias(Y, ldy, X, ldx, nullptr, C, ldc, batches * n_rows, N, k_len, stream, 2, BN_FULL, false, nullptr, n_rows, N,
+                     src_rows);
 }
 
 // S = M / batch_m_rows GEMMs in one launch: C[b] [batch_m_rows, N] = A[b] [batch_m_rows, K] W[b] [batch_w_rows = N, K]^T,

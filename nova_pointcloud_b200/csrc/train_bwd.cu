@@ -23,6 +23,7 @@
 // Gradients are WRITTEN (not accumulated) as fp32 in the reference's state_dict shapes; the residual-stream gradient
 // is carried in fp32.  Nothing here is on the sampling path; the product never falls back to the CPU.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -538,6 +539,15 @@ struct Plan {
   size_t bytes;
 };
 
+// NOVA_B200_WGRAD_TRANSPOSE=1 restores the K-major weight gradients (split-major transposed copies + launch_batched)
+inline bool mn_major_wgrad() {
+  static const bool on = [] {
+    const char* e = std::getenv("NOVA_B200_WGRAD_TRANSPOSE");
+    return e == nullptr || std::atoi(e) == 0;
+  }();
+  return on;
+}
+
 inline int pick_split(bool tensor_path, int64_t M, int n_rows, int k_out) {
   if (!tensor_path) return 1;
   const int64_t tiles = ceil_div(n_rows, 256) * ceil_div(k_out, 256);
@@ -567,8 +577,11 @@ Plan<AT> make_plan(const HeadWeightsView& w, void* base, int64_t M) {
   p.dx = cv.take<float>(m * D);
   p.Mp = static_cast<int64_t>(align_up(m, 64) + 64 * 16);  // any split S <= 16 with 64-aligned chunks fits
   const size_t wide = n_ada, narrow = D > Dc ? (D > 256 ? D : 256) : (Dc > 256 ? Dc : 256);
-  p.yt = cv.take<AT>(wide * p.Mp);
-  p.xt = cv.take<AT>(narrow * p.Mp);
+  // split-major transposed copies: only the K-major weight-gradient path needs them (SIMT GEMMs, or
+  // NOVA_B200_WGRAD_TRANSPOSE=1); the MN-major tensor-core path reads dY and X as they lie
+  const bool need_t = !(std::is_same<AT, bf16>::value && !w.use_simt_gemm && mn_major_wgrad());
+  p.yt = cv.take<AT>(need_t ? wide * p.Mp : 8);
+  p.xt = cv.take<AT>(need_t ? narrow * p.Mp : 8);
   // S partial products of an [n_rows, k_out] gradient with S <= ceil(74 / tiles), tiles = (n_rows / 256) ceil(k_out / 256):
   // S n_rows k_out <= 74 * 256 * 256 + n_rows k_out for every shape
   p.partial = cv.take<AT>((size_t)75 * 65536 + n_ada * narrow);
@@ -625,6 +638,15 @@ int wgrad(const HeadWeightsView& w, const Plan<AT>& p, const AT* dY, int64_t ldy
   const bool tensor_path = std::is_same<AT, bf16>::value && !w.use_simt_gemm;
   const int S = pick_split(tensor_path, M, n_rows, k_out);
   const int64_t Mc = static_cast<int64_t>(align_up(static_cast<size_t>(ceil_div(M, S)), 64));
+  if (tensor_path && n_rows % 256 == 0 && mn_major_wgrad()) {
+    // MN-major operands: the tensor cores read dY [M, n_rows] and X [M, k_out] as they lie (TMA boxes of 64 columns x
+    // 64 rows, the reduction running over the rows) -- no transposed copies at all
+    NOVA_PROPAGATE(tc::launch_batched_mn(reinterpret_cast<const bf16*>(dY), ldy, reinterpret_cast<const bf16*>(X), ldx,
+                                         reinterpret_cast<bf16*>(p.partial), k_out, (int)M, n_rows, k_out, (int)Mc, S, s));
+    splitk_reduce_kernel<AT><<<blocks_for((int64_t)n_rows * k_out), 256, 0, s>>>(p.partial, S, (int64_t)n_rows * k_out, out);
+    NOVA_CHECK_LAUNCH();
+    return NOVA_OK;
+  }
   if (!yt_ready) NOVA_PROPAGATE((transpose_split<AT, AT>(dY, ldy, M, n_rows, p.yt, Mc, S, s)));
   NOVA_PROPAGATE((transpose_split<AT, AT>(X, ldx, M, k_out, p.xt, Mc, S, s)));
   if (tensor_path && n_rows % 256 == 0) {

@@ -28,6 +28,7 @@ def ev():
 for _ in range(2):
     v, ws = ops.head_train_forward(h, x, t, z)
     ops.head_backward(h, v * 1e-3, x, z, ws, shapes)
+    del ws  # as autograd does after backward: one workspace alive at a time
 torch.cuda.synchronize()
 e = [ev() for _ in range(3)]
 fw = bw = 0.0
@@ -40,7 +41,9 @@ for _ in range(3):
     torch.cuda.synchronize()
     fw += e[0].elapsed_time(e[1]) / 3
     bw += e[1].elapsed_time(e[2]) / 3
+    nbytes = ws.numel()
+    del ws
 fwd_flop = 2.0 * M * (256 * D + D * D + Dc * D + D * D + 20 * D * D + 12 * D * D + 2 * T * D)
 print(json.dumps({"D": D, "rows": M, "forward_ms": round(fw, 2), "backward_ms": round(bw, 2),
                   "forward_tflops": round(fwd_flop / fw / 1e9, 1), "backward_tflops": round(2 * fwd_flop / bw / 1e9, 1),
-                  "workspace_gb": round(ws.numel() / 2**30, 2), "finite": bool(all(torch.isfinite(g_).all() for g_ in grads.values()))}))
+                  "workspace_gb": round(nbytes / 2**30, 2), "finite": bool(all(torch.isfinite(g_).all() for g_ in grads.values()))}))
