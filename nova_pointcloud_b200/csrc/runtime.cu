@@ -3,6 +3,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <unordered_map>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -79,7 +80,34 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+namespace {
+// Encoded tensor maps are pure functions of (pointer, shape, stride, box): a launch-heavy eager pass (training step,
+// first pass of a sampling call before its graph exists) re-creates the same few dozen maps over and over, so they
+// are kept per host thread (no locking; the map is a 128-byte POD that is copied into the kernel parameters anyway).
+struct TmapKey {
+  const void* ptr;
+  int64_t rows, K, ld;
+  int box_rows;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (int64_t v : {k.rows, k.K, k.ld, static_cast<int64_t>(k.box_rows)}) h = h * 1000003u ^ std::hash<int64_t>()(v);
+    return h;
+  }
+};
+thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t TMAP_CACHE_MAX = 4096;
+}  // namespace
+
 int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  const TmapKey key{ptr, rows, K, ld, box_rows};
+  auto hit = g_tmap_cache.find(key);
+  if (hit != g_tmap_cache.end()) {
+    *map = hit->second;
+    return NOVA_OK;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -97,6 +125,8 @@ int make_tmap_kmajor(CUtensorMap* map, const bf16* ptr, int64_t rows, int64_t K,
               (long long)K, (long long)ld);
     return NOVA_ERR_CUDA;
   }
+  if (g_tmap_cache.size() >= TMAP_CACHE_MAX) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *map);
   return NOVA_OK;
 }
 

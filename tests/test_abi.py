@@ -45,8 +45,11 @@ def test_sass_is_blackwell_native():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    # tcgen05.mma (both CTA groups), TMA loads / stores / multicast, tcgen05.ld, packed fp32 pairs in the epilogues,
+    # cluster barriers of the chain kernel; no legacy mma.sync
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "FFMA2", "FADD2", "UCGABAR"):
         assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA.", "")
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
