@@ -521,8 +521,9 @@ def main():
             fl = algorithmic_flops(width, max(clouds_local, 0) * points)
             tf_leg = fl / (ms_leg * 1e-3) / 1e12
             ada_ms_, ada_n_ = pr["gemm_ada"]
-            n_ada_ = (3 * DEPTH + 2) * width
-            ada_tf_ = (2.0 * clouds_local * points * n_ada_ * width * S_STEPS / max(ada_n_, 1)) / (ada_ms_ / max(ada_n_, 1) * 1e-3) / 1e12 if ada_n_ else 0.0
+            # the modulation GEMMs: N = 2 * width for each of the DEPTH + 1 launches of a step (the gate columns are the
+            # separate gemm_tail class)
+            ada_tf_ = (2.0 * clouds_local * points * 2 * width * width) / (ada_ms_ / max(ada_n_, 1) * 1e-3) / 1e12 if ada_n_ else 0.0
             tot = sum(v[0] for v in pr.values()) or 1.0
             return {"value": clouds_total / (ms_leg * 1e-3), "unit": "clouds/s", "ms_per_pass": ms_leg, "n_gpus": world,
                     "clouds_total": clouds_total, "clouds_this_gpu": clouds_local, "points": points, "width": width,
@@ -531,7 +532,7 @@ def main():
                                       "frac": tf_leg / pk["sustained"], "frac_of_burst": tf_leg / pk["burst"]},
                     "roofline": {"bound": "tensor", "achieved": ada_tf_, "peak": pk["sustained"], "unit": "TFLOP/s",
                                  "frac": ada_tf_ / pk["sustained"], "frac_of_burst": ada_tf_ / pk["burst"],
-                                 "kernel": "AdaLN statistics GEMM, in situ (rank 0)", "launches_timed": ada_n_},
+                                 "kernel": "modulation GEMM (M x 2D x D, EPI_ADALN), in situ (rank 0)", "launches_timed": ada_n_},
                     "kernel_shares": {k: round(v[0] / tot, 4) for k, v in pr.items() if v[1]},
                     "clocks": clk}
 
@@ -867,12 +868,13 @@ def main():
                       "share": v[0] / prof_total} for k, v in prof.items() if v[1]}
         ada_ms, ada_n = prof["gemm_ada"]
         ada_avg_ms = ada_ms / max(ada_n, 1)
-        n_ada = (3 * DEPTH + 2) * D
-        # algorithmic FLOP of the AdaLN-statistics GEMMs of one sampling step (all of it is needed), spread
-        # over the launches the library used for them (one N = 3D GEMM per block + one N = 2D final GEMM)
-        ada_flops_step = 2.0 * B * N * n_ada * D * S_STEPS
-        ada_flops = ada_flops_step * prof_steps / max(ada_n, 1)
+        # the dominant kernel: the modulation GEMM, M x 2D x D, DEPTH + 1 launches per diffusion step (every launch has
+        # the same shape; the gate columns of the AdaLN projection are the separate gemm_tail class)
+        ada_flops = 2.0 * B * N * 2 * D * D
         ada_tf = ada_flops / (ada_avg_ms * 1e-3) / 1e12 if ada_n else 0.0
+        tail_ms, tail_n = prof.get("gemm_tail", (0.0, 0))
+        tail_avg_ms = tail_ms / max(tail_n, 1)
+        tail_tf = 2.0 * B * N * D * D / (tail_avg_ms * 1e-3) / 1e12 if tail_n else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):  # dram bytes per launch from the committed ncu --set full capture
@@ -892,15 +894,20 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ada_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": ada_tf / pk["sustained"], "traffic": traffic,
-                         "kernel": "nova::tc::gemm_kernel<EPI_ADALN | EPI_TAIL, cta_group 2>: the AdaLN statistics GEMMs of the step "
-                                   "(dominant class, 3D of the 5D output columns per block): modulation part M x 2D x D with "
-                                   "LN(x)(1+scale)+shift in its epilogue and gate part M x D x D with the block tail "
-                                   "x += LN(u) gamma gate in its epilogue; FLOP and time averaged over both kinds of launch",
+                         "kernel": "nova::tc::gemm_kernel<EPI_ADALN, cta_group 2>: modulation GEMM M x 2D x D of the AdaLN projection "
+                                   "with h = LN(x)(1+scale)+shift in its epilogue (x staged by TMA); the dominant kernel of the step "
+                                   "by time (kernel_shares.gemm_ada)",
                          "flop_per_launch": ada_flops, "avg_launch_ms": ada_avg_ms, "launches_timed": ada_n,
                          "how": "CUDA events recorded by the library around every launch on the launching stream, "
                                 "inside real sampling steps (nova_profile_*)",
                          "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
                          "frac_of_burst": ada_tf / pk["burst"]},
+            "roofline_tail": {"bound": "tensor", "achieved": tail_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
+                              "frac": tail_tf / pk["sustained"], "flop_per_launch": 2.0 * B * N * D * D,
+                              "avg_launch_ms": tail_avg_ms, "launches_timed": tail_n,
+                              "kernel": "nova::tc::gemm_kernel<EPI_TAIL, cta_group 2>: gate GEMM M x D x D with the block tail "
+                                        "x += (LN(u) gamma + beta) gate in its epilogue (in place on TMA-staged chunks); "
+                                        "epilogue-paced, the step's second kernel by time"},
             "step_roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                               "frac": achieved / pk["sustained"], "frac_of_burst": achieved / pk["burst"],
                               "what": "whole sampling step per GPU: algorithmic FLOP (BASELINE.md section 3: "

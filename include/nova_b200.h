@@ -288,9 +288,11 @@ NOVA_API void nova_launch_count_reset(void);
 /*
  * In-situ kernel timing for bench.py: while enabled (per calling thread), CUDA events are recorded on
  * the launching stream around every launch of these kernel classes:
- *   0 = AdaLN GEMM (M x 20D x D), 1 = other GEMMs (fc1 / fc2 / condition), 2 = row kernels, 3 = prep, 4 = other,
- *   5 = the cluster chain kernel (small M: all stages of a step after the statistics GEMM in one launch).
- * nova_profile_read sums the elapsed ms and launches per class (arrays of >= 6 entries), then clears.
+ *   0 = AdaLN statistics GEMMs (the modulation GEMM M x 2D x D of the fused step; M x 20D x D in the wide dataflow),
+ *   1 = other GEMMs (fc1 / fc2 / condition), 2 = row kernels, 3 = prep, 4 = other,
+ *   5 = the cluster chain kernel (small M: all stages of a step after the statistics GEMM in one launch),
+ *   6 = the gate GEMM M x D x D with the block tail in its epilogue.
+ * nova_profile_read sums the elapsed ms and launches per class (arrays of >= 7 entries), then clears.
  */
 NOVA_API int nova_profile_enable(int32_t on);
 NOVA_API int nova_profile_read(double* ms_by_class, int64_t* launches_by_class, int32_t n_classes);

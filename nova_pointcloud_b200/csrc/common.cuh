@@ -18,7 +18,7 @@ void count_launch(int n = 1);
 
 // In-situ kernel timing (nova_profile_*): CUDA events recorded around launches of one kernel class on
 // the launching stream, so bench.py can report per-kernel durations measured inside the real step.
-enum KernelClass : int { KC_GEMM_ADA = 0, KC_GEMM_FC = 1, KC_ROW = 2, KC_PREP = 3, KC_OTHER = 4, KC_CHAIN = 5, KC_COUNT = 6 };
+enum KernelClass : int { KC_GEMM_ADA = 0, KC_GEMM_FC = 1, KC_ROW = 2, KC_PREP = 3, KC_OTHER = 4, KC_CHAIN = 5, KC_GEMM_TAIL = 6, KC_COUNT = 7 };
 bool profile_enabled();
 void profile_begin(int kernel_class, cudaStream_t stream);
 void profile_end(cudaStream_t stream);

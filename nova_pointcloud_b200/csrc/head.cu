@@ -317,7 +317,7 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
                                 EPI_BIAS, s, 0, flip(), tail ? w.uparts : nullptr));
     }
     if (tail) {  // gate part (N = D) + block tail in its epilogue
-      ProfileScope ps(KC_GEMM_ADA, s);
+      ProfileScope ps(KC_GEMM_TAIL, s);
       tc::TailArgs ta{};
       ta.u = u2; ta.ldu = D; ta.x = x; ta.ldx = D; ta.gamma = h->gamma[i]; ta.beta = h->beta[i];
       ta.u_parts = w.uparts; ta.x_parts = w.xparts; ta.n_parts = parts;

@@ -548,7 +548,7 @@ def launch_count_reset():
     _lib.lib().nova_launch_count_reset()
 
 
-KERNEL_CLASSES = ("gemm_ada", "gemm_fc", "row", "prep", "other", "chain")
+KERNEL_CLASSES = ("gemm_ada", "gemm_fc", "row", "prep", "other", "chain", "gemm_tail")
 
 
 def profile_enable(on: bool):
