@@ -193,6 +193,81 @@ int main(void) {
     return 1;
   }
 
+  /* earth mover's distance (auction algorithm): clouds 0,1 against clouds 2,3.  The matching is a permutation, its mean
+     distance is at least the mean nearest-neighbour distance (Chamfer lower bound), and a cloud matches itself at 0 */
+  float* d_emd;
+  int* d_assign;
+  int* d_status;
+  CUDA(cudaMalloc((void**)&d_emd, sizeof(float) * 2));
+  CUDA(cudaMalloc((void**)&d_assign, sizeof(int) * 2 * N));
+  CUDA(cudaMalloc((void**)&d_status, sizeof(int) * 2));
+  CHECK(nova_emd(d_out, d_out + 2 * N * T, 2, N, 1e-5f, 400000, d_emd, d_assign, d_status, stream));
+  float h_emd[2];
+  static int h_assign[2 * N], h_status[2], seen[N];
+  CUDA(cudaStreamSynchronize(stream));
+  CUDA(cudaMemcpy(h_emd, d_emd, sizeof(h_emd), cudaMemcpyDeviceToHost));
+  CUDA(cudaMemcpy(h_assign, d_assign, sizeof(h_assign), cudaMemcpyDeviceToHost));
+  CUDA(cudaMemcpy(h_status, d_status, sizeof(h_status), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < 2; ++c) {
+    memset(seen, 0, sizeof(seen));
+    for (int i = 0; i < N; ++i) {
+      const int j = h_assign[c * N + i];
+      if (j < 0 || j >= N || seen[j]++) { fprintf(stderr, "EMD assignment of pair %d is not a permutation at %d\n", c, i); return 1; }
+    }
+    if (h_status[c] <= 0) { fprintf(stderr, "EMD pair %d did not converge (status %d)\n", c, h_status[c]); return 1; }
+  }
+  if ((h_emd[0] + h_emd[1]) * N < cd - 1e-3) { fprintf(stderr, "EMD %g below the Chamfer bound %g\n", h_emd[0] + h_emd[1], cd / N); return 1; }
+  CHECK(nova_emd(d_out, d_out, 2, N, 1e-5f, 400000, d_emd, NULL, NULL, stream));
+  CUDA(cudaStreamSynchronize(stream));
+  CUDA(cudaMemcpy(h_emd, d_emd, sizeof(h_emd), cudaMemcpyDeviceToHost));
+  if (h_emd[0] != 0.0f || h_emd[1] != 0.0f) { fprintf(stderr, "EMD of a cloud with itself: %g %g\n", h_emd[0], h_emd[1]); return 1; }
+
+  /* one training step of the head (what autograd does for the reference between get_losses and loss.backward()):
+     forward with per-row timesteps, then the gradients of two parameters and of z.  d loss / d head.bias is the column
+     sum of dv, which the host can check exactly enough */
+  const size_t tr_bytes = nova_head_train_bytes(head, M);
+  void* d_tr = NULL;
+  CUDA(cudaMalloc(&d_tr, tr_bytes));
+  float *d_t, *d_v, *d_dv, *d_gbias, *d_gfc1, *d_dz;
+  float* h_t = (float*)malloc(sizeof(float) * M);
+  for (int64_t i = 0; i < M; ++i) h_t[i] = 500.0f * (frand() + 1.0f);
+  CUDA(cudaMalloc((void**)&d_t, sizeof(float) * M));
+  CUDA(cudaMalloc((void**)&d_v, sizeof(float) * M * T));
+  CUDA(cudaMalloc((void**)&d_dv, sizeof(float) * M * T));
+  CUDA(cudaMalloc((void**)&d_gbias, sizeof(float) * T));
+  CUDA(cudaMalloc((void**)&d_gfc1, sizeof(float) * D * D));
+  CUDA(cudaMalloc((void**)&d_dz, sizeof(float) * M * D));
+  CUDA(cudaMemcpy(d_t, h_t, sizeof(float) * M, cudaMemcpyHostToDevice));
+  CHECK(nova_head_train_forward(head, d_noise, d_t, d_z, M, d_v, d_tr, tr_bytes, stream));
+  float* h_v = (float*)malloc(sizeof(float) * M * T);
+  CUDA(cudaStreamSynchronize(stream));
+  CUDA(cudaMemcpy(h_v, d_v, sizeof(float) * M * T, cudaMemcpyDeviceToHost));
+  double colsum[T] = {0.0, 0.0, 0.0};
+  for (int64_t i = 0; i < M * T; ++i) {  /* loss = sum(v^2) / (2 M): dv = v / M */
+    h_v[i] /= (float)M;
+    colsum[i % T] += h_v[i];
+  }
+  CUDA(cudaMemcpy(d_dv, h_v, sizeof(float) * M * T, cudaMemcpyHostToDevice));
+  const char* gnames[2] = {"head.bias", "blocks.0.proj.fc1.weight"};
+  float* gptrs[2] = {d_gbias, d_gfc1};
+  CHECK(nova_head_backward(head, d_dv, d_noise, d_z, M, 2, gnames, gptrs, d_dz, d_tr, tr_bytes, stream));
+  float h_gbias[T];
+  static float h_gfc1[D * D];
+  CUDA(cudaStreamSynchronize(stream));
+  CUDA(cudaMemcpy(h_gbias, d_gbias, sizeof(h_gbias), cudaMemcpyDeviceToHost));
+  CUDA(cudaMemcpy(h_gfc1, d_gfc1, sizeof(h_gfc1), cudaMemcpyDeviceToHost));
+  double gnorm = 0.0;
+  for (int i = 0; i < D * D; ++i) {
+    if (!isfinite(h_gfc1[i])) { fprintf(stderr, "non-finite weight gradient at %d\n", i); return 1; }
+    gnorm += fabs(h_gfc1[i]);
+  }
+  for (int k = 0; k < T; ++k)
+    if (fabs(h_gbias[k] - colsum[k]) > 1e-4 * (fabs(colsum[k]) + 1e-3)) {
+      fprintf(stderr, "head.bias gradient %g vs column sum %g\n", h_gbias[k], colsum[k]);
+      return 1;
+    }
+  if (gnorm == 0.0) { fprintf(stderr, "zero fc1 weight gradient\n"); return 1; }
+
   /* error path: a too-small workspace must be refused with a message, not crash */
   if (nova_head_sample(head, d_noise, d_z, NULL, B, B, N, N, timesteps, sigmas, S, &g, d_out, d_ws, 1024, stream) != NOVA_ERR_WORKSPACE) {
     fprintf(stderr, "small workspace was not rejected\n");
