@@ -126,6 +126,7 @@ struct nova_head {
   // statistics travel between kernels as per-tile partials.  No separate HBM-bound row kernel per block, and the gate
   // tensor never exists.  NOVA_B200_FUSE_TAIL=0 restores the resid kernel.
   bool fuse_tail = true;
+  bool fuse_cfg = true;   // guided steps of the fused dataflow: combine + Euler inside the head-out kernel (NOVA_B200_FUSE_CFG=0: separate kernel)
   bool use_chain = true;
   bool chained(int64_t rows) const {
     return use_chain && cfg.dtype == NOVA_BF16 && !use_simt_gemm && !fused(rows) && rows <= chain::profitable_rows(cfg.width);
@@ -261,6 +262,11 @@ struct StepIO {
   float* xt_out;       // Euler-updated latent [M, T] or nullptr (then xt_in = x_tok)
   float dt;
   const void* st_pre = nullptr;  // wide dataflow: this step's statistics were computed ahead (forked branch)
+  // guided step with the combine fused into the head-out kernel (fused dataflow, T == 3, no renorm): M = passes * Mx
+  // rows, latent rows x_tok [Mx, T] stepped in place
+  int cfg_passes = 0;   // 0: plain head-out
+  int cfg_mode = 0;     // 0 two-pass, 1 image, 2 spatiotemporal (three-pass)
+  float cfg_scale = 0.f, cfg_scale3 = 0.f;
 };
 
 // bf16 / tcgen05 dataflow with the AdaLN modulation fused into the statistics GEMM's epilogue:
@@ -336,6 +342,9 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
                                     D, fin, (int)M, 2 * D, D, s, 0, flip()));
   }
   ProfileScope ps(KC_ROW, s);
+  if (io.cfg_passes > 0)
+    return rw::headout_cfg_bf16(hh, h->w_head, h->b_head, const_cast<float*>(io.x_tok), io.dt, io.x_rows, D, io.cfg_passes,
+                                io.cfg_mode, io.cfg_scale, io.cfg_scale3, s);
   return rw::headout_bf16(hh, h->w_head, h->b_head, io.v_out, io.x_tok, io.xt_out, io.dt, M, D, T, s);
 }
 
@@ -536,6 +545,9 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const r
     return gemm<AT>(h, a_buf, h->D(), static_cast<const AT*>(h->w_ada), h->D(), h->b_ada, st_buf, h->n_ada(), M, h->n_ada(),
                     h->D(), EPI_BIAS, st);
   };
+  // the fused dataflow's head-out kernel can do the guidance combine itself when no per-cloud renorm is asked for
+  const bool fuse_cfg = guided && h->fuse_cfg && w.st == nullptr && T == 3 && !(g->renorm < 1.0f) &&
+                        (B == 2 * Bx || B == 3 * Bx) && (gmode == 0 ? B == 2 * Bx : B == 3 * Bx);
   auto run_loop = [&](cudaStream_t st, bool forked) -> int {
     bool active = guided;
     forked = forked && w.st != nullptr && h->can_fork(M, S);
@@ -555,7 +567,14 @@ int sample_impl(const nova_head* h, const float* noise_tok, const AT* z, const r
       io.x_rows = Mx;
       io.dt = dts.v[i];
       if (forked) io.st_pre = static_cast<const AT*>(w.st) + static_cast<size_t>(i & 1) * M * h->n_ada();
-      if (active) {
+      if (active && fuse_cfg) {  // guidance combine + Euler inside the head-out kernel: same launch count as unguided
+        io.M = M;
+        io.cfg_passes = static_cast<int>(B / Bx);
+        io.cfg_mode = gmode;
+        io.cfg_scale = g->scale;
+        io.cfg_scale3 = gscale3;
+        NOVA_PROPAGATE(head_step<AT>(h, w, io, st));
+      } else if (active) {
         io.M = M;
         io.v_out = w.v;
         NOVA_PROPAGATE(head_step<AT>(h, w, io, st));
@@ -719,6 +738,7 @@ extern "C" int nova_head_create(const nova_head_config* cfg, nova_head_t** out) 
   if (const char* env_alt = std::getenv("NOVA_B200_ALTERNATE")) h->alternate_rows = std::atoi(env_alt) != 0;
   if (const char* env_chain = std::getenv("NOVA_B200_CHAIN")) h->use_chain = std::atoi(env_chain) != 0;
   if (const char* env_tail = std::getenv("NOVA_B200_FUSE_TAIL")) h->fuse_tail = std::atoi(env_tail) != 0;
+  if (const char* env_cfg = std::getenv("NOVA_B200_FUSE_CFG")) h->fuse_cfg = std::atoi(env_cfg) != 0;
   const char* env_graph = std::getenv("NOVA_B200_GRAPH");
   h->use_graphs = env_graph == nullptr || std::atoi(env_graph) != 0;
   if (h->use_graphs && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -682,6 +682,86 @@ headout3_kernel(const bf16* __restrict__ y, const float* __restrict__ Wh, const 
   }
 }
 
+// Velocity head of a GUIDED step with the guidance combine and the Euler update in the same kernel (no renorm):
+// row r of the conditional pass, row r + Mx of the unconditional pass (and r + 2 Mx of the third pass) share latent
+// row r, so one warp forms the two (three) head outputs, combines them as GuidanceScaler.scale does
+// (guidance_scaler.py:74-87; the formulas of cfg_euler_kernel with ratio == 1) and steps the latent
+// (scheduling_cfm.py:136).  Each head output is the same fmaf chain and butterfly as in headout3_kernel, so the result
+// is bit-identical to headout3 + cfg_euler_kernel; the [passes, Mx, 3] velocity tensor is never written.
+template <int VPL, bool WREG>
+__global__ void __launch_bounds__(THREADS, ROWLOOP_CTAS_PER_SM)
+headout3_cfg_kernel(const bf16* __restrict__ y, const float* __restrict__ Wh, const float* __restrict__ bh,
+                    float* __restrict__ x_sel, float dt, int64_t Mx, int D, int passes, int mode, float scale,
+                    float scale3) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float wh_s[];  // !WREG: [3, D] head weights staged once per CTA
+  float w[WREG ? 3 : 1][VPL][8];
+  if (WREG) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) load8(Wh + (int64_t)t * D + (i * 32 + lane) * 8, w[t][i]);
+  } else {
+    for (int e = threadIdx.x * 4; e < 3 * D; e += THREADS * 4)
+      *reinterpret_cast<float4*>(wh_s + e) = *reinterpret_cast<const float4*>(Wh + e);
+    __syncthreads();
+  }
+  const float bias = lane < 3 ? bh[lane] : 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * WARPS + warp; row < Mx; row += stride) {
+    uint4 q[3][VPL];  // the passes' rows of y, all requested before the first is used
+#pragma unroll
+    for (int ps = 0; ps < 3; ++ps) {
+      if (ps < passes) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) q[ps][i] = reinterpret_cast<const uint4*>(y + (row + ps * Mx) * D)[i * 32 + lane];
+      }
+    }
+    const float xin = lane < 3 ? x_sel[row * 3 + lane] : 0.f;
+    float vp[3] = {0.f, 0.f, 0.f};  // lane t < 3: output t of pass ps
+#pragma unroll
+    for (int ps = 0; ps < 3; ++ps) {
+      if (ps < passes) {
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          float x[8];
+          unpack8(q[ps][i], x);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            if (WREG) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[t] = fmaf(x[j], w[t][i][j], acc[t]);
+            } else {
+              float wv[8];
+              load8(wh_s + t * D + (i * 32 + lane) * 8, wv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[t] = fmaf(x[j], wv[j], acc[t]);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+          acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
+          acc[2] += __shfl_xor_sync(0xffffffffu, acc[2], o);
+        }
+        vp[ps] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + bias;
+      }
+    }
+    if (lane < 3) {
+      const float c = vp[0], u = vp[1], t3 = vp[2];
+      float v;
+      if (mode == 0) v = fmaf(c - u, scale, u);
+      else if (mode == 1) v = fmaf(t3 - u, scale3, fmaf(c - t3, scale, u));
+      else v = fmaf(c - t3, scale3, fmaf(c - u, scale, u));
+      x_sel[row * 3 + lane] = __fadd_rn(__fmul_rn(v, dt), xin);
+    }
+  }
+}
+
 int num_sms_rw();  // SM count of the current device (runtime.cu)
 inline unsigned rowloop_grid(int64_t M, int ctas_per_sm) {
   const int64_t want = ceil_div(M, WARPS), cap = (int64_t)num_sms_rw() * ctas_per_sm;
@@ -952,6 +1032,18 @@ __global__ void permute_patch_kernel(const TS* __restrict__ src, float* __restri
 }
 
 
+template <typename AT, int VPL>
+struct HeadoutCfgLauncher {
+  static int run(const AT* y, const float* Wh, const float* bh, float* x_sel, float dt, int64_t Mx, int D, int passes,
+                 int mode, float scale, float scale3, cudaStream_t s) {
+    launch_pdl(headout3_cfg_kernel<VPL, (VPL <= 3)>, dim3(rowloop_grid(Mx, ROWLOOP_CTAS_PER_SM)), dim3(THREADS),
+               (VPL <= 3) ? 0 : 3 * D * sizeof(float), s, reinterpret_cast<const bf16*>(y), Wh, bh, x_sel, dt, Mx, D, passes,
+               mode, scale, scale3);
+    NOVA_CHECK_LAUNCH();
+    return NOVA_OK;
+  }
+};
+
 // ------------------------------------------------------------------ out-of-line entry points
 // The heavy instantiations (8 widths x kernel variants) live in their own translation units so that they build
 // in parallel with head.cu:  rowwise_row_f32.cu, rowwise_row_bf16.cu (launch_row) and rowwise_fused.cu (the
@@ -964,6 +1056,9 @@ int resid_bf16(const bf16* u, const bf16* x_in, const bf16* gate, const float* g
                float* rowstats, int64_t M, int D, int reverse, cudaStream_t stream);
 int headout_bf16(const bf16* y, const float* Wh, const float* bh, float* v_out, const float* xt_in, float* xt_out, float dt,
                  int64_t M, int D, int T, cudaStream_t stream);
+// T == 3 only: head + guidance combine (passes = 2 | 3 over Mx latent rows each) + Euler step of x_sel in place
+int headout_cfg_bf16(const bf16* y, const float* Wh, const float* bh, float* x_sel, float dt, int64_t Mx, int D, int passes,
+                     int mode, float scale, float scale3, cudaStream_t stream);
 
 }  // namespace rw
 }  // namespace nova

@@ -16,5 +16,9 @@ int headout_bf16(const bf16* y, const float* Wh, const float* bh, float* v_out, 
                  int64_t M, int D, int T, cudaStream_t stream) {
   return dispatch_vpl<bf16, HeadoutLauncher>(D, y, Wh, bh, v_out, xt_in, xt_out, dt, M, D, T, stream);
 }
+int headout_cfg_bf16(const bf16* y, const float* Wh, const float* bh, float* x_sel, float dt, int64_t Mx, int D, int passes,
+                     int mode, float scale, float scale3, cudaStream_t stream) {
+  return dispatch_vpl<bf16, HeadoutCfgLauncher>(D, y, Wh, bh, x_sel, dt, Mx, D, passes, mode, scale, scale3, stream);
+}
 }  // namespace rw
 }  // namespace nova

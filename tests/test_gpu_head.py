@@ -180,6 +180,48 @@ def test_three_pass_guidance_matches_oracle(mode, kw):
     assert relmax(outb, refb) < 5e-2
 
 
+@pytest.mark.parametrize("mode,kw", [
+    ("two_pass", dict()),
+    ("two_pass_trunc", dict(guidance_trunc=400.0)),
+    ("two_pass_ids", dict()),
+    ("img", dict(image_guidance_scale=1.5)),
+    ("st", dict(spatiotemporal_guidance_scale=0.8)),
+])
+def test_guidance_combine_in_the_headout_kernel(monkeypatch, mode, kw):
+    """Fused (large-M) dataflow, T = 3, no renorm: the guidance combine (guidance_scaler.py:74-87) and the Euler step
+    run inside the head-out kernel, so a guided step launches what an unguided one does.  Bit-identical to the
+    separate combine kernel (NOVA_B200_FUSE_CFG=0) and within the bf16 tolerance of the oracle."""
+    import nova_pointcloud_b200 as nb
+
+    monkeypatch.setenv("NOVA_B200_WIDE_ADA_ROWS", "0")  # the fused dataflow at test-sized row counts
+    passes = 3 if mode in ("img", "st") else 2
+    B, N, D = 2, 160, 768
+    head, x, z, _, pred_ids = make_case(2, D, D, B, N, 1, n_pred=70 if mode == "two_pass_ids" else None)
+    g = torch.Generator().manual_seed(78)
+    zz = torch.cat([z] + [torch.randn(z.shape, generator=g) for _ in range(passes - 1)]).bfloat16()
+    pp = None if pred_ids is None else torch.cat([pred_ids] * passes)
+    hb = head.to(torch.bfloat16)
+    ref = OL.denoise(cpu_sd(hb, torch.float32), zz.float(), x, pred_ids=pp, guidance_scale=3.0, **kw)
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(25)
+    outs, counts = [], []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("NOVA_B200_FUSE_CFG", fuse)  # read when the library handle is created
+        import copy
+
+        hh = copy.deepcopy(hb).cuda()  # a copy packs its own handle
+        gs = nb.GuidanceScaler(guidance_scale=3.0, **kw)
+        for _ in range(3):  # eager, graph capture, replay
+            nb.ops.launch_count_reset()
+            out = nb.denoise(hh, sched, zz.cuda(), x.cuda(), gs.clone(), None, None if pp is None else pp.cuda())
+        outs.append(out)
+        counts.append(nb.ops.launch_count())
+    assert torch.equal(outs[0], outs[1])
+    assert relmax(outs[0], ref) < 5e-2
+    guided_steps = sum(1 for t in sched.timesteps if not (kw.get("guidance_trunc", 0.0) > 0 and float(t) < kw["guidance_trunc"]))
+    assert counts[1] - counts[0] == guided_steps  # one launch less per guided step
+
+
 @pytest.mark.parametrize("shift,steps", [(3.0, 10), (1.0, 1)])
 def test_sample_fp32_other_schedules(shift, steps):
     import nova_pointcloud_b200 as nb
