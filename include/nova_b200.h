@@ -123,6 +123,16 @@ NOVA_API int nova_head_forward(const nova_head_t* h, const float* x_tok, const f
                       float* v_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * DiffusionMLP.forward with a PRE-EMBEDDED input: a 3-D x passes through PatchEmbed.forward unchanged
+ * (diffnext/models/embeddings.py:160-166), so the blocks start from the caller's rows.
+ *   x_emb [B, N, D] handle dtype; t, t_per_token, z, v_out, workspace as nova_head_forward (same workspace size).
+ * No pred_ids: the reference's scatter target patchify(x) does not exist for an embedded input.
+ */
+NOVA_API int nova_head_forward_embedded(const nova_head_t* h, const void* x_emb, const float* t, int32_t t_per_token,
+                                        const void* z, int64_t B, int64_t N, float* v_out, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+
+/*
  * The fused sampling loop (denoise): S Euler steps of the head with the condition
  * projection hoisted out of the loop and the latent kept in fp32.
  *   noise_tok [Bx, N, T] fp32   initial latent, token layout

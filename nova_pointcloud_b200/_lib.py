@@ -19,7 +19,7 @@ EPI_BIAS, EPI_BIAS_SILU = 0, 1
 EXPORTS = [
     "nova_last_error", "nova_abi_version", "nova_device_check", "nova_head_create", "nova_head_destroy",
     "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
-    "nova_head_sample", "nova_head_generate_sets", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
+    "nova_head_sample", "nova_head_forward_embedded", "nova_head_generate_sets", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
     "nova_debug_chain_timeline", "nova_debug_words_clear", "nova_comm_unique_id", "nova_comm_init_rank",
     "nova_comm_destroy", "nova_allgather", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_farthest_point_sampling", "nova_add_noise", "nova_flow_loss",
@@ -63,6 +63,8 @@ def _declare(lib):
     lib.nova_head_workspace_bytes.argtypes = [vp, i64, i32]
     lib.nova_head_forward.restype = C.c_int
     lib.nova_head_forward.argtypes = [vp, vp, vp, i32, vp, vp, i64, i64, i64, i64, vp, vp, sz, vp]
+    lib.nova_head_forward_embedded.restype = C.c_int
+    lib.nova_head_forward_embedded.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, vp, sz, vp]
     lib.nova_head_sample.restype = C.c_int
     lib.nova_head_sample.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, C.POINTER(C.c_float),
                                      C.POINTER(C.c_double), i32, C.POINTER(Guidance), vp, vp, sz, vp]

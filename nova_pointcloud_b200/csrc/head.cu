@@ -264,6 +264,7 @@ struct StepIO {
   const void* st_pre = nullptr;  // wide dataflow: this step's statistics were computed ahead (forked branch)
   // guided step with the combine fused into the head-out kernel (fused dataflow, T == 3, no renorm): M = passes * Mx
   // rows, latent rows x_tok [Mx, T] stepped in place
+  const void* x_emb = nullptr;   // [M, D] handle dtype: rows that are already embedded (x_tok is then unused by the embed stage)
   int cfg_passes = 0;   // 0: plain head-out
   int cfg_mode = 0;     // 0 two-pass, 1 image, 2 spatiotemporal (three-pass)
   float cfg_scale = 0.f, cfg_scale3 = 0.f;
@@ -287,7 +288,12 @@ int head_step_fused(const nova_head* h, const Workspace& w, const StepIO& io, cu
                static_cast<const bf16*>(w.c), w.temb, io.rows_per_t, io.t_offset, a, M, D);
     NOVA_CHECK_LAUNCH();
   }
-  {
+  if (io.x_emb != nullptr) {
+    ProfileScope ps(KC_ROW, s);
+    rw::adopt_rows_kernel<bf16><<<(unsigned)ceil_div(M, rw::WARPS), rw::THREADS, 0, s>>>(static_cast<const bf16*>(io.x_emb), x,
+                                                                                        w.rstat, M, D, 1e-6f);
+    NOVA_CHECK_LAUNCH();
+  } else {
     ProfileScope ps(KC_ROW, s);
     NOVA_PROPAGATE(rw::embed_bf16(io.x_tok, io.x_rows, h->w_patchT, h->b_patch, x, w.rstat, M, D, T, s));
   }
@@ -371,7 +377,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
     NOVA_PROPAGATE(gemm<AT>(h, static_cast<const AT*>(w.a), D, static_cast<const AT*>(h->w_ada), D, h->b_ada,
                             static_cast<AT*>(w.st), n_ada, M, n_ada, D, EPI_BIAS, s));
   }
-  if (h->chained(M)) {
+  if (h->chained(M) && io.x_emb == nullptr) {
     chain::ChainParams cp{};
     cp.M = M; cp.D = D; cp.T = T; cp.depth = depth;
     cp.x = static_cast<bf16*>(w.x); cp.h = static_cast<bf16*>(w.h);
@@ -389,6 +395,7 @@ int head_step(const nova_head* h, const Workspace& w, const StepIO& io, cudaStre
   p.M = M; p.D = D; p.T = T;
   p.x_in = w.x; p.x_out = w.x; p.u = w.u2; p.st = io.st_pre ? io.st_pre : w.st; p.ldst = n_ada; p.h_out = w.h;
   p.x_tok = io.x_tok; p.x_rows = io.x_rows; p.Wp = h->w_patch; p.WpT = h->w_patchT; p.bp = h->b_patch;
+  p.x_emb = io.x_emb;
   p.Wh = h->w_head; p.bh = h->b_head;
   p.v_out = io.v_out; p.xt_in = io.x_tok; p.xt_out = io.xt_out; p.dt = io.dt;
   const int64_t final_off = static_cast<int64_t>(3) * depth * D;
@@ -444,7 +451,7 @@ int check_call(const nova_head* h, int64_t B, int64_t Bx, int64_t N, int64_t n, 
 template <typename AT>
 int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_per_token, const AT* z,
                  const int64_t* pred_ids, int64_t B, int64_t Bx, int64_t N, int64_t n, float* v_out, void* ws,
-                 cudaStream_t s) {
+                 cudaStream_t s, const AT* x_emb = nullptr) {
   const int64_t M = B * n;
   if (M == 0) return NOVA_OK;
   pdl_set_for_rows(M);
@@ -461,7 +468,7 @@ int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_p
     z_rows = static_cast<const AT*>(w.zsel);
   }
   const float* x_rows = x_tok;
-  if (pred_ids || Bx != B) {
+  if (x_emb == nullptr && (pred_ids || Bx != B)) {
     rw::gather_tok_kernel<<<(unsigned)ceil_div(M * T, 256), 256, 0, s>>>(x_tok, rw::IdsView{pred_ids, n, B}, w.xsel, B, Bx,
                                                                          N, n, T, bad_ids_word());
     NOVA_CHECK_LAUNCH();
@@ -470,6 +477,7 @@ int forward_impl(const nova_head* h, const float* x_tok, const float* t, int t_p
   NOVA_PROPAGATE(time_embedding(h, t, R, w, s));
   NOVA_PROPAGATE(cond_embedding<AT>(h, z_rows, M, w, s));
   StepIO io{M, t_per_token ? 1 : n, 0, x_rows, M, v_out, nullptr, 0.f};
+  io.x_emb = x_emb;
   return head_step<AT>(h, w, io, s);
 }
 
@@ -978,6 +986,20 @@ extern "C" int nova_head_forward(const nova_head_t* h, const float* x_tok, const
                                workspace, s);
   return forward_impl<bf16>(h, x_tok, t, t_per_token, static_cast<const bf16*>(z), pred_ids, B, Bx, N, n, v_out, workspace,
                             s);
+}
+
+extern "C" int nova_head_forward_embedded(const nova_head_t* h, const void* x_emb, const float* t, int32_t t_per_token,
+                                          const void* z, int64_t B, int64_t N, float* v_out, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  NOVA_PROPAGATE(check_call(h, B, B, N, N, workspace, workspace_bytes, 0, "nova_head_forward_embedded"));
+  if (B * N == 0) return NOVA_OK;
+  NOVA_REQUIRE(x_emb && t && z && v_out, "nova_head_forward_embedded: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->cfg.dtype == NOVA_F32)
+    return forward_impl<float>(h, nullptr, t, t_per_token, static_cast<const float*>(z), nullptr, B, B, N, N, v_out, workspace,
+                               s, static_cast<const float*>(x_emb));
+  return forward_impl<bf16>(h, nullptr, t, t_per_token, static_cast<const bf16*>(z), nullptr, B, B, N, N, v_out, workspace, s,
+                            static_cast<const bf16*>(x_emb));
 }
 
 extern "C" int nova_head_sample(const nova_head_t* h, const float* noise_tok, const void* z, const int64_t* pred_ids,

@@ -153,6 +153,8 @@ struct RowParams {
   const float* Wp;     // [D, T] token-order patch-embed weight
   const float* WpT;    // [T, D] its transpose: vector loads (same fmaf chain per feature: bias, then t = 0, 1, ..)
   const float* bp;     // [D]
+  const void* x_emb = nullptr;  // !HAS_PREV, row kernels only: [M, D] rows that are ALREADY embedded (PatchEmbed.forward passes
+                                // a 3-D input through, embeddings.py:165); nullptr: embed x_tok
   const void* u;       // [M, D]   fc2 output of the finished block (HAS_PREV)
   const void* st;      // [M, ldst] all AdaLN statistics of this step
   int64_t ldst;
@@ -202,7 +204,7 @@ __device__ __forceinline__ void load8_cg(const bf16* p, float (&v)[8]) {
 }
 __device__ __forceinline__ void load8_cg(const float* p, float (&v)[8]) { load8(p, v); }
 
-template <typename AT, int VPL, bool HAS_PREV, int OUT, bool COHERENT = false>
+template <typename AT, int VPL, bool HAS_PREV, int OUT, bool COHERENT = false, bool EMBEDDED = false>
 __device__ __forceinline__ void row_body(const RowParams& p, const int64_t row, const int lane) {
   const int D = p.D;
   const float inv_d = 1.0f / static_cast<float>(D);
@@ -240,6 +242,15 @@ __device__ __forceinline__ void row_body(const RowParams& p, const int64_t row, 
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       if (COHERENT) load8_cg(xin + (i * 32 + lane) * 8, x[i]); else load8(xin + (i * 32 + lane) * 8, x[i]);
+    }
+  } else if (EMBEDDED) {
+    // the caller's rows are the embedded tokens already; the residual stream starts as a copy of them
+    const AT* xe = static_cast<const AT*>(p.x_emb) + row * D;
+    AT* xout = static_cast<AT*>(p.x_out) + row * D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      load8(xe + (i * 32 + lane) * 8, x[i]);
+      if (OUT == 0) store8(xout + (i * 32 + lane) * 8, x[i]);
     }
   } else {
     // PatchEmbed with K = T (embeddings.py:146,165): too skinny for a GEMM, fused here
@@ -357,7 +368,8 @@ row_kernel(const RowParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
   if (row >= p.M) return;
-  row_body<AT, VPL, HAS_PREV, OUT>(p, row, lane);
+  if (!HAS_PREV && p.x_emb != nullptr) row_body<AT, VPL, HAS_PREV, OUT, false, !HAS_PREV>(p, row, lane);
+  else row_body<AT, VPL, HAS_PREV, OUT>(p, row, lane);
 }
 
 template <typename AT, int VPL>
@@ -834,6 +846,32 @@ rowstats_kernel(const AT* __restrict__ x, float* __restrict__ rowstats, int64_t 
   const AT* xr = x + row * D;
   float s = 0.f;
   for (int e = lane; e < D; e += 32) s += to_float(xr[e]);
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    const float d = to_float(xr[e]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+  if (lane == 0) *reinterpret_cast<float2*>(rowstats + 2 * row) = make_float2(mean, rstd);
+}
+
+// Pre-embedded rows (DiffusionMLP.forward with a 3-D x: PatchEmbed passes it through, embeddings.py:165) entering the
+// fused dataflow: the residual stream starts as a copy of the caller's rows, with their LayerNorm statistics
+template <typename AT>
+__global__ void __launch_bounds__(THREADS)
+adopt_rows_kernel(const AT* __restrict__ x_emb, AT* __restrict__ x_out, float* __restrict__ rowstats, int64_t M, int D,
+                  float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= M) return;
+  const AT* xr = x_emb + row * D;
+  float s = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    const AT v = xr[e];
+    x_out[row * D + e] = v;
+    s += to_float(v);
+  }
   const float mean = warp_sum(s) / static_cast<float>(D);
   float q = 0.f;
   for (int e = lane; e < D; e += 32) {

@@ -172,12 +172,21 @@ class DiffusionMLP(nn.Module):
     def forward(self, x, timestep, z, pred_ids=None) -> torch.Tensor:
         """Velocity prediction (diffusion_mlp.py:89-99).
 
-        x: (B,C,H*p,W*p) image layout; timestep (B,) or (B,N); z (B,N,Dc); pred_ids (B,n,1) int64.
+        x: (B,C,H*p,W*p) image layout, or (B,N,D) rows that are embedded already (then no pred_ids);
+        timestep (B,) or (B,N); z (B,N,Dc); pred_ids (B,n,1) int64.
         Returns (B,N,T) in the module dtype; with ``pred_ids`` the rows that are not listed
         carry the patchified input, exactly like the reference's scatter into ``patchify(x)``.
         """
+        if x.dim() == 3:
+            # PatchEmbed.forward passes a 3-D input through unchanged (embeddings.py:160-166): the rows are embedded
+            # tokens already.  The reference then cannot take pred_ids (its scatter target patchify(x) needs the latent).
+            if pred_ids is not None:
+                raise NovaError("pre-embedded (B,N,D) inputs cannot be combined with pred_ids (no latent to scatter into)")
+            h = self.handle()
+            return torch.ops.nova_b200.head_forward_embedded(x.to(self.dtype), timestep.float(), z.to(self.dtype),
+                                                             h.id).to(z.dtype)
         if x.dim() != 4:
-            raise NovaError("pre-embedded (B,N,D) inputs are not supported: pass the (B,C,H*p,W*p) latent")
+            raise NovaError(f"x must be the (B,C,H*p,W*p) latent or pre-embedded (B,N,D) rows; got {tuple(x.shape)}")
         self.patch_embed.set_hw(x)
         tok = self.patch_embed.patchify(x)
         h = self.handle()

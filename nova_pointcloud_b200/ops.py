@@ -172,6 +172,40 @@ def _(x_tok, t, z, pred_ids, handle):
     return x_tok.new_empty((z.shape[0], n, x_tok.shape[-1]), dtype=torch.float32)
 
 
+@torch.library.custom_op("nova_b200::head_forward_embedded", mutates_args=(), device_types="cuda")
+def head_forward_embedded(x_emb: torch.Tensor, t: torch.Tensor, z: torch.Tensor, handle: int) -> torch.Tensor:
+    """Velocity for PRE-EMBEDDED rows, (B, N, T) fp32.  See nova_head_forward_embedded in nova_b200.h."""
+    h = HeadHandle.get(handle)
+    if z.dim() != 3 or z.dtype != h.dtype or not z.is_cuda:
+        raise NovaError(f"z must be a CUDA (B, N, Dc) tensor of the handle dtype; got {tuple(z.shape)} {z.dtype}")
+    B, N = z.shape[0], z.shape[1]
+    if tuple(x_emb.shape) != (B, N, h.cfg.width) or x_emb.dtype != h.dtype or x_emb.device != z.device:
+        raise NovaError(f"embedded x must be (B, N, D)=({B}, {N}, {h.cfg.width}) in the handle dtype on z's device; "
+                        f"got {tuple(x_emb.shape)} {x_emb.dtype}")
+    if z.shape[2] != h.cfg.cond_width:
+        raise NovaError(f"z must have Dc={h.cfg.cond_width} features; got {z.shape[2]}")
+    x_emb = x_emb.contiguous()
+    z = z.contiguous()
+    t = t.contiguous().float()
+    per_token = 1 if t.dim() == 2 else 0
+    if per_token and tuple(t.shape) != (B, N):
+        raise NovaError(f"per-token timesteps must be (B, N)=({B}, {N}); got {tuple(t.shape)}")
+    if not per_token and t.numel() != B:
+        raise NovaError(f"timestep must have B={B} entries; got {tuple(t.shape)}")
+    out = torch.empty(B, N, h.cfg.token_dim, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        ws = h.workspace(B * N, 0)
+        check(_lib.lib().nova_head_forward_embedded(h._h, _ptr(x_emb), _ptr(t), per_token, _ptr(z), B, N, _ptr(out), _ptr(ws),
+                                                    ws.numel(), _stream()), "nova_head_forward_embedded")
+    return out
+
+
+@head_forward_embedded.register_fake
+def _(x_emb, t, z, handle):
+    h = HeadHandle.get(handle)
+    return x_emb.new_empty((z.shape[0], z.shape[1], h.cfg.token_dim), dtype=torch.float32)
+
+
 @torch.library.custom_op("nova_b200::head_sample", mutates_args=(), device_types="cuda")
 def head_sample(noise_tok: torch.Tensor, z: torch.Tensor, pred_ids: Optional[torch.Tensor], handle: int,
                 timesteps: Sequence[float], sigmas: Sequence[float], guidance_scale: float, guidance_trunc: float,

@@ -129,6 +129,20 @@ def head_tokens(
     return F.linear(y, sd["head.weight"], sd["head.bias"])
 
 
+def head_embedded(sd: Dict[str, torch.Tensor], x_emb: torch.Tensor, timestep: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """``DiffusionMLP.forward`` with a PRE-EMBEDDED input (diffusion_mlp.py:89-99): ``PatchEmbed.forward`` returns a
+    3-D x unchanged (embeddings.py:160-166), so the blocks start from the caller's rows.  x_emb (B,N,D) -> (B,N,T)."""
+    depth, D, Dc, T, p, C = head_dims(sd)
+    t = time_embedding(sd, timestep, z.dtype)
+    t = t.unsqueeze(1) if t.dim() == 2 else t
+    zt = cond_embedding(sd, z) + t
+    x = x_emb.to(z.dtype)
+    for i in range(depth):
+        x = block(sd, i, x, zt)
+    y, _ = adaln(sd, "norm", x, zt, 2)
+    return F.linear(y, sd["head.weight"], sd["head.bias"])
+
+
 def head_forward(
     sd: Dict[str, torch.Tensor],
     x: torch.Tensor,

@@ -53,6 +53,36 @@ def test_forward_fp32_pred_ids_and_per_token_timesteps():
     assert relmax(head(x.cuda(), t_tok.cuda(), z.cuda()), ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("dtype,depth,D,B,N,wide_rows,per_token", [
+    (torch.float32, 2, 256, 2, 37, None, False),       # fp32 handle: SIMT GEMM + row kernels
+    (torch.float32, 0, 256, 1, 9, None, False),        # no blocks: rows -> final modulation -> head
+    (torch.bfloat16, 6, 768, 3, 77, "1000000", True),  # bf16 wide dataflow (launch chain: the chain kernel embeds itself)
+    (torch.bfloat16, 6, 768, 3, 77, "0", False),       # bf16 fused dataflow, tail epilogue, 231 ragged rows
+    (torch.bfloat16, 2, 1024, 1, 130, "0", True),      # second row block ragged
+])
+def test_forward_pre_embedded_rows(monkeypatch, dtype, depth, D, B, N, wide_rows, per_token):
+    """DiffusionMLP.forward with a (B,N,D) input: PatchEmbed passes it through (embeddings.py:160-166).  The oracle's
+    head_embedded is pinned to the live reference in tests/test_oracle_vs_reference.py."""
+    if wide_rows is not None:
+        monkeypatch.setenv("NOVA_B200_WIDE_ADA_ROWS", wide_rows)
+    head, _, z, t, _ = make_case(depth, D, D, B, N, 1)
+    g = torch.Generator().manual_seed(41)
+    x_emb = torch.randn(B, N, D, generator=g)
+    t = torch.rand(B, N, generator=g) * 1000 if per_token else t
+    head = head.to(dtype)
+    sd = cpu_sd(head, torch.float32)
+    xe, zz = x_emb.to(dtype), z.to(dtype)
+    ref = OH.head_embedded(sd, xe.float(), t, zz.float())
+    head = head.cuda()
+    out = head(xe.cuda(), t.cuda(), zz.cuda())
+    assert out.shape == (B, N, 3) and out.dtype == dtype
+    assert relmax(out.float(), ref) < (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+    with pytest.raises(Exception):
+        head(xe.cuda(), t.cuda(), zz.cuda(), torch.zeros(B, 2, 1, dtype=torch.int64, device="cuda"))
+    with pytest.raises(Exception):
+        head(xe.cuda()[:, :, : D // 2], t.cuda(), zz.cuda())
+
+
 def test_forward_fp32_golden_weights_embedded(golden_dir):
     """The reference's own fixture (D=128) embedded into a D=256 head: zero-padding the width keeps
     LayerNorm statistics different, so instead check the library on the fixture's *inputs* with a

@@ -52,6 +52,20 @@ def test_head_forward_fresh_seeds(ref, depth, D, Dc, patch, chan, B, H, W, n_pre
     assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("depth,per_token", [(2, False), (3, True), (0, False)])
+def test_head_forward_pre_embedded_rows(ref, depth, per_token):
+    """A 3-D x passes through PatchEmbed.forward unchanged (embeddings.py:160-166): the blocks start from the caller's rows."""
+    head, sd, _, z, t, _ = _case(ref, depth, 64, 96, 1, 3, 2, 12, 1, None, 31 + depth)
+    g = torch.Generator().manual_seed(77)
+    x_emb = torch.randn(2, 12, 64, generator=g)
+    t = torch.rand(2, 12, generator=g) * 1000 if per_token else t
+    with torch.no_grad():
+        want = head(x_emb, t, z)
+    got = OH.head_embedded(sd, x_emb, t, z)
+    assert got.shape == want.shape == (2, 12, 3)
+    assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))
+
+
 def test_head_forward_per_token_timesteps(ref):
     head, sd, x, z, _, _ = _case(ref, 2, 64, 64, 1, 3, 2, 12, 1, None, 21)
     t = torch.rand(2, 12) * 1000  # training-mode call: one timestep per token (transformer_3d.py:85-90)
