@@ -54,6 +54,8 @@ def _inputs(B, N, D, n, seed=5, T=3):
     (6, 1024, 8, 80, 37),     # NOVA-0.6B width, 296 rows
     (6, 1536, 5, 40, 27),     # NOVA-1.4B width, 135 rows
     (3, 1280, 3, 50, 43),     # mlp_d3w1280, 129 rows (one row in the second block)
+    (2, 1792, 2, 40, 35),     # widths beyond the registry's heads: 7 and 8 column groups per lane (the library
+    (2, 2048, 3, 30, 23),     # accepts multiples of 256 up to 2048), 70 / 69 rows
     (2, 256, 3, 200, None),   # all tokens, 600 rows, smallest width
     (0, 512, 2, 9, 4),        # no blocks: embed -> final modulation -> head
 ])
