@@ -133,6 +133,27 @@ def test_backward_matches_autograd_two_blocks_patch2(dtype, tol):
     assert relmax(dz, ref_dz) <= tol
 
 
+@pytest.mark.parametrize("depth,D,B,N", [
+    (6, 768, 3, 111),     # NOVA-0.3B head as BASELINE's cfg2 has it, 333 rows (ragged against every tile size)
+    (2, 1024, 2, 331),    # NOVA-0.6B width, 662 rows: three 256-row blocks, the last ragged
+    (2, 1536, 1, 257),    # NOVA-1.4B width, one row into the second 256-row block
+])
+def test_backward_bf16_at_the_registry_widths(depth, D, B, N):
+    """The bf16 training step (tcgen05 dgrad / wgrad GEMMs, MN-major weight-gradient operands) at the widths of the
+    registry heads against torch autograd through the fp32 oracle on the bf16-rounded weights: <= 2e-2 of each tensor's
+    maximum (north_star's bf16 tolerance), loss included."""
+    sd, head, x, z, mask, noise, t_idx = _train_case(depth, D, D, 1, 3, B, N, 1, 1, 23, torch.bfloat16)
+    loss, grads, dz = _gpu_loss_and_grads(head, x, z, mask, noise, t_idx, 1)
+    want, ref, ref_dz = _oracle_loss_and_grads(sd, z, x, noise, t_idx, mask, 1)
+    assert abs(loss - want) <= 2e-2 * abs(want)
+    errs = {k: relmax(grads[k], ref[k]) for k in ref}
+    record(f"training backward bf16 (depth {depth}, D {D}, {B * N} rows): worst parameter gradient", max(errs.values()))
+    record(f"training backward bf16 (depth {depth}, D {D}, {B * N} rows): dz", relmax(dz, ref_dz))
+    for k, e in errs.items():
+        assert e <= 2e-2, (k, e)
+    assert relmax(dz, ref_dz) <= 2e-2
+
+
 def test_backward_split_reduction_on_tensor_cores_matches_fp32_handle():
     """4096 rows: the bf16 handle's weight gradients run as ONE batched tcgen05 launch over a split M-reduction
     (tc::launch_batched); compared with the fp32 handle (SIMT GEMMs, itself pinned to autograd above) on the same
