@@ -571,6 +571,7 @@ def main():
                 return nb.gather_shards(cd, Bc)
 
             cms, _, _ = timed(chamfer_pass, 10, 3)
+            kms, _, _ = timed(lambda: torch.ops.nova_b200.chamfer_nn(pa, pb, False), 10, 3)  # this rank's kernel alone
             pair_evals = 2.0 * Bc * Nc * Nc  # directed
             # fp32 issue bound: >= 8 thread instructions per undirected pair (3 sub, 3 mul/fma, 2 min); the chip issues
             # 148 SMs x 4 schedulers x 32 lanes per clock at the maximum SM clock
@@ -578,8 +579,11 @@ def main():
             north["chamfer_sharded"] = {
                 "value": Bc / (cms * 1e-3), "unit": "cloud pairs/s", "ms": cms, "pairs_total": Bc, "pairs_this_gpu": hi - lo,
                 "n_gpus": world, "points": Nc, "pair_evals_per_s": pair_evals / (cms * 1e-3),
+                "kernel_ms_this_gpu": kms, "kernel_pair_evals_per_s_per_gpu": 2.0 * (hi - lo) * Nc * Nc / (kms * 1e-3),
                 "what": "BASELINE configs[4]: Chamfer A of 256 x (2048 vs 2048), pairs sharded over the ranks, one all-gather "
-                        "of the per-pair distances; timed through the public chamfer_distance call",
+                        "of the per-pair distances; timed through the public chamfer_distance call (a 0.4 ms job on one GPU: "
+                        "with 32 pairs per GPU the kernel is kernel_ms_this_gpu and the rest of `ms` is launch, reduction and "
+                        "NCCL latency, which is what bounds its scaling)",
                 "roofline": {"bound": "fp32_issue", "achieved": pair_evals / (cms * 1e-3) / 1e12, "peak": issue_peak * world / 1e12,
                              "unit": "T directed pair-evals/s", "frac": pair_evals / (cms * 1e-3) / (issue_peak * world),
                              "note": "algorithmically HBM-trivial (16.8 MB per 2.1 G pair evaluations); the bound is fp32 "
