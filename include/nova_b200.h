@@ -188,6 +188,11 @@ NOVA_API int nova_euler_step(const void* model_output, const void* sample, doubl
 NOVA_API int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_t N, int64_t M, float* d1, float* d2,
                     int32_t* idx1, int32_t* idx2, void* stream);
 
+/* cd [B] fp64 = mean_i d1[b, i] + mean_j d2[b, j]: the two means of chamfer_distance (demo.py:50-53) over the
+ * distances nova_chamfer_nn returned, accumulated in double in a fixed order (deterministic), one launch. */
+NOVA_API int nova_chamfer_pair_mean(const float* d1, const float* d2, int64_t B, int64_t N, int64_t M, double* cd,
+                                    void* stream);
+
 /*
  * Neighbourhood ops on the Chamfer tiling (callers either side of the sampling path).
  * All distances are Euclidean (not squared), exact difference form in fp32; ties keep the lowest index.

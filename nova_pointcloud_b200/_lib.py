@@ -19,7 +19,7 @@ EPI_BIAS, EPI_BIAS_SILU = 0, 1
 EXPORTS = [
     "nova_last_error", "nova_abi_version", "nova_device_check", "nova_head_create", "nova_head_destroy",
     "nova_head_get_config", "nova_head_load", "nova_head_workspace_bytes", "nova_head_forward",
-    "nova_head_sample", "nova_head_forward_embedded", "nova_head_generate_sets", "nova_euler_step", "nova_chamfer_nn", "nova_launch_count",
+    "nova_head_sample", "nova_head_forward_embedded", "nova_head_generate_sets", "nova_euler_step", "nova_chamfer_nn", "nova_chamfer_pair_mean", "nova_launch_count",
     "nova_launch_count_reset", "nova_debug_gemm", "nova_debug_words", "nova_profile_enable", "nova_profile_read", "nova_debug_adaln_gemm",
     "nova_debug_chain_timeline", "nova_debug_words_clear", "nova_comm_unique_id", "nova_comm_init_rank",
     "nova_comm_destroy", "nova_allgather", "nova_knn", "nova_local_density", "nova_softmax_interp", "nova_farthest_point_sampling", "nova_add_noise", "nova_flow_loss",
@@ -76,6 +76,8 @@ def _declare(lib):
     lib.nova_euler_step.argtypes = [vp, vp, C.c_double, vp, i64, i32, vp]
     lib.nova_chamfer_nn.restype = C.c_int
     lib.nova_chamfer_nn.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp]
+    lib.nova_chamfer_pair_mean.restype = C.c_int
+    lib.nova_chamfer_pair_mean.argtypes = [vp, vp, i64, i64, i64, vp, vp]
     lib.nova_knn.restype = C.c_int
     lib.nova_knn.argtypes = [vp, vp, i64, i64, i64, i32, vp, vp, vp]
     lib.nova_local_density.restype = C.c_int

@@ -222,6 +222,51 @@ static bool chamfer_one_sweep() {  // NOVA_B200_CHAMFER_SWEEPS=2 keeps the two-s
   return e == nullptr || std::atoi(e) != 2;
 }
 
+namespace nova {
+namespace chamfer {
+// cd[b] = mean_i d1[b, i] + mean_j d2[b, j] in double (chamfer_distance's two np.mean over float64 distances,
+// demo.py:50-53): one CTA per pair, fixed-order reduction (deterministic), one launch instead of five ATen kernels
+__global__ void __launch_bounds__(256) pair_mean_kernel(const float* __restrict__ d1, const float* __restrict__ d2, int64_t N,
+                                                        int64_t M, double* __restrict__ cd) {
+  __shared__ double red[2][8];
+  const int64_t b = blockIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) s1 += static_cast<double>(d1[b * N + i]);
+  for (int64_t j = threadIdx.x; j < M; j += blockDim.x) s2 += static_cast<double>(d2[b * M + j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s1;
+    red[1][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      t1 += red[0][w];
+      t2 += red[1][w];
+    }
+    cd[b] = t1 / static_cast<double>(N) + t2 / static_cast<double>(M);
+  }
+}
+}  // namespace chamfer
+}  // namespace nova
+
+extern "C" int nova_chamfer_pair_mean(const float* d1, const float* d2, int64_t B, int64_t N, int64_t M, double* cd,
+                                      void* stream) {
+  using namespace nova;
+  NOVA_REQUIRE(d1 && d2 && cd, "nova_chamfer_pair_mean: null pointer");
+  NOVA_REQUIRE(B >= 0 && N > 0 && M > 0, "nova_chamfer_pair_mean: empty input (B=%lld N=%lld M=%lld)", (long long)B,
+               (long long)N, (long long)M);
+  if (B == 0) return NOVA_OK;
+  chamfer::pair_mean_kernel<<<(unsigned)B, 256, 0, static_cast<cudaStream_t>(stream)>>>(d1, d2, N, M, cd);
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
 extern "C" int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_t N, int64_t M, float* d1, float* d2,
                                int32_t* idx1, int32_t* idx2, void* stream) {
   using namespace nova;

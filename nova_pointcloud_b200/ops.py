@@ -342,6 +342,24 @@ def _(a, b, with_indices=True):
             a.new_empty((B, M) if with_indices else (0,), dtype=torch.int32))
 
 
+@torch.library.custom_op("nova_b200::chamfer_pair_mean", mutates_args=(), device_types="cuda")
+def chamfer_pair_mean(d1: torch.Tensor, d2: torch.Tensor) -> torch.Tensor:
+    """(B,) float64: mean of d1 over its points + mean of d2 over its points (the reduction of Chamfer variant A)."""
+    if d1.dim() != 2 or d2.dim() != 2 or d1.shape[0] != d2.shape[0] or d1.dtype != torch.float32 or d2.dtype != torch.float32:
+        raise NovaError(f"chamfer_pair_mean expects fp32 (B,N) and (B,M); got {tuple(d1.shape)} {d1.dtype}, {tuple(d2.shape)} {d2.dtype}")
+    d1, d2 = d1.contiguous(), d2.contiguous()
+    out = torch.empty(d1.shape[0], dtype=torch.float64, device=d1.device)
+    with torch.cuda.device(d1.device):
+        check(_lib.lib().nova_chamfer_pair_mean(_ptr(d1), _ptr(d2), d1.shape[0], d1.shape[1], d2.shape[1], _ptr(out), _stream()),
+              "nova_chamfer_pair_mean")
+    return out
+
+
+@chamfer_pair_mean.register_fake
+def _(d1, d2):
+    return d1.new_empty((d1.shape[0],), dtype=torch.float64)
+
+
 def _cloud3(x: torch.Tensor, what: str) -> torch.Tensor:
     if x.dim() != 3 or x.shape[-1] != 3:
         raise NovaError(f"{what} expects (B,N,3) point clouds; got {tuple(x.shape)}")
