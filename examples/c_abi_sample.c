@@ -157,6 +157,21 @@ int main(void) {
   CUDA(cudaMemcpy(h_d1, d_d1, sizeof(h_d1), cudaMemcpyDeviceToHost));
   double cd = 0.0;
   for (int i = 0; i < 2 * N; ++i) cd += h_d1[i];
+  /* the two means of chamfer_distance (demo.py:50-53) on the device, in float64: per pair mean(d1) + mean(d2) */
+  double* d_cd;
+  double h_cd[2];
+  static float h_d2[2 * N];
+  CUDA(cudaMalloc((void**)&d_cd, sizeof(double) * 2));
+  CHECK(nova_chamfer_pair_mean(d_d1, d_d2, 2, N, N, d_cd, stream));
+  CUDA(cudaStreamSynchronize(stream));
+  CUDA(cudaMemcpy(h_cd, d_cd, sizeof(h_cd), cudaMemcpyDeviceToHost));
+  CUDA(cudaMemcpy(h_d2, d_d2, sizeof(h_d2), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < 2; ++c) {
+    double m1 = 0.0, m2 = 0.0;
+    for (int i = 0; i < N; ++i) { m1 += h_d1[c * N + i]; m2 += h_d2[c * N + i]; }
+    const double want = m1 / N + m2 / N;
+    if (fabs(h_cd[c] - want) > 1e-12 * (1.0 + fabs(want))) { fprintf(stderr, "pair mean %d: %.17g vs %.17g\n", c, h_cd[c], want); return 1; }
+  }
   CHECK(nova_chamfer_nn(d_out, d_out, 2, N, N, d_d1, d_d2, NULL, NULL, stream));
   CUDA(cudaStreamSynchronize(stream));
   CUDA(cudaMemcpy(h_d1, d_d1, sizeof(h_d1), cudaMemcpyDeviceToHost));
