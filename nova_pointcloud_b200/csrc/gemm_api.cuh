@@ -61,6 +61,10 @@ struct TailArgs {
 int launch(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M, int N,
            int K, int epi, cudaStream_t stream, int cta_group = 0, bool reverse_m = false, float2* part_out = nullptr);
 
+// pre = A W^T + bias and act = silu(pre), both [M, N] bf16, from one launch (the training forward keeps pre for the backward)
+int launch_silu_dual(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* pre, int64_t ldpre,
+                     bf16* act, int64_t ldact, int M, int N, int K, cudaStream_t stream);
+
 // S = M / batch_m_rows independent GEMMs in one launch (the split-M weight gradients of train_bwd.cu):
 //   C[b] [batch_m_rows, N] = A[b] [batch_m_rows, K] W[b] [N, K]^T, all three stacked along their rows.
 int launch_batched(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, bf16* C, int64_t ldc, int M, int N, int K,

@@ -11,7 +11,8 @@ namespace nova {
 
 // EPI_ADALN and EPI_TAIL exist on the tcgen05 kernel only (AdaLN statistics GEMM with the modulation fused in; gate
 // GEMM with the block tail x += LN_aff(u) * gate fused in).
-enum Epilogue : int { EPI_BIAS = 0, EPI_BIAS_SILU = 1, EPI_ADALN = 2, EPI_TAIL = 3 };
+enum Epilogue : int { EPI_BIAS = 0, EPI_BIAS_SILU = 1, EPI_ADALN = 2, EPI_TAIL = 3,
+                      EPI_BIAS_SILU_DUAL = 4 };  // tcgen05 only: also stores the pre-activation (training forward)
 
 namespace simt {
 

@@ -898,6 +898,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int out_n = EPI == EPI_ADALN ? (tile_n - p.n_mod_tiles) * BN : n_idx;
         const int out_cols = EPI == EPI_ADALN ? p.N - p.n_mod_tiles * BN : p.N;
         const bool want_parts = EPI == EPI_BIAS && p.part_out != nullptr;  // fc2: partial LayerNorm statistics of u
+        // EPI_BIAS_SILU_DUAL (training forward): the pre-activation a chunk's SiLU is taken of goes out as well (through
+        // tmap_c2; the backward pass needs it), so a chunk fills BOTH staging buffers: 0 = pre-activation, 1 = activation
+        constexpr bool SILU = EPI == EPI_BIAS_SILU || EPI == EPI_BIAS_SILU_DUAL;
+        constexpr bool DUAL = EPI == EPI_BIAS_SILU_DUAL;
         float c0 = 0.f;
         f32x2 nc02 = pk2(0.f, 0.f), s1v = pk2(0.f, 0.f), s2v = pk2(0.f, 0.f);
         constexpr int CPW = (BN / C_CHUNK) / (WIDE_EPI ? 2 : 1);  // chunks per warp set
@@ -909,20 +913,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_ld_32x32(t_row + cc * C_CHUNK, ra);
           tmem_ld_32x32(t_row + cc * C_CHUNK + 32, rb);
           if (lane == 0) {  // the store that last used this staging buffer has read it
-            if (WIDE_EPI) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            if (WIDE_EPI || DUAL) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
           __syncwarp();
           tmem_ld_wait();
-          const uint32_t dst = cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
+          const uint32_t dst = cbuf + static_cast<uint32_t>((WIDE_EPI || DUAL) ? 0 : cpar) * C_BUF_BYTES + static_cast<uint32_t>(lane) * 128u;
           const float* bs = bias_s + cc * C_CHUNK;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks of this thread's 128 B row, XOR-swizzled
             uint32_t w[4];
+            uint32_t wp[DUAL ? 4 : 1];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int e = c * 8 + 2 * h;  // compile-time after unrolling: picks ra or rb statically
               f32x2 x2 = add2(e < 32 ? pk2u(ra[e & 31], ra[(e + 1) & 31]) : pk2u(rb[e & 31], rb[(e + 1) & 31]), lds_f32x2(bs + e));
-              if (EPI == EPI_BIAS_SILU) {  // silu(x) = h + h tanh(h), h = x / 2 (common.cuh), on the pair
+              if (DUAL) wp[h] = pack_bf16x2(x2);
+              if (SILU) {  // silu(x) = h + h tanh(h), h = x / 2 (common.cuh), on the pair
                 const f32x2 h2 = mul2(x2, pk2(0.5f, 0.5f));
                 float h0, h1, t0, t1;
                 upk2(h2, h0, h1);
@@ -942,12 +948,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 s2v = fma2(d2, d2, s2v);
               }
             }
-            st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+            if (DUAL) {
+              st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), wp[0], wp[1], wp[2], wp[3]);
+              st_shared_v4(dst + C_BUF_BYTES + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+            } else {
+              st_shared_v4(dst + (static_cast<uint32_t>(c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+            }
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(out_map, cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES, n0, m0);
+            if (DUAL) {
+              tma_store_2d(&tmap_c2, cbuf, n0, m0);               // pre-activation
+              tma_store_2d(&tmap_c, cbuf + C_BUF_BYTES, n0, m0);  // activation
+            } else {
+              tma_store_2d(out_map, cbuf + static_cast<uint32_t>(WIDE_EPI ? 0 : cpar) * C_BUF_BYTES, n0, m0);
+            }
             tma_store_commit();
           }
           cpar ^= 1;
@@ -995,7 +1011,7 @@ template <int EPI, int CG, int BN = BN_FULL>
 int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc,
                int M, int N, int K, cudaStream_t stream, const AdaLNArgs* ada = nullptr, bool reverse_m = false,
                float2* part_out = nullptr, const TailArgs* tail = nullptr, int batch_m_rows = 0, int batch_w_rows = 0,
-               int mn_rows = 0) {
+               int mn_rows = 0, bf16* pre_out = nullptr, int64_t ldpre = 0) {
   using P = Plan<CG, BN, EPI == EPI_TAIL>;
   static std::atomic<unsigned long long> attr_done{0ull};  // one bit per device
   NOVA_PROPAGATE(ensure_smem_attr(reinterpret_cast<const void*>(gemm_kernel<EPI, CG, BN>), P::SMEM_BYTES, &attr_done));
@@ -1034,6 +1050,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
     NOVA_PROPAGATE(make_tmap_kmajor(&tc_, C, M, N, ldc, 32));
     tc2 = tc_;
     tc3 = tc_;
+    if (EPI == EPI_BIAS_SILU_DUAL) NOVA_PROPAGATE(make_tmap_kmajor(&tc2, pre_out, M, N, ldpre, 32));  // the pre-activation
   }
   const int tiles = static_cast<int>(ceil_div(M, BM * CG) * ceil_div(N, BN));
   const int groups = tiles < num_sms() / CG ? tiles : num_sms() / CG;
@@ -1056,7 +1073,7 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
   // reproducible; taking ANY one of the four kinds out of the chain restores bit-identical results (a gpu-scope fence
   // after griddepcontrol.wait -- i.e. an L1 invalidate -- does not).  The unfused flow never had the problem because its
   // resid kernel is an ordinary launch.
-  cfg.numAttrs = (pdl_enabled() && ((pdl_epi_mask() >> EPI) & 1)) ? 2 : 1;
+  cfg.numAttrs = (pdl_enabled() && ((pdl_epi_mask() >> (EPI == EPI_BIAS_SILU_DUAL ? EPI_BIAS_SILU : EPI)) & 1)) ? 2 : 1;
   NOVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, CG, BN>, ta, tb, tc_, tc2, tc3, p, debug_word()));
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
@@ -1090,6 +1107,23 @@ int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const fl
 int launch_silu(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* C, int64_t ldc, int M,
                 int N, int K, cudaStream_t stream, int cta_group, int bn, bool reverse_m) {
   return launch_plain<EPI_BIAS_SILU>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, cta_group, bn, reverse_m);
+}
+
+// pre [M, N] = A W^T + bias and act [M, N] = silu(that) from ONE launch (256-column tiles): the training forward keeps the
+// pre-activation for the backward pass without a separate SiLU kernel re-reading and re-writing [M, N]
+int launch_silu_dual(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* pre, int64_t ldpre,
+                     bf16* act, int64_t ldact, int M, int N, int K, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return NOVA_OK;
+  NOVA_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldpre % 8 == 0 && ldact % 8 == 0,
+               "tcgen05 dual gemm: K and leading dimensions must be multiples of 8");
+  NOVA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(act) & 15) == 0 && pre && act,
+               "tcgen05 dual gemm: operands must be 16-byte aligned");
+  if (default_cta_group(M) == 2)
+    return launch_epi<EPI_BIAS_SILU_DUAL, 2, BN_FULL>(A, lda, W, ldw, bias, act, ldact, M, N, K, stream, nullptr, false, nullptr,
+                                                      nullptr, 0, 0, 0, pre, ldpre);
+  return launch_epi<EPI_BIAS_SILU_DUAL, 1, BN_FULL>(A, lda, W, ldw, bias, act, ldact, M, N, K, stream, nullptr, false, nullptr,
+                                                    nullptr, 0, 0, 0, pre, ldpre);
 }
 #endif
 

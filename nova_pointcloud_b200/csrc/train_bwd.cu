@@ -502,6 +502,30 @@ int gemm_nt<bf16>(bool simt_path, const bf16* A, int64_t lda, const bf16* W, int
   return tc::launch(A, lda, W, ldw, bias, C, ldc, (int)M, N, K, EPI_BIAS, s);
 }
 
+// pre = A W^T + bias (kept for the backward pass) and act = silu(pre).  bf16 handle on the tensor cores: ONE launch whose
+// epilogue stores both (tc::launch_silu_dual); otherwise the GEMM followed by the element-wise kernel.
+template <typename AT>
+int gemm_nt_silu(bool simt_path, const AT* A, int64_t lda, const AT* W, int64_t ldw, const float* bias, AT* pre, AT* act,
+                 int64_t ldc, int64_t M, int N, int K, cudaStream_t s);
+template <>
+int gemm_nt_silu<float>(bool simt_path, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* pre,
+                        float* act, int64_t ldc, int64_t M, int N, int K, cudaStream_t s) {
+  NOVA_PROPAGATE(gemm_nt<float>(simt_path, A, lda, W, ldw, bias, pre, ldc, M, N, K, s));
+  silu_fwd_kernel<float><<<blocks_for(M * N / 8), 256, 0, s>>>(pre, act, M * N);
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+template <>
+int gemm_nt_silu<bf16>(bool simt_path, const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, bf16* pre,
+                       bf16* act, int64_t ldc, int64_t M, int N, int K, cudaStream_t s) {
+  static const bool dual = [] { const char* e = std::getenv("NOVA_B200_TRAIN_DUAL_SILU"); return e == nullptr || e[0] != '0'; }();
+  if (!simt_path && dual) return tc::launch_silu_dual(A, lda, W, ldw, bias, pre, ldc, act, ldc, (int)M, N, K, s);
+  NOVA_PROPAGATE(gemm_nt<bf16>(simt_path, A, lda, W, ldw, bias, pre, ldc, M, N, K, s));
+  silu_fwd_kernel<bf16><<<blocks_for(M * N / 8), 256, 0, s>>>(pre, act, M * N);
+  NOVA_CHECK_LAUNCH();
+  return NOVA_OK;
+}
+
 struct Carve {
   uint8_t* base;
   size_t off = 0;
@@ -688,13 +712,9 @@ int train_forward(const HeadWeightsView& w, const float* x_tok, const float* t, 
   // time / condition embedding (diffusion_mlp.py:65-75)
   freq_kernel<AT><<<blocks_for(M * 128), 256, 0, s>>>(t, M, p.f);
   NOVA_CHECK_LAUNCH();
-  NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.f, 256, wt1, 256, w.b_t1, p.t1p, D, M, D, 256, s));
-  silu_fwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.t1p, p.t1, MD);
-  NOVA_CHECK_LAUNCH();
+  NOVA_PROPAGATE(gemm_nt_silu<AT>(simt_path, p.f, 256, wt1, 256, w.b_t1, p.t1p, p.t1, D, M, D, 256, s));
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.t1, D, wt2, D, w.b_t2, p.s0, D, M, D, D, s));  // temb
-  NOVA_PROPAGATE(gemm_nt<AT>(simt_path, z, Dc, static_cast<const AT*>(w.w_c1), Dc, w.b_c1, p.c1p, D, M, D, Dc, s));
-  silu_fwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.c1p, p.c1, MD);
-  NOVA_CHECK_LAUNCH();
+  NOVA_PROPAGATE(gemm_nt_silu<AT>(simt_path, z, Dc, static_cast<const AT*>(w.w_c1), Dc, w.b_c1, p.c1p, p.c1, D, M, D, Dc, s));
   NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.c1, D, static_cast<const AT*>(w.w_c2), D, w.b_c2, p.s1, D, M, D, D, s));  // c
   add_silu_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.s1, p.s0, p.zt, p.a, MD);
   NOVA_CHECK_LAUNCH();
@@ -705,9 +725,8 @@ int train_forward(const HeadWeightsView& w, const float* x_tok, const float* t, 
   for (int i = 0; i < L; ++i) {
     ln_mod_fwd_kernel<AT><<<row_blocks(M), THREADS, 0, s>>>(p.x[i], p.st, n_ada, (int64_t)3 * i * D, p.h[i], p.sx[i], M, D);
     NOVA_CHECK_LAUNCH();
-    NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.h[i], D, static_cast<const AT*>(w.w_fc1[i]), D, w.b_fc1[i], p.p1[i], D, M, D, D, s));
-    silu_fwd_kernel<AT><<<blocks_for(MD / 8), 256, 0, s>>>(p.p1[i], p.u1[i], MD);
-    NOVA_CHECK_LAUNCH();
+    NOVA_PROPAGATE(gemm_nt_silu<AT>(simt_path, p.h[i], D, static_cast<const AT*>(w.w_fc1[i]), D, w.b_fc1[i], p.p1[i], p.u1[i], D, M,
+                                    D, D, s));
     NOVA_PROPAGATE(gemm_nt<AT>(simt_path, p.u1[i], D, static_cast<const AT*>(w.w_fc2[i]), D, w.b_fc2[i], p.u2[i], D, M, D, D, s));
     tail_fwd_kernel<AT><<<row_blocks(M), THREADS, 0, s>>>(p.u2[i], p.x[i], p.st, n_ada, (int64_t)3 * i * D + 2 * D, w.gamma[i],
                                                          w.beta[i], p.x[i + 1], p.su[i], M, D);
