@@ -45,6 +45,9 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# Chamfer: 6 fp32 lane-operations per undirected pair, 148 SMs x 128 fp32 lanes per clock at 1.965 GHz -> directed pair-evals/s
+CHAMFER_FP32_PEAK = 148 * 128 * 1.965e9 / 6.0 * 2.0
+
 WORKLOADS = {
     # name: (width, points, clouds per GPU, dtype)
     "cfg2": dict(width=768, points=2048, batch=32, desc="NOVA-0.3B d48w768 head mlp_d6w768, 2048 points, bf16"),
@@ -573,9 +576,11 @@ def main():
             cms, _, _ = timed(chamfer_pass, 10, 3)
             kms, _, _ = timed(lambda: torch.ops.nova_b200.chamfer_nn(pa, pb, False), 10, 3)  # this rank's kernel alone
             pair_evals = 2.0 * Bc * Nc * Nc  # directed
-            # fp32 issue bound: >= 8 thread instructions per undirected pair (3 sub, 3 mul/fma, 2 min); the chip issues
-            # 148 SMs x 4 schedulers x 32 lanes per clock at the maximum SM clock
-            issue_peak = 148 * 4 * 32 * 1.965e9 / 8.0 * 2.0  # directed pair evaluations per second
+            # fp32 pipe bound: 6 fp32 lane-operations per undirected pair in the exact difference form (3 subtractions,
+            # 1 multiply, 2 FMAs; the minima run on the ALU pipe), 148 SMs x 128 fp32 lanes per clock at the maximum SM
+            # clock.  (The one-sweep kernel issues them as packed FADD2 / FMUL2 / FFMA2, which halves the issue slots, not
+            # the lane-operations.)
+            issue_peak = CHAMFER_FP32_PEAK  # directed pair evaluations per second per GPU
             north["chamfer_sharded"] = {
                 "value": Bc / (cms * 1e-3), "unit": "cloud pairs/s", "ms": cms, "pairs_total": Bc, "pairs_this_gpu": hi - lo,
                 "n_gpus": world, "points": Nc, "pair_evals_per_s": pair_evals / (cms * 1e-3),
@@ -584,11 +589,13 @@ def main():
                         "of the per-pair distances; timed through the public chamfer_distance call (a 0.4 ms job on one GPU: "
                         "with 32 pairs per GPU the kernel is kernel_ms_this_gpu and the rest of `ms` is launch, reduction and "
                         "NCCL latency, which is what bounds its scaling)",
-                "roofline": {"bound": "fp32_issue", "achieved": pair_evals / (cms * 1e-3) / 1e12, "peak": issue_peak * world / 1e12,
+                "kernel_roofline_frac": 2.0 * (hi - lo) * Nc * Nc / (kms * 1e-3) / issue_peak,
+                "roofline": {"bound": "fp32_pipe", "achieved": pair_evals / (cms * 1e-3) / 1e12, "peak": issue_peak * world / 1e12,
                              "unit": "T directed pair-evals/s", "frac": pair_evals / (cms * 1e-3) / (issue_peak * world),
-                             "note": "algorithmically HBM-trivial (16.8 MB per 2.1 G pair evaluations); the bound is fp32 "
-                                     "instruction issue: 8 thread instructions per undirected pair, 148 x 4 x 32 lanes per clock "
-                                     "at 1.965 GHz; includes the Python-side reductions and the all-gather of this call"}}
+                             "note": "algorithmically HBM-trivial (16.8 MB per 2.1 G pair evaluations); the bound is the fp32 "
+                                     "pipe: 6 lane-operations per undirected pair (exact difference form), 148 x 128 lanes per "
+                                     "clock at 1.965 GHz; `frac` includes the Python-side reductions and the all-gather of this "
+                                     "call, kernel_roofline_frac is this rank's kernel alone"}}
             del pa, pb
         except Exception as e:
             north["chamfer_sharded"] = {"error": str(e)[:300]}
@@ -712,10 +719,14 @@ def main():
             extras["chamfer"] = {
                 "value": Bc / (cms * 1e-3), "unit": "cloud pairs/s", "ms": cms, "pairs": Bc, "points": Nc,
                 "pair_evals_per_s": 2.0 * Bc * Nc * Nc / (cms * 1e-3),
+                "roofline_fp32": {"bound": "fp32_pipe", "achieved": 2.0 * Bc * Nc * Nc / (cms * 1e-3) / 1e12,
+                                  "peak": CHAMFER_FP32_PEAK / 1e12, "unit": "T directed pair-evals/s",
+                                  "frac": 2.0 * Bc * Nc * Nc / (cms * 1e-3) / CHAMFER_FP32_PEAK,
+                                  "note": "6 fp32 lane-operations per undirected pair, 148 SMs x 128 lanes at 1.965 GHz"},
                 "roofline": {"bound": "hbm", "achieved": alg_bytes / (cms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                              "frac": alg_bytes / (cms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
                              "note": "algorithmically HBM-trivial (%.1f MB for 2.1 G pair evaluations): the limiter is "
-                                     "fp32 issue rate, see pair_evals_per_s" % (alg_bytes / 1e6)}}
+                                     "the fp32 pipe, see roofline_fp32" % (alg_bytes / 1e6)}}
             if not args.no_cpu_baseline:
                 import numpy as np
                 from oracle import chamfer as OC

@@ -208,6 +208,127 @@ nn_sym_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t 
   }
 }
 
+// ---- the same sweep on packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2) and three-input minima (FMNMX3).
+// A 64-bit register holds one coordinate of TWO consecutive targets, so the six arithmetic instructions of a pair
+// evaluation (3 subtractions, 1 multiply, 2 FMAs) serve two pairs, the query's running minimum takes both with one
+// FMNMX3, and a target's minimum over the lane's SQ queries takes SQ / 2 of them: 4.5 issued instructions per pair
+// evaluation instead of 8 (+ the shuffle tree).  The kernel is issue-bound, so that is the speed-up to expect.  Each
+// lane computes (t - q) instead of (q - t): the squares are the same bits, results are identical to nn_sym_kernel.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+template <int SQ, int SWARPS>
+__global__ void __launch_bounds__(SWARPS * 32)
+nn_sym2_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t N, int64_t M, float* __restrict__ d1,
+               unsigned int* __restrict__ d2sq_bits) {
+  // coordinate planes of the target tile: element i of a plane = that coordinate of targets (2i, 2i + 1)
+  __shared__ __align__(16) float tx[STILE], ty[STILE], tz[STILE];
+  __shared__ unsigned int tmin[STILE];
+  constexpr int STHREADS = SWARPS * 32, SQPB = SWARPS * 32 * SQ;
+  const int64_t cloud = blockIdx.y;
+  const float* qry = a + cloud * N * 3;
+  const float* tgt = b + cloud * M * 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q0 = (int64_t)blockIdx.x * SQPB + warp * (32 * SQ);
+  f32x2 nqx[SQ], nqy[SQ], nqz[SQ];  // (-q, -q)
+  float best[SQ];
+#pragma unroll
+  for (int k = 0; k < SQ; ++k) {
+    int64_t qi = q0 + k * 32 + lane;
+    if (qi >= N) qi = N - 1;  // duplicates of a valid query change neither minimum
+    const float x = qry[qi * 3 + 0], y = qry[qi * 3 + 1], z = qry[qi * 3 + 2];
+    nqx[k] = pk2(-x, -x);
+    nqy[k] = pk2(-y, -y);
+    nqz[k] = pk2(-z, -z);
+    best[k] = 3.4e38f;
+  }
+  for (int64_t t0 = 0; t0 < M; t0 += STILE) {
+    const int cnt = static_cast<int>(M - t0 < STILE ? M - t0 : STILE);
+    const int cnt32 = (cnt + 31) & ~31;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt32 * 3; i += STHREADS) {  // coalesced read of the xyz stream
+      const int pt = i / 3, c = i - pt * 3;
+      const float v = pt < cnt ? tgt[t0 * 3 + i] : 1e18f;  // padding: a point far away
+      (c == 0 ? tx : c == 1 ? ty : tz)[pt] = v;
+    }
+    for (int i = threadIdx.x; i < cnt32; i += STHREADS) tmin[i] = 0x7F7F7F7Fu;
+    __syncthreads();
+    for (int g = 0; g < cnt32; g += 32) {
+      float pm[32];
+#pragma unroll
+      for (int t = 0; t < 32; t += 2) {
+        const f32x2 px = *reinterpret_cast<const f32x2*>(tx + g + t);
+        const f32x2 py = *reinterpret_cast<const f32x2*>(ty + g + t);
+        const f32x2 pz = *reinterpret_cast<const f32x2*>(tz + g + t);
+        float lo[SQ], hi[SQ];
+#pragma unroll
+        for (int k = 0; k < SQ; ++k) {
+          const f32x2 dx = add2(px, nqx[k]), dy = add2(py, nqy[k]), dz = add2(pz, nqz[k]);
+          const f32x2 d = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+          upk2(d, lo[k], hi[k]);
+          best[k] = min3(best[k], lo[k], hi[k]);
+        }
+        float m0 = lo[0], m1 = hi[0];
+#pragma unroll
+        for (int k = 1; k + 1 < SQ; k += 2) {
+          m0 = min3(m0, lo[k], lo[k + 1]);
+          m1 = min3(m1, hi[k], hi[k + 1]);
+        }
+        if (SQ % 2 == 0) {
+          m0 = fminf(m0, lo[SQ - 1]);
+          m1 = fminf(m1, hi[SQ - 1]);
+        }
+        pm[t] = m0;
+        pm[t + 1] = m1;
+      }
+      // butterfly transpose-reduce: lane l ends with min over the 32 lanes of pm[l]
+#pragma unroll
+      for (int r = 16; r >= 1; r >>= 1) {
+        const bool upper = (lane & r) != 0;
+#pragma unroll
+        for (int i = 0; i < r; ++i) {
+          const float keep = upper ? pm[i + r] : pm[i];
+          const float give = upper ? pm[i] : pm[i + r];
+          pm[i] = fminf(keep, __shfl_xor_sync(0xffffffffu, give, r));
+        }
+      }
+      atomicMin(&tmin[g + lane], __float_as_uint(pm[0]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += STHREADS) atomicMin(&d2sq_bits[cloud * M + t0 + i], tmin[i]);
+  }
+#pragma unroll
+  for (int k = 0; k < SQ; ++k) {
+    const int64_t qi = q0 + k * 32 + lane;
+    if (qi < N) d1[cloud * N + qi] = sqrtf(best[k]);
+  }
+}
+
 // d2 <- sqrt(d2^2) in place (the buffer holds float bit patterns written by atomicMin)
 __global__ void sqrt_inplace_kernel(float* __restrict__ d, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +338,10 @@ __global__ void sqrt_inplace_kernel(float* __restrict__ d, int64_t n) {
 }  // namespace chamfer
 }  // namespace nova
 
+static int chamfer_packed() {  // NOVA_B200_CHAMFER_PACKED=0 keeps the scalar one-sweep kernel, =8 takes 8 queries per lane (A/B runs)
+  const char* e = std::getenv("NOVA_B200_CHAMFER_PACKED");
+  return e == nullptr ? 1 : std::atoi(e);
+}
 static bool chamfer_one_sweep() {  // NOVA_B200_CHAMFER_SWEEPS=2 keeps the two-sweep distance-only kernel (A/B runs)
   const char* e = std::getenv("NOVA_B200_CHAMFER_SWEEPS");
   return e == nullptr || std::atoi(e) != 2;
@@ -285,7 +410,13 @@ extern "C" int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     NOVA_CHECK_CUDA(cudaMemsetAsync(d2, 0x7F, sizeof(float) * B * M, s));  // 0x7F7F7F7F = 3.39e38
     dim3 sgrid((unsigned)ceil_div(N, chamfer::SQPB), (unsigned)B);
-    chamfer::nn_sym_kernel<<<sgrid, chamfer::STHREADS, 0, s>>>(a, b, N, M, d1, reinterpret_cast<unsigned int*>(d2));
+    if (chamfer_packed() == 8) {  // 8 queries per lane: the shuffle tree of a 32-target group serves twice the pairs
+      dim3 g8((unsigned)ceil_div(N, 4 * 32 * 8), (unsigned)B);
+      chamfer::nn_sym2_kernel<8, 4><<<g8, 128, 0, s>>>(a, b, N, M, d1, reinterpret_cast<unsigned int*>(d2));
+    } else if (chamfer_packed())
+      chamfer::nn_sym2_kernel<chamfer::SQ, chamfer::SWARPS><<<sgrid, chamfer::STHREADS, 0, s>>>(a, b, N, M, d1, reinterpret_cast<unsigned int*>(d2));
+    else
+      chamfer::nn_sym_kernel<<<sgrid, chamfer::STHREADS, 0, s>>>(a, b, N, M, d1, reinterpret_cast<unsigned int*>(d2));
     NOVA_CHECK_LAUNCH();
     chamfer::sqrt_inplace_kernel<<<(unsigned)ceil_div(B * M, 256), 256, 0, s>>>(d2, B * M);
   } else

@@ -25,6 +25,7 @@ int num_sms();  // SM count of the current device
 int ensure_smem_attr(const void* func, int bytes, std::atomic<unsigned long long>* done_mask);
 int default_cta_group(int M);  // env NOVA_B200_CTA_GROUP=1|2 overrides the heuristic
 int pdl_epi_mask();            // env NOVA_B200_PDL_EPI_MASK: bit e = GEMMs with epilogue e take part in programmatic dependent launch (default 7: every kind but the tail GEMM, see launch_epi)
+bool fixed_column_grid();      // env NOVA_B200_FIXED_N=1 turns the fixed-column grids of launch_epi on
 int tile_columns_override();   // env NOVA_B200_TILE_N=64|128|256 forces the tile columns of the plain GEMMs (tests)
 
 struct AdaLNArgs {

@@ -642,8 +642,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int NB = BN / (32 * epi_warps(EPI)) > 0 ? BN / (32 * epi_warps(EPI)) : 1;  // bias values per thread
     RP rp_n;
     float2 st2_n = make_float2(0.f, 0.f);
-    float bv_n[NB], gv_n[NB], btv_n[NB];
-    auto fetch = [&](int t) {
+    float bv_n[NB] = {}, gv_n[NB] = {}, btv_n[NB] = {};
+    // fetch() only LOADS (addresses clamped into range instead of predicated): the masking of out-of-range columns and
+    // the (1 + bias) of the scale columns happen where the values are consumed, a tile later -- an add or a select right
+    // behind its load made the warp sit out the whole L2 round trip inside fetch() (ncu source view, round 2: 172 + 33
+    // samples on the two FADDs behind the modulation epilogue's bias loads, 95 in the tail's).  The constants of a column
+    // tile are skipped when the next tile is in the same column (fixed-column grids, launch_epi).
+    auto fetch = [&](int t, int have_n) {
       const int t_n = t % num_n;
       const int t_m0 = (p.reverse_m ? num_m - 1 - t / num_n : t / num_n) * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
       const bool t_mod = EPI == EPI_ADALN && t_n < p.n_mod_tiles;
@@ -651,19 +656,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (EPI == EPI_TAIL || p.stats_parts > 0) load_partials(p.part_in, p.stats_parts, p.M, t_m0 + lane, rp_n);
         else st2_n = *reinterpret_cast<const float2*>(p.rowstats + 2 * static_cast<int64_t>(t_m0 + lane));
       }
+      if (t_n == have_n) return;
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int j = tid_e + i * 32 * epi_warps(EPI);
-        const bool in = j < BN && t_n * BN + j < p.N;
-        // modulation tiles: the scale half carries (1 + bias), so the epilogue forms 1 + scale with one addition
-        bv_n[i] = ((p.bias != nullptr && in) ? __ldg(p.bias + t_n * BN + j) : 0.f) + ((t_mod && j < 128) ? 1.0f : 0.f);
+        const int col = t_n * BN + j < p.N ? t_n * BN + j : p.N - 1;
+        if (p.bias != nullptr) bv_n[i] = __ldg(p.bias + col);
         if (EPI == EPI_TAIL) {
-          gv_n[i] = in ? __ldg(p.gamma + t_n * BN + j) : 0.f;
-          btv_n[i] = in ? __ldg(p.beta + t_n * BN + j) : 0.f;
+          gv_n[i] = __ldg(p.gamma + col);
+          btv_n[i] = __ldg(p.beta + col);
         }
       }
     };
-    if (group < num_tiles) fetch(group);
+    int smem_n = -1;  // column tile whose bias (gamma, beta) tile is in shared memory
+    if (group < num_tiles) fetch(group, -1);
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_tile = p.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
       const int m_idx = m_tile * (BM * CG) + static_cast<int>(rank) * BM, n_idx = (tile % num_n) * BN;
@@ -697,26 +703,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         gv[i] = EPI == EPI_TAIL ? gv_n[i] : 0.f;
         btv[i] = EPI == EPI_TAIL ? btv_n[i] : 0.f;
       }
-      if (tile + num_groups < num_tiles) fetch(tile + num_groups);
+      if (tile + num_groups < num_tiles) fetch(tile + num_groups, tile_n);
       if (EPI == EPI_TAIL && prev_tb >= 0) {
         // the staged buffer of the previous tile's last chunk goes back to the producer (its store has had the time of
         // the loads above to read it); waiting until my next chunk would hold up the other half's next chunk
         if (lane == 0) { tma_store_wait_read<0>(); mbar_arrive(tail_empty(prev_tb)); }
         prev_tb = -1;
       }
-      NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // every epilogue warp has finished reading the previous tile's bias
+      if (tile_n != smem_n) {  // same for every epilogue warp: the two barriers stay matched
+        smem_n = tile_n;
+        NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // every epilogue warp has finished reading the previous tile's bias
 #pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        const int j = tid_e + i * 32 * epi_warps(EPI);
-        if (j < BN) {
-          bias_s[j] = bv[i];
-          if (EPI == EPI_TAIL) {
-            reinterpret_cast<float*>(smem + P::OFF_GAMMA)[j] = gv[i];
-            reinterpret_cast<bf16*>(smem + P::OFF_BETA)[j] = __float2bfloat16_rn(btv[i]);  // column pairs: (beta_e, beta_e+1)
+        for (int i = 0; i < NB; ++i) {
+          const int j = tid_e + i * 32 * epi_warps(EPI);
+          if (j < BN) {
+            const bool in = tile_n * BN + j < p.N;
+            // modulation tiles: the scale half carries (1 + bias), so the epilogue forms 1 + scale with one addition
+            bias_s[j] = ((p.bias != nullptr && in) ? bv[i] : 0.f) + ((mod_tile && j < 128) ? 1.0f : 0.f);
+            if (EPI == EPI_TAIL) {
+              reinterpret_cast<float*>(smem + P::OFF_GAMMA)[j] = in ? gv[i] : 0.f;
+              reinterpret_cast<bf16*>(smem + P::OFF_BETA)[j] = __float2bfloat16_rn(in ? btv[i] : 0.f);  // column pairs: (beta_e, beta_e+1)
+            }
           }
         }
+        NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // bias tile visible to the epilogue warps
       }
-      NOVA_TT(tt_bar, epi_bar_sync<32 * epi_warps(EPI)>());  // bias tile visible to the epilogue warps
       // AdaLN modulation tile: this thread's row statistics (and, when x is not staged, its 128 features of x) do not
       // depend on the MMA, so they are requested BEFORE waiting for the accumulator and land while the tile is computed.
       uint4 xv[(EPI == EPI_ADALN && !X_STAGED) ? 8 * KPW : 1];  // my features of x: [64 half KPW, .. + 64 KPW) of the tile's 128
@@ -1053,7 +1064,18 @@ int launch_epi(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const flo
     if (EPI == EPI_BIAS_SILU_DUAL) NOVA_PROPAGATE(make_tmap_kmajor(&tc2, pre_out, M, N, ldpre, 32));  // the pre-activation
   }
   const int tiles = static_cast<int>(ceil_div(M, BM * CG) * ceil_div(N, BN));
-  const int groups = tiles < num_sms() / CG ? tiles : num_sms() / CG;
+  int groups = tiles < num_sms() / CG ? tiles : num_sms() / CG;
+  // Fixed-column grid (NOVA_B200_FIXED_N=1; off by default): with a group count that is a multiple of the column tiles,
+  // group g works on column tile g % num_n for the whole launch (tile = g + i * groups), so the epilogue keeps its bias /
+  // gamma / beta tile in shared memory and drops the two epilogue-wide barriers per tile around it (ncu source view of the
+  // tail GEMM, round 2: 350 of the epilogue warps' ~3000 samples sat behind those two barriers).  Taken only when it
+  // costs no extra wave: 768 tiles (cfg2's fc and gate GEMMs) are 11 waves on 74 CTA pairs and on 72.  Measured at cfg2,
+  // same box, twice: 66.4 / 67.0 ms per pass with, 66.4 / 66.9 without -- the power-capped step does not see the stall.
+  const int num_n_tiles = static_cast<int>(ceil_div(N, BN));
+  if (fixed_column_grid() && groups > num_n_tiles && groups % num_n_tiles != 0) {
+    const int g2 = groups / num_n_tiles * num_n_tiles;
+    if (ceil_div(tiles, g2) == ceil_div(tiles, groups)) groups = g2;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
   cfg.blockDim = dim3(num_threads(EPI));

@@ -188,6 +188,11 @@ int pdl_epi_mask() {
   return m;
 }
 
+bool fixed_column_grid() {  // NOVA_B200_FIXED_N=1: GEMM grids rounded down to a multiple of the column tiles (launch_epi)
+  const char* env = std::getenv("NOVA_B200_FIXED_N");  // read per call
+  return env != nullptr && std::atoi(env) != 0;
+}
+
 int tile_columns_override() {
   const char* env = std::getenv("NOVA_B200_TILE_N");  // read per call: tests switch it between launches
   const int v = env ? std::atoi(env) : 0;

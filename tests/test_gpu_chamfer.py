@@ -94,6 +94,27 @@ def test_full_size_properties():
     assert abs(float(cd[255]) - (m1.mean() + m2.mean())) < 1e-6
 
 
+@pytest.mark.parametrize("B,N,M", [(256, 2048, 2048), (3, 1000, 777), (2, 33, 4097), (5, 1, 1), (1, 2049, 31)])
+def test_packed_sweep_is_bit_identical_to_the_scalar_sweep(monkeypatch, B, N, M):
+    """The one-sweep distance-only kernel on packed fp32 pairs (FADD2 / FMUL2 / FFMA2 + three-input minima, the default;
+    4 or 8 queries per lane) evaluates (t - q)^2 where the scalar kernel evaluates (q - t)^2: the same bits."""
+    import nova_pointcloud_b200 as nb
+
+    g = torch.Generator().manual_seed(B * 31 + N + M)
+    a = torch.randn(B, N, 3, generator=g).cuda()
+    b = torch.randn(B, M, 3, generator=g).cuda()
+    out = {}
+    for variant in ("0", "1", "8"):
+        monkeypatch.setenv("NOVA_B200_CHAMFER_PACKED", variant)
+        d1, d2, _, _ = nb.chamfer_nn(a, b, with_indices=False)
+        out[variant] = (d1.clone(), d2.clone())
+    monkeypatch.delenv("NOVA_B200_CHAMFER_PACKED")
+    for variant in ("1", "8"):
+        assert torch.equal(out[variant][0], out["0"][0]) and torch.equal(out[variant][1], out["0"][1]), variant
+    d1, d2, _, _ = nb.chamfer_nn(a, b)  # the two-sweep kernel with indices
+    assert torch.equal(d1, out["1"][0]) and torch.equal(d2, out["1"][1])
+
+
 # ---------------------------------------------------------------- earth mover's distance (SURVEY 8(f) #4)
 def _emd_clouds(B, N, seed, spread=1.0):
     g = np.random.default_rng(seed)

@@ -178,6 +178,25 @@ def test_full_size_batch_invariance_and_ragged_batches():
     assert err < 2e-2  # measured 6e-4 (profiles/r2_parity_errors.jsonl)
 
 
+def test_fixed_column_grids_reproduce_the_default_grids(monkeypatch):
+    """NOVA_B200_FIXED_N=1 rounds a GEMM's grid down to a multiple of its column tiles where that costs no extra wave,
+    so that a CTA pair stays in one column and its epilogue keeps the bias / gamma / beta tile (no per-tile barriers).
+    6 400 rows at D = 768: the fc and gate GEMMs have 25 x 3 = 75 tiles -> 72 groups instead of 74.  Same tiles, same
+    arithmetic per output element: the sample must not change by a bit."""
+    import nova_pointcloud_b200 as nb
+
+    head = nb.synth.make_head(768, 6, dtype=torch.bfloat16)
+    sched = nb.FlowMatchEulerDiscreteScheduler()
+    sched.set_timesteps(4)
+    noise, z = nb.synth.make_inputs(25, 256, 768, dtype=torch.bfloat16)
+    ref = nb.denoise(head, sched, z, noise)
+    monkeypatch.setenv("NOVA_B200_FIXED_N", "1")
+    head2 = nb.synth.make_head(768, 6, dtype=torch.bfloat16)  # a fresh handle: no CUDA graph captured with the default grids
+    out = nb.denoise(head2, sched, z, noise)
+    monkeypatch.delenv("NOVA_B200_FIXED_N")
+    assert bool(torch.isfinite(out).all()) and torch.equal(out, ref)
+
+
 @pytest.mark.parametrize("name,D,N,B", [("cfg3: NOVA-0.6B, 1024 points, batch 64", 1024, 1024, 64),
                                        ("cfg4 per-GPU shard: NOVA-1.4B, 2048 points, 32 clouds", 1536, 2048, 32)])
 def test_full_size_batch_invariance_other_configs(name, D, N, B):
