@@ -23,19 +23,29 @@
 // every phase so that eps_final = 1e-5 stays well above their rounding step.
 #include <atomic>
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace nova {
 namespace emd {
 
-constexpr int THREADS = 1024;
-constexpr int NWARPS = THREADS / 32;
+constexpr int MAX_THREADS = 1024;  // the kernel runs with 1024 or 512 threads per CTA (nova_emd picks), same results
 constexpr int MAX_POINTS = 4096;
 
 __device__ __forceinline__ float dist(const float4 a, const float4 b) {
   const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
   return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+}
+// the bidding loop's distance with MUFU.SQRT (<= 2 ulp) instead of the correctly rounded square root (MUFU.RSQ + a
+// Newton step + fix-up: ~8 of the ~25 instructions of a (person, object) evaluation).  Only the VALUES that steer the
+// auction see it -- the matching stays eps-optimal for costs that differ from the exact ones by 2 ulp (1e-7 relative,
+// against eps_final = 1e-5) -- the reported mean is always summed from exact distances.
+__device__ __forceinline__ float dist_fast(const float4 a, const float4 b) {
+  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
+  return r;
 }
 // monotone map float -> uint32 (bids are finite and may be negative after re-basing)
 __device__ __forceinline__ uint32_t ordered(float f) {
@@ -71,7 +81,8 @@ __device__ __forceinline__ Best merge(const Best& a, float ov1, float ov2, int o
   return r;
 }
 
-// block-wide exclusive scan of one int per thread (THREADS = 1024: 32 warps), returns the total in `total`
+// block-wide exclusive scan of one int per thread (<= 32 warps), returns the total in `total`
+template <int NWARPS>
 __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
@@ -83,13 +94,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int& total
   if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int w = warp_sums[lane];
+    int w = lane < NWARPS ? warp_sums[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, w, o);
       if (lane >= o) w += t;
     }
-    warp_sums[lane] = w;  // inclusive over warps
+    if (lane < NWARPS) warp_sums[lane] = w;  // inclusive over warps
   }
   __syncthreads();
   total = warp_sums[NWARPS - 1];
@@ -98,7 +109,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int& total
   return base + incl - v;
 }
 
-static __global__ void __launch_bounds__(THREADS, 1)
+// THREADS = 1024: one CTA per SM, every warp of the SM on one pair (few pairs).  THREADS = 512: two CTAs per SM at
+// 2048 points (106 KB of shared memory each), so that 256 pairs are ONE wave on 148 SMs instead of 148 + 108 -- a pair's
+// late rounds (a handful of bidders, barrier-paced) leave most of an SM idle, which the second resident pair fills.
+// Bids, prices and the compaction order do not depend on the thread count; the closing sum is taken in the 1024-thread
+// order by both, so the two variants return the same bits.
+template <int THREADS, bool FAST_SQRT>
+static __global__ void __launch_bounds__(THREADS, MAX_THREADS / THREADS)
 auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N, float eps_final, int max_rounds,
                float* __restrict__ emd_out, int32_t* __restrict__ assign_out, int32_t* __restrict__ status_out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -109,8 +126,9 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
   int* owner = reinterpret_cast<int*>(price + N);      // person holding object j, -1 if none
   int* mine = owner + N;                               // object held by person i, -1 if none
   int* todo = mine + N;                                // compact list of unassigned persons
+  constexpr int NWARPS = THREADS / 32;
   __shared__ int warp_sums[NWARPS];
-  __shared__ float red[NWARPS];
+  __shared__ float red[MAX_THREADS / 32];
   __shared__ int n_todo;
 
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -182,7 +200,7 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
         const int i = todo[u];
         const float4 a = sa[i];
         Best b{-FLT_MAX, -FLT_MAX, 0x7fffffff};
-        for (int j = lane; j < N; j += 32) offer(b, -dist(a, sb[j]) - price[j], j);
+        for (int j = lane; j < N; j += 32) offer(b, -(FAST_SQRT ? dist_fast(a, sb[j]) : dist(a, sb[j])) - price[j], j);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float ov1 = __shfl_xor_sync(0xffffffffu, b.v1, o), ov2 = __shfl_xor_sync(0xffffffffu, b.v2, o);
@@ -222,7 +240,7 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
       int c = 0;
       for (int i = i0; i < i1; ++i) c += mine[i] < 0 ? 1 : 0;
       int total;
-      int pos = block_excl_scan(c, warp_sums, total);
+      int pos = block_excl_scan<NWARPS>(c, warp_sums, total);
       for (int i = i0; i < i1; ++i)
         if (mine[i] < 0) todo[pos++] = i;
       if (tid == 0) n_todo = total;
@@ -241,7 +259,7 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
     int c = 0;
     for (int j = i0; j < i1; ++j) c += owner[j] < 0 ? 1 : 0;
     int total;
-    int pos = block_excl_scan(c, warp_sums, total);
+    int pos = block_excl_scan<NWARPS>(c, warp_sums, total);
     for (int j = i0; j < i1; ++j)
       if (owner[j] < 0) {
         const int i = todo[pos++];
@@ -249,18 +267,22 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
       }
     __syncthreads();
   }
-  float acc = 0.f;
-  for (int i = tid; i < N; i += THREADS) {
-    const int j = mine[i];
-    acc += dist(sa[i], sb[j]);
-    if (assign_out != nullptr) assign_out[(size_t)pair * N + i] = j;
+  // person i belongs to virtual thread i % 1024; a real thread sums its MAX_THREADS / THREADS virtual threads separately
+#pragma unroll
+  for (int v = 0; v < MAX_THREADS / THREADS; ++v) {
+    float acc = 0.f;
+    for (int i = tid + v * THREADS; i < N; i += MAX_THREADS) {
+      const int j = mine[i];
+      acc += dist(sa[i], sb[j]);
+      if (assign_out != nullptr) assign_out[(size_t)pair * N + i] = j;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp + v * NWARPS] = acc;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) red[warp] = acc;
   __syncthreads();
   if (tid == 0) {
     float s = 0.f;
-    for (int w = 0; w < NWARPS; ++w) s += red[w];
+    for (int w = 0; w < MAX_THREADS / 32; ++w) s += red[w];
     emd_out[pair] = s / static_cast<float>(N);
     if (status_out != nullptr) status_out[pair] = failed ? -rounds : rounds;
   }
@@ -284,10 +306,34 @@ extern "C" int nova_emd(const float* a, const float* b, int64_t B, int64_t N, fl
   int dev = 0;
   NOVA_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !((attr_done.load() >> dev) & 1ull)) {
-    NOVA_CHECK_CUDA(cudaFuncSetAttribute(emd::auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    const int cap = 227 * 1024 - 1024;
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(emd::auction_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(emd::auction_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(emd::auction_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NOVA_CHECK_CUDA(cudaFuncSetAttribute(emd::auction_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     attr_done.fetch_or(1ull << dev);
   }
-  emd::auction_kernel<<<static_cast<unsigned>(B), emd::THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  // more pairs than SMs and two CTAs' clouds fit one SM: 512 threads per pair, two pairs per SM (NOVA_B200_EMD_THREADS
+  // = 512 | 1024 forces either; the results are the same bits).  Measured at 256 pairs of 2048 points: 397 -> 288 ms;
+  // at 32 pairs the 1024-thread form is the faster one (246 vs 263 ms).
+  int sms = 0;
+  NOVA_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const char* env = std::getenv("NOVA_B200_EMD_THREADS");
+  const int forced = env ? std::atoi(env) : 0;
+  // The approximate square root steers the bids only (dist_fast); on by default: 288 -> 227 ms at 256 pairs, the mean
+  // matched distance moves by <= 1.2e-7 (NOVA_B200_EMD_FAST_SQRT=0 restores the correctly rounded one).
+  const char* fenv = std::getenv("NOVA_B200_EMD_FAST_SQRT");
+  const bool fast = fenv == nullptr || std::atoi(fenv) != 0;
+  bool half = forced == 512;
+  if (forced != 512 && forced != 1024 && B > sms) {
+    int resident = 0;
+    NOVA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &resident, fast ? emd::auction_kernel<512, true> : emd::auction_kernel<512, false>, 512, smem));
+    half = resident >= 2;
+  }
+  auto* kern = half ? (fast ? emd::auction_kernel<512, true> : emd::auction_kernel<512, false>)
+                    : (fast ? emd::auction_kernel<1024, true> : emd::auction_kernel<1024, false>);
+  kern<<<static_cast<unsigned>(B), half ? 512 : 1024, smem, static_cast<cudaStream_t>(stream)>>>(
       a, b, static_cast<int>(N), eps_final, max_rounds, emd_out, assign_out, status_out);
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;

@@ -186,3 +186,28 @@ def test_emd_full_size_cfg5():
     assert bool((out >= torch.maximum(d1.mean(1), d2.mean(1)) - 1e-6).all())
     srt = assign.sort(dim=1).values.cpu()
     assert torch.equal(srt, torch.arange(2048, dtype=torch.int32).expand(16, -1))
+
+
+def test_emd_thread_count_variants_are_bit_identical(monkeypatch):
+    """nova_emd runs a pair with 1024 threads (one CTA per SM) or, when there are more pairs than SMs, with 512 (two
+    CTAs per SM).  Bids, prices and the compaction order do not depend on the thread count and the closing sum keeps the
+    1024-thread order: same matching, same mean, same round count.  The bidding loop steers by an approximate square root
+    (the default; NOVA_B200_EMD_FAST_SQRT=0 restores the correctly rounded one), which may settle near-ties differently:
+    same mean within the auction's own tolerance."""
+    a, b = _emd_clouds(6, 700, 5)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    res = {}
+    for threads in ("1024", "512"):
+        monkeypatch.setenv("NOVA_B200_EMD_THREADS", threads)
+        out, assign, status = torch.ops.nova_b200.emd(ta, tb, 1e-5)
+        res[threads] = (out.clone(), assign.clone(), status.clone())
+    for k in range(3):
+        assert torch.equal(res["512"][k], res["1024"][k]), k
+    monkeypatch.setenv("NOVA_B200_EMD_FAST_SQRT", "0")
+    out, assign, status = torch.ops.nova_b200.emd(ta, tb, 1e-5)
+    monkeypatch.delenv("NOVA_B200_EMD_FAST_SQRT")
+    monkeypatch.delenv("NOVA_B200_EMD_THREADS")
+    assert bool((status > 0).all())
+    assert float((out - res["1024"][0]).abs().max()) <= 2e-5
+    srt = assign.sort(dim=1).values.cpu()
+    assert torch.equal(srt, torch.arange(700, dtype=torch.int32).expand(6, -1))
