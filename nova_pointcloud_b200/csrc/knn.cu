@@ -13,6 +13,8 @@
 // through a per-lane queue in shared memory so that the (divergent) insertion runs warp-wide, see knn_kernel.
 // Ties keep the lowest index.
 // Bound: fp32 issue rate (HBM traffic is 12 B per query + 12 B per target per CTA against N targets of work).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nova {
@@ -26,6 +28,44 @@ __device__ __forceinline__ void stage_tile(float4* tile, const float* __restrict
   for (int i = threadIdx.x; i < cnt * 3; i += THREADS) {  // coalesced read of cnt*3 consecutive floats
     const int pt = i / 3, c = i - pt * 3;
     tf[pt * 4 + c] = tgt[t0 * 3 + i];
+  }
+}
+
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): the two queries of a thread share every arithmetic instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// Packed form of the tile: every coordinate twice, (x, x, y, y) + (z, z), so that one LDS.128 + one LDS.64 put a
+// target into 64-bit registers that pair with (query 0, query 1) -- no register moves to build the broadcast.
+constexpr int TILE2 = 512;  // 24 B per target
+__device__ __forceinline__ void stage_tile2(ulonglong2* txy, f32x2* tzz, const float* __restrict__ tgt, int64_t t0, int cnt) {
+  float* fxy = reinterpret_cast<float*>(txy);
+  float* fz = reinterpret_cast<float*>(tzz);
+  for (int i = threadIdx.x; i < cnt * 3; i += THREADS) {
+    const int pt = i / 3, c = i - pt * 3;
+    const float v = tgt[t0 * 3 + i];
+    float* dst = c < 2 ? fxy + pt * 4 + 2 * c : fz + pt * 2;
+    dst[0] = v;
+    dst[1] = v;
   }
 }
 
@@ -45,11 +85,17 @@ __device__ __forceinline__ void stage_tile(float4* tile, const float* __restrict
 constexpr int QCAP = 8;  // queue entries per query
 constexpr int GRP = 4;   // targets between two queue checks (tile padded to a multiple with NaN points)
 
-template <int KCAP, int MODE, int QPT>
+// PACKED (QPT == 2 only): the distance arithmetic of the thread's two queries on packed fp32 pairs; (t - q)^2 instead of
+// (q - t)^2, the same bits.
+template <int KCAP, int MODE, int QPT, bool PACKED = false>
 __global__ void __launch_bounds__(THREADS)
 knn_kernel(const float* __restrict__ q, const float* __restrict__ t, int64_t Nq, int64_t Nt, int k,
            float* __restrict__ dist, int32_t* __restrict__ idx) {
-  __shared__ float4 tile[TILE];
+  static_assert(!PACKED || QPT == 2, "the packed form pairs the two queries of a thread");
+  constexpr int TILE_PTS = PACKED ? TILE2 : TILE;
+  __shared__ __align__(16) float4 tile[PACKED ? TILE2 * 3 / 2 : TILE];  // PACKED: TILE2 x (x,x,y,y) then TILE2 x (z,z)
+  ulonglong2* txy = reinterpret_cast<ulonglong2*>(tile);
+  f32x2* tzz = reinterpret_cast<f32x2*>(tile + TILE2);
   __shared__ float qd[QPT][QCAP][THREADS];
   __shared__ int qj[MODE == 0 ? QPT : 1][QCAP][THREADS];
   const int64_t cloud = blockIdx.y;
@@ -115,21 +161,45 @@ knn_kernel(const float* __restrict__ q, const float* __restrict__ t, int64_t Nq,
     }
   };
 
-  for (int64_t t0 = 0; t0 < Nt; t0 += TILE) {
-    const int cnt = static_cast<int>(Nt - t0 < TILE ? Nt - t0 : TILE);
+  f32x2 nqx2 = 0, nqy2 = 0, nqz2 = 0;  // PACKED: (-q0, -q1) per coordinate
+  if (PACKED) {
+    nqx2 = pk2(-qx[0], -qx[QPT - 1]);
+    nqy2 = pk2(-qy[0], -qy[QPT - 1]);
+    nqz2 = pk2(-qz[0], -qz[QPT - 1]);
+  }
+  for (int64_t t0 = 0; t0 < Nt; t0 += TILE_PTS) {
+    const int cnt = static_cast<int>(Nt - t0 < TILE_PTS ? Nt - t0 : TILE_PTS);
     const int cntp = (cnt + GRP - 1) / GRP * GRP;
     __syncthreads();
-    stage_tile(tile, tgt, t0, cnt);
-    if (tid < cntp - cnt) tile[cnt + tid] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);  // NaN: never < anything
+    if (PACKED) {
+      stage_tile2(txy, tzz, tgt, t0, cnt);
+      if (tid < cntp - cnt) txy[cnt + tid] = make_ulonglong2(pk2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000)), 0ull);  // NaN: never < anything
+      if (tid < cntp - cnt) tzz[cnt + tid] = 0ull;
+    } else {
+      stage_tile(tile, tgt, t0, cnt);
+      if (tid < cntp - cnt) tile[cnt + tid] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);  // NaN: never < anything
+    }
     __syncthreads();
     for (int j0 = 0; j0 < cntp; j0 += GRP) {
 #pragma unroll
       for (int g = 0; g < GRP; ++g) {
-        const float4 p = tile[j0 + g];
+        float dd[QPT];
+        if (PACKED) {
+          const ulonglong2 pxy = txy[j0 + g];
+          const f32x2 pzz = tzz[j0 + g];
+          const f32x2 dx = add2(pxy.x, nqx2), dy = add2(pxy.y, nqy2), dz = add2(pzz, nqz2);
+          upk2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), dd[0], dd[QPT - 1]);
+        } else {
+          const float4 p = tile[j0 + g];
+#pragma unroll
+          for (int u = 0; u < QPT; ++u) {
+            const float dx = qx[u] - p.x, dy = qy[u] - p.y, dz = qz[u] - p.z;
+            dd[u] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          }
+        }
 #pragma unroll
         for (int u = 0; u < QPT; ++u) {
-          const float dx = qx[u] - p.x, dy = qy[u] - p.y, dz = qz[u] - p.z;
-          const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          const float d = dd[u];
           if (d < best[u][KCAP - 1]) {
             qd[u][pending[u]][tid] = d;
             if (MODE == 0) qj[u][pending[u]][tid] = static_cast<int>(t0) + j0 + g;
@@ -214,11 +284,21 @@ softmax_interp_kernel(const float* __restrict__ q, const float* __restrict__ t, 
   o[2] = az * inv;
 }
 
+static bool knn_packed() {  // NOVA_B200_KNN_PACKED=0 keeps the scalar arithmetic for two queries per thread (A/B runs)
+  const char* e = std::getenv("NOVA_B200_KNN_PACKED");
+  return e == nullptr || std::atoi(e) != 0;
+}
 template <int KCAP, int MODE, int QPT>
 static void launch_one(const float* q, const float* t, int64_t B, int64_t Nq, int64_t Nt, int k, float* dist,
                        int32_t* idx, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(Nq, THREADS * QPT), (unsigned)B);
-  knn_kernel<KCAP, MODE, QPT><<<grid, THREADS, 0, s>>>(q, t, Nq, Nt, k, dist, idx);
+  if constexpr (QPT == 2 && KCAP <= 9) {  // measured: -4 % (density), -6 % (k = 4), -1 % (k = 9); +0.7 % at k = 16 (insertion-bound)
+    if (knn_packed()) {
+      knn_kernel<KCAP, MODE, QPT, true><<<grid, THREADS, 0, s>>>(q, t, Nq, Nt, k, dist, idx);
+      return;
+    }
+  }
+  knn_kernel<KCAP, MODE, QPT, false><<<grid, THREADS, 0, s>>>(q, t, Nq, Nt, k, dist, idx);
 }
 
 template <int MODE>

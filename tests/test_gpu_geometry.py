@@ -35,6 +35,25 @@ def test_knn_matches_oracle(B, Nq, Nt, k):
         assert (np.diff(d[b], axis=1) >= 0).all()
 
 
+@pytest.mark.parametrize("B,N,k", [(160, 1024, 4), (150, 1030, 9), (150, 1000, 16), (256, 2048, 9)])
+def test_packed_pair_arithmetic_is_bit_identical_to_the_scalar_form(monkeypatch, B, N, k):
+    """Two queries per thread (grids that still cover the chip) take their distances on packed fp32 pairs (FADD2 / FMUL2 /
+    FFMA2, (t - q)^2 instead of (q - t)^2): same distances, same indices, same densities as NOVA_B200_KNN_PACKED=0."""
+    import nova_pointcloud_b200 as nb
+
+    a = torch.from_numpy(clouds(B, N, 7 * N + k)).cuda()
+    out = {}
+    for packed in ("0", "1"):
+        monkeypatch.setenv("NOVA_B200_KNN_PACKED", packed)
+        d, i = nb.knn(a, a, k)
+        out[packed] = (d.clone(), i.clone(), nb.compute_local_density(a, k_neighbors=k - 1).clone())
+    monkeypatch.delenv("NOVA_B200_KNN_PACKED")
+    for j in range(3):
+        assert torch.equal(out["0"][j], out["1"][j]), j
+    od, _ = OG.knn(a[0].cpu().numpy(), a[0].cpu().numpy(), k)
+    assert np.abs(out["1"][0][0].cpu().numpy() - od).max() < 1e-6
+
+
 def test_knn_ties_and_errors():
     import nova_pointcloud_b200 as nb
 
