@@ -14,8 +14,8 @@
 // `eps_final` by factors of 5, prices kept between phases.
 //
 // One CTA per cloud pair.  Both clouds, prices, owners and the bid table live in shared memory (52 B per point: up to
-// 4096 points); a bid is one warp: its lanes scan the objects (distances recomputed from the coordinates -- cheaper than
-// a 16 MB matrix per pair through L2), a shuffle tree merges (best, second best), lane 0 posts the bid with a 64-bit
+// 4096 points; the objects as three coordinate planes); a bid is one warp: its lanes scan the objects two at a time on
+// packed fp32 pairs (distances recomputed from the coordinates -- cheaper than a 16 MB matrix per pair through L2), a shuffle tree merges (best, second best), lane 0 posts the bid with a 64-bit
 // atomicMax of (bid bits, person) -- unique keys, so the winner does not depend on the order of arrival.  The list of
 // unassigned persons is rebuilt by an ordered block scan.  Everything is deterministic run to run; every loop is
 // bounded (a cloud that does not converge within the round budget is reported in `status`, never spun on).
@@ -37,14 +37,36 @@ __device__ __forceinline__ float dist(const float4 a, const float4 b) {
   const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
   return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 }
-// the bidding loop's distance with MUFU.SQRT (<= 2 ulp) instead of the correctly rounded square root (MUFU.RSQ + a
-// Newton step + fix-up: ~8 of the ~25 instructions of a (person, object) evaluation).  Only the VALUES that steer the
-// auction see it -- the matching stays eps-optimal for costs that differ from the exact ones by 2 ulp (1e-7 relative,
-// against eps_final = 1e-5) -- the reported mean is always summed from exact distances.
-__device__ __forceinline__ float dist_fast(const float4 a, const float4 b) {
-  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): a lane evaluates objects (j, j + 1) with one set of instructions
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// The bidding loop's square root as MUFU.SQRT (<= 2 ulp) instead of the correctly rounded one (MUFU.RSQ + a Newton step +
+// fix-up: ~8 of the ~25 instructions of a (person, object) evaluation).  Only the VALUES that steer the auction see it --
+// the matching stays eps-optimal for costs that differ from the exact ones by 2 ulp (1e-7 relative, against eps_final =
+// 1e-5) -- the reported mean is always summed from exact distances.
+__device__ __forceinline__ float sqrt_fast(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 // monotone map float -> uint32 (bids are finite and may be negative after re-basing)
@@ -68,6 +90,13 @@ __device__ __forceinline__ void offer(Best& b, float v, int j) {
   } else if (v > b.v2) {
     b.v2 = v;
   }
+}
+// the same for a lane's own scan, where j only grows (an equal later value never displaces the earlier index): no branch
+__device__ __forceinline__ void offer_ascending(Best& b, float v, int j) {
+  const bool better = v > b.v1;
+  b.v2 = fmaxf(b.v2, fminf(v, b.v1));
+  b.j1 = better ? j : b.j1;
+  b.v1 = fmaxf(b.v1, v);
 }
 __device__ __forceinline__ Best merge(const Best& a, float ov1, float ov2, int oj1) {
   Best r;
@@ -120,8 +149,11 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
                float* __restrict__ emd_out, int32_t* __restrict__ assign_out, int32_t* __restrict__ status_out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float4* sa = reinterpret_cast<float4*>(smem_raw);                                  // persons
-  float4* sb = sa + N;                                                               // objects
-  unsigned long long* bidkey = reinterpret_cast<unsigned long long*>(sb + N);        // per object: (ordered bid, ~person)
+  const int Np = (N + 1) & ~1;                                                       // objects: three coordinate planes of
+  float* bx = reinterpret_cast<float*>(sa + N);                                      // Np floats (a lane reads objects j, j + 1
+  float* by = bx + Np;                                                               // of a plane with one LDS.64)
+  float* bz = by + Np;
+  unsigned long long* bidkey = reinterpret_cast<unsigned long long*>(bz + Np);       // per object: (ordered bid, ~person)
   float* price = reinterpret_cast<float*>(bidkey + N);
   int* owner = reinterpret_cast<int*>(price + N);      // person holding object j, -1 if none
   int* mine = owner + N;                               // object held by person i, -1 if none
@@ -139,12 +171,15 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
     const float4 a = make_float4(pa[j * 3], pa[j * 3 + 1], pa[j * 3 + 2], 0.f);
     const float4 b = make_float4(pb[j * 3], pb[j * 3 + 1], pb[j * 3 + 2], 0.f);
     sa[j] = a;
-    sb[j] = b;
+    bx[j] = b.x;
+    by[j] = b.y;
+    bz[j] = b.z;
     price[j] = 0.f;
     lo[0] = fminf(lo[0], fminf(a.x, b.x)); hi[0] = fmaxf(hi[0], fmaxf(a.x, b.x));
     lo[1] = fminf(lo[1], fminf(a.y, b.y)); hi[1] = fmaxf(hi[1], fmaxf(a.y, b.y));
     lo[2] = fminf(lo[2], fminf(a.z, b.z)); hi[2] = fmaxf(hi[2], fmaxf(a.z, b.z));
   }
+  if (tid == 0 && Np != N) bx[N] = by[N] = bz[N] = 0.f;  // the pad object of an odd cloud is evaluated, never offered
   // upper bound of any distance: the diagonal of the joint bounding box
   float diag2 = 0.f;
 #pragma unroll
@@ -200,7 +235,21 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
         const int i = todo[u];
         const float4 a = sa[i];
         Best b{-FLT_MAX, -FLT_MAX, 0x7fffffff};
-        for (int j = lane; j < N; j += 32) offer(b, -(FAST_SQRT ? dist_fast(a, sb[j]) : dist(a, sb[j])) - price[j], j);
+        // lane l scans objects (2l, 2l + 1), (2l + 64, 2l + 65), ...: (b - a)^2 on packed pairs, the same bits as dist()
+        const f32x2 nax = pk2(-a.x, -a.x), nay = pk2(-a.y, -a.y), naz = pk2(-a.z, -a.z);
+#pragma unroll 2
+        for (int j = 2 * lane; j < N; j += 64) {
+          const f32x2 dx = add2(*reinterpret_cast<const f32x2*>(bx + j), nax);
+          const f32x2 dy = add2(*reinterpret_cast<const f32x2*>(by + j), nay);
+          const f32x2 dz = add2(*reinterpret_cast<const f32x2*>(bz + j), naz);
+          float d0, d1;
+          upk2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d0, d1);
+          const float2 pr = *reinterpret_cast<const float2*>(price + j);
+          d0 = FAST_SQRT ? sqrt_fast(d0) : sqrtf(d0);
+          d1 = FAST_SQRT ? sqrt_fast(d1) : sqrtf(d1);
+          offer_ascending(b, -d0 - pr.x, j);
+          if (j + 1 < N) offer_ascending(b, -d1 - pr.y, j + 1);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float ov1 = __shfl_xor_sync(0xffffffffu, b.v1, o), ov2 = __shfl_xor_sync(0xffffffffu, b.v2, o);
@@ -273,7 +322,7 @@ auction_kernel(const float* __restrict__ A, const float* __restrict__ Bp, int N,
     float acc = 0.f;
     for (int i = tid + v * THREADS; i < N; i += MAX_THREADS) {
       const int j = mine[i];
-      acc += dist(sa[i], sb[j]);
+      acc += dist(sa[i], make_float4(bx[j], by[j], bz[j], 0.f));
       if (assign_out != nullptr) assign_out[(size_t)pair * N + i] = j;
     }
     acc = warp_sum(acc);
@@ -301,7 +350,7 @@ extern "C" int nova_emd(const float* a, const float* b, int64_t B, int64_t N, fl
   NOVA_REQUIRE(N <= emd::MAX_POINTS, "nova_emd: at most %d points per cloud (got %lld)", emd::MAX_POINTS, (long long)N);
   NOVA_REQUIRE(a && b && emd_out, "nova_emd: null argument");
   NOVA_REQUIRE(eps_final > 0.f && max_rounds > 0, "nova_emd: eps_final and max_rounds must be positive");
-  const size_t smem = static_cast<size_t>(N) * (16 + 16 + 8 + 4 + 4 + 4 + 4);
+  const size_t smem = static_cast<size_t>(N) * (16 + 8 + 4 + 4 + 4 + 4) + static_cast<size_t>((N + 1) & ~1ll) * 12 + 8;
   static std::atomic<unsigned long long> attr_done{0ull};
   int dev = 0;
   NOVA_CHECK_CUDA(cudaGetDevice(&dev));
@@ -320,7 +369,7 @@ extern "C" int nova_emd(const float* a, const float* b, int64_t B, int64_t N, fl
   NOVA_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const char* env = std::getenv("NOVA_B200_EMD_THREADS");
   const int forced = env ? std::atoi(env) : 0;
-  // The approximate square root steers the bids only (dist_fast); on by default: 288 -> 227 ms at 256 pairs, the mean
+  // The approximate square root steers the bids only (sqrt_fast); on by default: 288 -> 227 ms at 256 pairs, the mean
   // matched distance moves by <= 1.2e-7 (NOVA_B200_EMD_FAST_SQRT=0 restores the correctly rounded one).
   const char* fenv = std::getenv("NOVA_B200_EMD_FAST_SQRT");
   const bool fast = fenv == nullptr || std::atoi(fenv) != 0;
