@@ -284,6 +284,74 @@ softmax_interp_kernel(const float* __restrict__ q, const float* __restrict__ t, 
   o[2] = az * inv;
 }
 
+// The same on two sources per iteration: the tile as three coordinate planes, one LDS.64 per plane puts sources (j, j + 1)
+// into 64-bit registers, the distance arithmetic runs on packed fp32 pairs ((p - t)^2, the same bits as (t - p)^2), and
+// the weights use ex2.approx on x log2(e) (<= 2 ulp + |x| 6e-8 relative: the sources that carry weight have |x| of a few
+// units) instead of the ~11-instruction expf.  The square root stays correctly rounded: its error is the one that the
+// far-from-origin case multiplies by the distance.  Sources are still visited in index order (lo, then hi).
+__device__ __forceinline__ float exp_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+__global__ void __launch_bounds__(THREADS)
+softmax_interp2_kernel(const float* __restrict__ q, const float* __restrict__ t, int64_t Nq, int64_t Nt,
+                       float* __restrict__ out) {
+  __shared__ __align__(16) float tx[TILE], ty[TILE], tz[TILE];
+  const int64_t cloud = blockIdx.y;
+  const float* qry = q + cloud * Nq * 3;
+  const float* tgt = t + cloud * Nt * 3;
+  const int64_t qi = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int64_t ql = qi < Nq ? qi : Nq - 1;
+  const float qx = qry[ql * 3 + 0], qy = qry[ql * 3 + 1], qz = qry[ql * 3 + 2];
+  const f32x2 nqx = pk2(-qx, -qx), nqy = pk2(-qy, -qy), nqz = pk2(-qz, -qz);
+  float m = 3.4e38f, s = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+  for (int64_t t0 = 0; t0 < Nt; t0 += TILE) {
+    const int cnt = static_cast<int>(Nt - t0 < TILE ? Nt - t0 : TILE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 3; i += THREADS) {  // coalesced read of the xyz stream
+      const int pt = i / 3, c = i - pt * 3;
+      (c == 0 ? tx : c == 1 ? ty : tz)[pt] = tgt[t0 * 3 + i];
+    }
+    if ((cnt & 1) && threadIdx.x == 0) tx[cnt] = ty[cnt] = tz[cnt] = 1e18f;  // pad source: weight exp(-1e18) = 0
+    __syncthreads();
+#pragma unroll 2
+    for (int j = 0; j < cnt; j += 2) {
+      const f32x2 px = *reinterpret_cast<const f32x2*>(tx + j), py = *reinterpret_cast<const f32x2*>(ty + j);
+      const f32x2 pz = *reinterpret_cast<const f32x2*>(tz + j);
+      const f32x2 dx = add2(px, nqx), dy = add2(py, nqy), dz = add2(pz, nqz);
+      float d2[2], cx[2], cy[2], cz[2];
+      upk2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d2[0], d2[1]);
+      upk2(px, cx[0], cx[1]);
+      upk2(py, cy[0], cy[1]);
+      upk2(pz, cz[0], cz[1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float d = sqrtf(d2[h]);
+        if (d < m) {  // new nearest source: rescale what has been accumulated (exp(-inf) = 0 the first time)
+          const float r = exp_fast(d - m);
+          s *= r;
+          ax *= r;
+          ay *= r;
+          az *= r;
+          m = d;
+        }
+        const float w = exp_fast(m - d);
+        s += w;
+        ax = fmaf(w, cx[h], ax);
+        ay = fmaf(w, cy[h], ay);
+        az = fmaf(w, cz[h], az);
+      }
+    }
+  }
+  if (qi >= Nq) return;
+  const float inv = 1.0f / s;
+  float* o = out + (cloud * Nq + qi) * 3;
+  o[0] = ax * inv;
+  o[1] = ay * inv;
+  o[2] = az * inv;
+}
+
 static bool knn_packed() {  // NOVA_B200_KNN_PACKED=0 keeps the scalar arithmetic for two queries per thread (A/B runs)
   const char* e = std::getenv("NOVA_B200_KNN_PACKED");
   return e == nullptr || std::atoi(e) != 0;
@@ -359,7 +427,11 @@ extern "C" int nova_softmax_interp(const float* targets, const float* points, in
   NOVA_REQUIRE(B <= 65535 && S < (1ll << 31) && N < (1ll << 31), "nova_softmax_interp: batch > 65535 or cloud too large");
   if (B == 0) return NOVA_OK;
   dim3 grid((unsigned)ceil_div(S, knn::THREADS), (unsigned)B);
-  knn::softmax_interp_kernel<<<grid, knn::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(targets, points, S, N, out);
+  const char* env = std::getenv("NOVA_B200_INTERP_FAST");  // =0: scalar arithmetic and expf (A/B runs)
+  if (env == nullptr || std::atoi(env) != 0)
+    knn::softmax_interp2_kernel<<<grid, knn::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(targets, points, S, N, out);
+  else
+    knn::softmax_interp_kernel<<<grid, knn::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(targets, points, S, N, out);
   NOVA_CHECK_LAUNCH();
   return NOVA_OK;
 }

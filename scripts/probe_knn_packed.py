@@ -33,4 +33,15 @@ for packed in ("0", "1", "0", "1"):
         "knn_k4_idx_ms": round(timed(lambda: torch.ops.nova_b200.knn(a, a, 4)), 4),
         "knn_k9_idx_ms": round(timed(lambda: torch.ops.nova_b200.knn(a, a, 9)), 4),
         "knn_k16_idx_ms": round(timed(lambda: torch.ops.nova_b200.knn(a, a, 16)), 4)})
+os.environ.pop("NOVA_B200_KNN_PACKED", None)
+idx = torch.randperm(2048, device=a.device)[:512]
+tg = a[:, idx].contiguous()
+res = {}
+for fast in ("0", "1", "0", "1"):
+    os.environ["NOVA_B200_INTERP_FAST"] = fast
+    ms = timed(lambda: torch.ops.nova_b200.softmax_interp(tg, a))
+    res[fast] = torch.ops.nova_b200.softmax_interp(tg, a).clone()
+    out.setdefault("softmax_interp_fast" + fast, []).append(round(ms, 4))
+os.environ.pop("NOVA_B200_INTERP_FAST", None)
+out["softmax_interp_max_abs_diff_fast_vs_exact"] = float((res["0"] - res["1"]).abs().max())
 print(json.dumps(out))
