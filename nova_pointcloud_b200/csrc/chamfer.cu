@@ -329,6 +329,111 @@ nn_sym2_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t
   }
 }
 
+// ---- the two-sweep kernel WITH indices on packed pairs: a 64-bit register holds one coordinate of TWO queries of the lane
+// and the tile stores every target coordinate twice ((x, x, y, y) + (z, z): one LDS.128 + one LDS.64, no register moves
+// to build the broadcast), so the six arithmetic instructions serve two pair evaluations; compare + two selects per
+// pair as before.  (t - q)^2 instead of (q - t)^2: the same bits, the same arg-min.
+__global__ void __launch_bounds__(THREADS)
+nn_idx2_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t N, int64_t M, float* __restrict__ d1,
+               float* __restrict__ d2, int32_t* __restrict__ idx1, int32_t* __restrict__ idx2) {
+  static_assert(Q % 2 == 0, "queries are taken in pairs");
+  __shared__ ulonglong2 txy[TILE];
+  __shared__ f32x2 tzz[TILE];
+  __shared__ float red_d[WARPS][QPB];
+  __shared__ int red_i[WARPS][QPB];
+
+  const int dir = blockIdx.z;
+  const int64_t cloud = blockIdx.y;
+  const float* qry = (dir == 0 ? a + cloud * N * 3 : b + cloud * M * 3);
+  const float* tgt = (dir == 0 ? b + cloud * M * 3 : a + cloud * N * 3);
+  const int64_t nq = dir == 0 ? N : M, nt = dir == 0 ? M : N;
+  float* dout = (dir == 0 ? d1 + cloud * N : d2 + cloud * M);
+  int32_t* iout = dir == 0 ? (idx1 ? idx1 + cloud * N : nullptr) : (idx2 ? idx2 + cloud * M : nullptr);
+
+  const int64_t q0 = (int64_t)blockIdx.x * QPB;
+  if (q0 >= nq) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  f32x2 nqx[Q / 2], nqy[Q / 2], nqz[Q / 2];  // (-q_2k, -q_2k+1)
+  float best[Q];
+  int bidx[Q];
+#pragma unroll
+  for (int k = 0; k < Q; k += 2) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int64_t qi = q0 + (k + h) * 32 + lane;
+      if (qi >= nq) qi = nq - 1;  // clamp: duplicates are computed and dropped at the store
+      c[h][0] = qry[qi * 3 + 0];
+      c[h][1] = qry[qi * 3 + 1];
+      c[h][2] = qry[qi * 3 + 2];
+      best[k + h] = 3.4e38f;
+      bidx[k + h] = 0;
+    }
+    nqx[k / 2] = pk2(-c[0][0], -c[1][0]);
+    nqy[k / 2] = pk2(-c[0][1], -c[1][1]);
+    nqz[k / 2] = pk2(-c[0][2], -c[1][2]);
+  }
+
+  for (int64_t t0 = 0; t0 < nt; t0 += TILE) {
+    const int cnt = static_cast<int>(nt - t0 < TILE ? nt - t0 : TILE);
+    __syncthreads();
+    float* fxy = reinterpret_cast<float*>(txy);
+    float* fz = reinterpret_cast<float*>(tzz);
+    for (int i = threadIdx.x; i < cnt * 3; i += THREADS) {  // coalesced read of cnt*3 consecutive floats
+      const int pt = i / 3, c = i - pt * 3;
+      const float v = tgt[t0 * 3 + i];
+      float* dst = c < 2 ? fxy + pt * 4 + 2 * c : fz + pt * 2;
+      dst[0] = v;
+      dst[1] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = warp; j < cnt; j += WARPS) {
+      const ulonglong2 pxy = txy[j];
+      const f32x2 pzz = tzz[j];
+      const int gj = static_cast<int>(t0) + j;
+#pragma unroll
+      for (int k = 0; k < Q; k += 2) {
+        const f32x2 dx = add2(pxy.x, nqx[k / 2]), dy = add2(pxy.y, nqy[k / 2]), dz = add2(pzz, nqz[k / 2]);
+        float d[2];
+        upk2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d[0], d[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (d[h] < best[k + h]) {  // strict: first (lowest) index wins within a warp's stride
+            best[k + h] = d[h];
+            bidx[k + h] = gj;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    red_d[warp][k * 32 + lane] = best[k];
+    red_i[warp][k * 32 + lane] = bidx[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < QPB) {
+    float m = red_d[0][threadIdx.x];
+    int mi = red_i[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+      const float v = red_d[w][threadIdx.x];
+      const int vi = red_i[w][threadIdx.x];
+      if (v < m || (v == m && vi < mi)) {  // ties -> lowest index, like argmin
+        m = v;
+        mi = vi;
+      }
+    }
+    const int64_t qi = q0 + threadIdx.x;
+    if (qi < nq) {
+      dout[qi] = sqrtf(m);
+      if (iout) iout[qi] = mi;
+    }
+  }
+}
+
 // d2 <- sqrt(d2^2) in place (the buffer holds float bit patterns written by atomicMin)
 __global__ void sqrt_inplace_kernel(float* __restrict__ d, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,7 +507,9 @@ extern "C" int nova_chamfer_nn(const float* a, const float* b, int64_t B, int64_
   if (B == 0) return NOVA_OK;
   const int64_t big = N > M ? N : M;
   dim3 grid((unsigned)ceil_div(big, chamfer::QPB), (unsigned)B, 2);
-  if (idx1 != nullptr || idx2 != nullptr)
+  if ((idx1 != nullptr || idx2 != nullptr) && chamfer_packed())
+    chamfer::nn_idx2_kernel<<<grid, chamfer::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, b, N, M, d1, d2, idx1, idx2);
+  else if (idx1 != nullptr || idx2 != nullptr)
     chamfer::nn_kernel<true><<<grid, chamfer::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, b, N, M, d1, d2, idx1,
                                                                                             idx2);
   else if (chamfer_one_sweep()) {

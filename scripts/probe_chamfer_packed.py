@@ -27,10 +27,16 @@ for pairs in (256, 32):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 50
+        e0.record()
+        for _ in range(20):
+            nb.chamfer_nn(a, b)  # with indices: two sweeps
+        e1.record()
+        torch.cuda.synchronize()
+        ms_idx = e0.elapsed_time(e1) / 20
         if ref is None:
             ref = (d1.clone(), d2.clone())
         same = bool(torch.equal(d1, ref[0]) and torch.equal(d2, ref[1]))
-        out.setdefault(f"pairs{pairs}", []).append({"packed": variant, "ms_per_call": round(ms, 4), "bit_identical_to_scalar": same,
+        out.setdefault(f"pairs{pairs}", []).append({"packed": variant, "ms_per_call": round(ms, 4), "ms_per_call_with_indices": round(ms_idx, 4), "bit_identical_to_scalar": same,
                                                     "T_directed_pair_evals_per_s": round(2.0 * pairs * 2048 * 2048 / (ms * 1e-3) / 1e12, 3)})
 os.environ.pop("NOVA_B200_CHAMFER_PACKED", None)
 # ragged shapes: N != M, sizes that are not multiples of the tile / the group of 32

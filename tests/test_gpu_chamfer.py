@@ -104,11 +104,15 @@ def test_packed_sweep_is_bit_identical_to_the_scalar_sweep(monkeypatch, B, N, M)
     a = torch.randn(B, N, 3, generator=g).cuda()
     b = torch.randn(B, M, 3, generator=g).cuda()
     out = {}
+    idx = {}
     for variant in ("0", "1", "8"):
         monkeypatch.setenv("NOVA_B200_CHAMFER_PACKED", variant)
         d1, d2, _, _ = nb.chamfer_nn(a, b, with_indices=False)
         out[variant] = (d1.clone(), d2.clone())
+        idx[variant] = [t.clone() for t in nb.chamfer_nn(a, b)]  # the indexed two-sweep kernel: scalar (0) / packed pairs
     monkeypatch.delenv("NOVA_B200_CHAMFER_PACKED")
+    for j in range(4):
+        assert torch.equal(idx["1"][j], idx["0"][j]), j  # same distances, same arg-min (ties included)
     for variant in ("1", "8"):
         assert torch.equal(out[variant][0], out["0"][0]) and torch.equal(out[variant][1], out["0"][1]), variant
     d1, d2, _, _ = nb.chamfer_nn(a, b)  # the two-sweep kernel with indices
