@@ -52,6 +52,39 @@ def test_sass_is_blackwell_native():
     assert "HMMA." not in sass.replace("UTCHMMA.", "")
 
 
+def test_metric_kernels_use_packed_fp32():
+    """The Chamfer / EMD / neighbourhood kernels do their distance arithmetic on packed fp32 pairs (FADD2 / FMUL2 / FFMA2),
+    the Chamfer sweep takes its minima three at a time (FMNMX3) and the EMD bidding loop uses MUFU.SQRT: per-kernel SASS."""
+    import re
+    import shutil
+    import subprocess
+
+    from nova_pointcloud_b200 import _lib
+
+    _lib.lib()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    bodies = {}
+    for chunk in re.split(r"\n\s*Function : ", sass)[1:]:
+        name, _, body = chunk.partition("\n")
+        bodies[name.strip()] = body
+    want = {
+        "nn_sym2_kernel": ("FADD2", "FMUL2", "FFMA2", "FMNMX3"),
+        "nn_idx2_kernel": ("FADD2", "FMUL2", "FFMA2"),
+        "auction_kernel": ("FADD2", "FMUL2", "FFMA2", "MUFU.SQRT"),
+        "softmax_interp2_kernel": ("FADD2", "FFMA2", "MUFU.EX2"),
+    }
+    for key, mnemonics in want.items():
+        hits = [body for name, body in bodies.items() if key in name]
+        assert hits, key
+        for m in mnemonics:
+            assert any(m in body for body in hits), (key, m)
+    packed_knn = [body for name, body in bodies.items() if "knn_kernel" in name and name.rstrip().endswith("Lb1EEEvPKfS3_lliPfPi")]
+    assert packed_knn and all("FFMA2" in body for body in packed_knn)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_product_fails_loudly_without_cuda():
     import nova_pointcloud_b200 as nb
